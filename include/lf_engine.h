@@ -1,0 +1,130 @@
+/*
+ * lf_engine.h -- C ABI of the B200 likelihood engine for LumFuncMCMC's hot path.
+ *
+ * One shared library (lumfuncmcmc_b200/csrc/liblfengine.so, sm_100a) exports exactly these symbols.  They are
+ * what a binding inside the reference would call in place of its NumPy arithmetic; INTEGRATION.md shows the
+ * ctypes stub.  Plain pointers and sizes only; no torch / Python types.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree):
+ *   lf_lnprob_batch            <- LumFuncMCMC.lnprob / lnprob_fix_comp   lumfuncmcmc.py:395-424
+ *                                 (= set_parameters_from_list :320-337, lnprior :339-358,
+ *                                    lnlike :360-378, lnlike_fix_comp :380-393), one row of `thetas` per call
+ *                                 of the reference; LumFuncMCMCz.lnprob   lumfuncmcmc_z.py:378-392
+ *                                 (= :332-341, :343-362, :364-376)
+ *   lf_set_sources/lf_set_grid <- the arrays those methods read from `self`, produced once by
+ *                                 setDLdVdz/setOmegaLz/setlnsimple/defineFlimOmArr  lumfuncmcmc.py:180-235, 283-288
+ *   lf_veff_bin                <- LumFuncMCMC.VeffLF lumfuncmcmc.py:515-525 -> V.lumfunc VmaxLumFunc.py:215-257
+ *                                 and the original-sample binning of V.getBootErrLog VmaxLumFunc.py:336-350
+ *   lf_boot_bin                <- one bootstrap replicate of V.getBootErrLog VmaxLumFunc.py:352-359
+ *
+ * Conventions: every function returns 0 on success, non-zero on error; the message is available from
+ * lf_last_error() (thread-local).  Numerical outcomes (-inf) are values, not errors; NaN is never returned by
+ * lf_lnprob_*.  The caller owns all host buffers; lf_set_* copy to the device and the context owns device memory
+ * until lf_destroy.  A context is single-caller (like the reference, whose lnprob mutates `self`).
+ * There is no CPU fallback: without a CUDA device lf_create fails.
+ */
+#ifndef LF_ENGINE_H
+#define LF_ENGINE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LF_MAX_FIELDS 16
+
+/* model kind: which reference likelihood the context evaluates */
+enum { LF_MODEL_FREE = 0,   /* lnlike: completeness parameters sampled   (lumfuncmcmc.py:360-378) */
+       LF_MODEL_FIXED = 1,  /* lnlike_fix_comp: tabulated Omega          (lumfuncmcmc.py:380-393) */
+       LF_MODEL_Z = 2 };    /* LumFuncMCMCz.lnlike: evolving L*, phi*    (lumfuncmcmc_z.py:364-376) */
+
+/* arithmetic of the walker x source loop */
+enum { LF_PREC_F64 = 0, LF_PREC_F32 = 1 };
+
+typedef struct lf_ctx lf_ctx;
+
+typedef struct lf_config {
+    int32_t model;           /* LF_MODEL_*                                                            */
+    int32_t precision;       /* LF_PREC_*                                                             */
+    int32_t device;          /* CUDA device ordinal                                                   */
+    int32_t nfields;         /* K <= LF_MAX_FIELDS                                                    */
+    int32_t size_ln;         /* S: quadrature grid is S x S per field (101 free / 201 fixed, z)       */
+    int32_t fix_sch_al;      /* 1: Schechter alpha is not in theta, use `sch_al` below                */
+    int32_t fixed_prior_ok;  /* 1 if the parameters NOT in theta lie inside their prior boxes: the
+                                reference's lnprior range-checks those too (lumfuncmcmc.py:347-354)   */
+    int32_t force_literal;   /* testing: 1 = evaluate every walker with the literal (reference-order)
+                                kernels instead of the fast kernels                                   */
+    double fcmin;            /* modified-Fleming threshold; 0 selects the plain curve (VmaxLumFunc.py:121) */
+    double sch_al;           /* value used when fix_sch_al                                            */
+    double Lstar_lims[2], phistar_lims[2], sch_al_lims[2], Flim_lims[2], alpha_lims[2];
+    double z_pivots[3];      /* LF_MODEL_Z: z1, z2, z3 (lumfuncmcmc_z.py:191)                         */
+} lf_config;
+
+/* theta layout (row-major, `ndim` doubles per walker), as set_parameters_from_list:
+ *   FREE : L*, phi*, [alpha_s], F50_0..F50_{K-1}, alpha_c      ndim = 2 + !fix_sch_al + K + 1
+ *   FIXED: L*, phi*, [alpha_s]                                  ndim = 2 + !fix_sch_al
+ *   Z    : L1, L2, L3, phi1, phi2, phi3, [alpha_s]              ndim = 6 + !fix_sch_al           */
+int lf_ndim(const lf_ctx* ctx);
+
+int lf_create(lf_ctx** out, const lf_config* cfg);
+void lf_destroy(lf_ctx* ctx);
+
+/* Per-source arrays (host pointers, n = field_ind[K]; sources sorted by field).
+ *   lum      log10 L_i                                      all models
+ *   flux     10^lum_i / (4 pi (3.086e24 DLf(z_i))^2)        FREE   (lumfuncmcmc.py:69-70; caller evaluates DLf once)
+ *   z        redshift                                        Z
+ *   om_arr   Om_arr_i (tabulated Omega, lumfuncmcmc.py:235)  FIXED, Z
+ *   omega0_int  per-field area truncated to integer           FREE   (dtype=int copy, lumfuncmcmc.py:285)
+ * Unused pointers may be NULL. */
+int lf_set_sources(lf_ctx* ctx, int64_t n, const double* lum, const double* flux, const double* z,
+                   const double* om_arr, const int64_t* field_ind, const int64_t* omega0_int);
+
+/* Quadrature grid (host pointers).  logL[K][S][S] (row = luminosity index, column = redshift index),
+ * zarr[S], DL_zarr[S] = DLf(zarr) in Mpc, volume_part[S], omega0[K] (float areas) for FREE;
+ * integ_part[K][S][S] for FIXED / Z (DL_zarr, volume_part, omega0 may then be NULL). */
+int lf_set_grid(lf_ctx* ctx, const double* logL, const double* zarr, const double* DL_zarr,
+                const double* volume_part, const double* integ_part, const double* omega0);
+
+/* Which walkers' quadrature term this context subtracts: walkers w with w % nshare == share.
+ * Default (0, 1) = all.  Multi-GPU source sharding: rank r calls (r, world) and the per-rank outputs are
+ * summed (all-reduce) to give lnprob. */
+int lf_set_quadrature_share(lf_ctx* ctx, int32_t share, int32_t nshare);
+
+/* Batched log-posterior, HOST buffers: thetas[W][ndim] -> out[W].  Includes H2D, kernels, D2H, sync. */
+int lf_lnprob_batch(lf_ctx* ctx, const double* thetas, int64_t W, double* out);
+
+/* Same with DEVICE buffers on a caller-provided CUDA stream (cudaStream_t as void*); asynchronous. */
+int lf_lnprob_batch_device(lf_ctx* ctx, const double* d_thetas, int64_t W, double* d_out, void* stream);
+
+/* Per-walker evaluation class of the last call: counts[0] = rejected before any source is read (prior or
+ * certain underflow), counts[1] = fast kernels, counts[2] = literal kernels.  `launches` = kernels launched. */
+int lf_last_call_info(lf_ctx* ctx, int64_t counts[3], int64_t* launches);
+
+/* 1/V_eff weights + binned LF over the original sample (host buffers).
+ *   phi_i = [zmax_i > zmin] / (sum_omega/sqarcsec * fleming(flux_i; 1e-17*flim[field(i)], alpha, fcmin) * vol_i)
+ *   vol_i = vol_int (shared) when vol_per_source == NULL, else vol_per_source[i]
+ *   counts[j], sumphi[j] over the half-open bins [edges[j], edges[j+1]) in lum.
+ * phi_out may be NULL.  The engine keeps lum/phi resident for lf_boot_bin. */
+int lf_veff_bin(lf_ctx* ctx, int64_t n, const double* flux, const double* lum, const int64_t* field_ind,
+                int32_t nfields, const double* flim, double alpha, double fcmin, double sum_omega,
+                double vol_int, const double* vol_per_source, const uint8_t* valid_or_null,
+                const double* edges, int32_t nbins, double* phi_out, int64_t* counts, double* sumphi);
+
+/* One bootstrap replicate on the resident sample: mult[i] = how many times source i was drawn.
+ * sumphi[j] = sum_i mult[i] * phi_i over bin j; counts[j] = sum_i mult[i]. */
+int lf_boot_bin(lf_ctx* ctx, const int32_t* mult, int64_t* counts, double* sumphi);
+
+/* Register-only FP64 FMA micro-benchmark on the context's device: sustained DFMA thread-instructions / s. */
+int lf_fp64_peak(lf_ctx* ctx, int32_t iters, double* dfma_per_s, double* ms);
+
+/* Device time (ms, CUDA events on the engine's stream) of the kernels of the last lf_lnprob_batch call. */
+int lf_last_kernel_ms(lf_ctx* ctx, double* ms);
+
+const char* lf_last_error(void);
+const char* lf_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LF_ENGINE_H */

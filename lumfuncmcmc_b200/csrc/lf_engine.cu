@@ -1,0 +1,1249 @@
+// lf_engine.cu -- B200 (sm_100a) likelihood engine behind include/lf_engine.h.
+//
+// Work decomposition (all three models): one THREAD per WALKER, one WARP = 32 walkers sweeping a contiguous
+// slab of sources (or quadrature points).  Source data are warp-uniform broadcast loads (every lane reads the
+// same 16 B), walker constants live in registers, so the loop is pure FP64-pipe arithmetic; there is no
+// cross-lane reduction at all -- each lane owns its walker's partial sum and writes partial[slab][walker],
+// which k_finish adds up in a fixed order (deterministic, no floating-point atomics).
+//
+// Per call: k_prologue (unpack theta, prior gate, walker constants, fast/literal classification)
+//        -> k_main<fast> + k_main<literal> (source sums and quadrature, one grid of warp work items each)
+//        -> k_finish (fixed-order reduction, sufficient statistics, -inf semantics).
+//
+// "fast" kernels use the hoisted log-space form with the lf_math.cuh routines; they are only
+// used for walkers for which the prologue PROVES that no term of the reference's product-then-log can
+// underflow or leave the validated argument ranges.  Every other walker is evaluated by the "literal" kernels,
+// which follow the reference's order of operations with IEEE/libdevice arithmetic so that -inf / denormal
+// behaviour is reproduced, not imitated (lumfuncmcmc.py:370).
+#include "../../include/lf_engine.h"
+#include "lf_math.cuh"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+using namespace lfm;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(const std::string& msg) {
+    g_err = msg;
+    return 1;
+}
+#define CK(call)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
+                        std::to_string(__LINE__) + ")");                                            \
+    } while (0)
+
+extern "C" const char* lf_last_error(void) { return g_err.c_str(); }
+extern "C" const char* lf_version(void) { return "lfengine 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// device-side data layout
+// ------------------------------------------------------------------------------------------------
+// walker-parameter slots: wp[slot * Wcap + w]
+enum {
+    P_ALPHA = 0,   // completeness slope alpha_c
+    P_TENML = 1,   // 10^-L*
+    P_C0 = 2,      // ln ln10 + phi* ln10 - L* c1
+    P_C1 = 3,      // (alpha_s + 1) ln10
+    P_LSTAR = 4,
+    P_PHISTAR = 5,
+    P_SCHAL = 6,
+    P_LNPART0 = 7,  // source-sum part that collapses to sufficient statistics (fast class)
+    // z model: quadratic coefficients
+    P_AL = 8, P_BL = 9, P_CL = 10, P_AP = 11, P_BP = 12, P_CP = 13,
+    P_FIELD0 = 16,  // + 4*k + {0: aF, 1: cinv, 2: F50 (cgs), 3: ftau}
+    P_NSLOTS = P_FIELD0 + 4 * LF_MAX_FIELDS
+};
+
+enum { CLS_NONE = 0, CLS_FAST = 1, CLS_LIT = 2 };
+
+struct FieldStats {          // per-field sufficient statistics and ranges of the resident sources
+    double n, sum_lum, sum_L, sum_lnom, sum_z, sum_z2;
+    double lum_min, lum_max, g_min, f_min, lnom_min, z_min, z_max;
+    double grid_g_min, grid_f_min;     // same ranges over the field's quadrature points (FREE)
+    double ln_om0;                      // ln(int(Omega_0)/sqarcsec)                        (FREE)
+    double om0_over_sq;                 // int(Omega_0)/sqarcsec                            (FREE)
+};
+
+struct QuadPointFree { double g, f, x, Lx, wt; };   // log10 flux, flux, logL, 10^logL, trapezoid*volume*area weight
+struct QuadPoint { double x, Lx, wt; };             // FIXED / Z (weight carries integ_part)
+
+struct KArgs {
+    int model, K, S, fix_sch_al, fixed_prior_ok, force_literal, modified;
+    int ndim;
+    double fcmin, fcA2;                // fcA2 = |a/(1-a)|, a = (2 fcmin - 1)^2        (VmaxLumFunc.py:164-165)
+    double sch_al;
+    double Lstar_lims[2], phistar_lims[2], sch_al_lims[2], Flim_lims[2], alpha_lims[2];
+    double z1, z2, z3;
+    long long field_ind[LF_MAX_FIELDS + 1];
+    FieldStats fs[LF_MAX_FIELDS];
+    double lum_max_all;
+    // resident arrays
+    const double2* src2;               // FREE: (log10 flux, flux)   Z: (lum, z)
+    const double* lum;
+    const double* flux;
+    const double* z;
+    const double* om_arr;
+    const double* zarr;                // Z: quadrature redshifts (column i <-> zarr[i])
+    const QuadPointFree* qpf;
+    const QuadPoint* qp;
+    long long N, NQ;                   // sources, quadrature points (K*S*S)
+    // per-call
+    const double* thetas;
+    double* out;
+    long long W, Wcap;
+    double* wp;
+    double* colA;                      // Z: per (column, walker) ln-amplitude  [K? no: S][Wcap]
+    double* colB;                      // Z: per (column, walker) 10^-L*(z_col)
+    int* cls_count;                    // [3]
+    int* list_fast;
+    int* list_lit;
+    double* partial;                   // [rows][Wcap]
+    int n_src_slabs, n_quad_slabs;
+    int share, nshare;
+    const Tables* tables;
+};
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
+
+__device__ __forceinline__ bool in_box(double v, const double* lims) { return (v >= lims[0]) && (v <= lims[1]); }
+__device__ __forceinline__ bool in_box_strict(double v, const double* lims) { return (v > lims[0]) && (v < lims[1]); }
+
+// literal modified-Fleming value, reference operation order (VmaxLumFunc.py:118-126, 141, 164-167)
+__device__ __forceinline__ double fleming_literal(double f, double F50, double alpha, double ftau, bool modified) {
+    double num = alpha * log10(f / F50);
+    double den = sqrt(1.0 + num * num);
+    double fc = 0.5 * (1.0 + num / den);
+    if (!modified) return fc;
+    double dec = 1.0 - exp(-f / ftau);
+    return pow(fc, 1.0 / dec);
+}
+
+// literal Schechter value (lumfuncmcmc.py:44)
+__device__ __forceinline__ double schechter_literal(double logL, double sch_al, double Lstar, double phistar) {
+    double dex = logL - Lstar;
+    return LN10 * pow(10.0, phistar) * pow(10.0, dex * (sch_al + 1.0)) * exp(-pow(10.0, dex));
+}
+
+// getQuadCoef, reference operation order (lumfuncmcmc_z.py:40-42)
+__device__ __forceinline__ void quad_coef(double y1, double y2, double y3, double z1, double z2, double z3,
+                                          double& a, double& b, double& c) {
+    a = ((y3 - y1) + (y2 - y1) * (z1 - z3) / (z2 - z1)) /
+        (z3 * z3 - z1 * z1 + (z2 * z2 - z1 * z1) * (z1 - z3) / (z2 - z1));
+    b = (y2 - y1 - a * (z2 * z2 - z1 * z1)) / (z2 - z1);
+    c = y1 - a * z1 * z1 - b * z1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prologue: one thread per walker
+// ------------------------------------------------------------------------------------------------
+// Classification thresholds: a walker takes the fast kernels only if every term of the reference's
+// product-then-log is provably >= exp(-700) (normal range, 8 above the denormal boundary) and every fast-math
+// argument stays inside its validated range.
+#define LB_SAFE (-700.0)
+#define N_MIN_SAFE (-30.0)
+#define X_MIN_SAFE (1.0e-4)
+
+__global__ void k_prologue(KArgs a) {
+    long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (w >= a.W) return;
+    const double* th = a.thetas + w * a.ndim;
+    double* wp = a.wp + w;
+    const long long WS = a.Wcap;
+    const double NINF = neg_inf();
+    int cls = CLS_FAST;
+    bool ok = a.fixed_prior_ok != 0;
+
+    if (a.model == LF_MODEL_Z) {
+        double L1 = th[0], L2 = th[1], L3 = th[2], p1 = th[3], p2 = th[4], p3 = th[5];
+        double sal = a.fix_sch_al ? a.sch_al : th[6];
+        // lumfuncmcmc_z.py:350-358: alpha inclusive (only when sampled), L and phi strict
+        if (!a.fix_sch_al) ok = ok && in_box(sal, a.sch_al_lims);
+        ok = ok && in_box_strict(L1, a.Lstar_lims) && in_box_strict(L2, a.Lstar_lims) && in_box_strict(L3, a.Lstar_lims);
+        ok = ok && in_box_strict(p1, a.phistar_lims) && in_box_strict(p2, a.phistar_lims) && in_box_strict(p3, a.phistar_lims);
+        if (!ok) { a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return; }
+        double aL, bL, cL, aP, bP, cP;
+        quad_coef(L1, L2, L3, a.z1, a.z2, a.z3, aL, bL, cL);
+        quad_coef(p1, p2, p3, a.z1, a.z2, a.z3, aP, bP, cP);
+        double c1 = (sal + 1.0) * LN10;
+        wp[P_AL * WS] = aL; wp[P_BL * WS] = bL; wp[P_CL * WS] = cL;
+        wp[P_AP * WS] = aP; wp[P_BP * WS] = bP; wp[P_CP * WS] = cP;
+        wp[P_C1 * WS] = c1; wp[P_SCHAL * WS] = sal;
+        // sufficient-statistics part of the source sum and a conservative lower bound of every term
+        double lnpart0 = 0.0, lb = 1.0e300;
+        for (int k = 0; k < a.K; ++k) {
+            const FieldStats& s = a.fs[k];
+            if (s.n == 0.0) continue;
+            // sum_i [ ln ln10 + ln10 phi*(z_i) + c1 (lum_i - L*(z_i)) + ln Om_i ]
+            double sphi = aP * s.sum_z2 + bP * s.sum_z + cP * s.n;
+            double sL = aL * s.sum_z2 + bL * s.sum_z + cL * s.n;
+            lnpart0 += s.n * LNLN10 + LN10 * sphi + c1 * (s.sum_lum - sL) + s.sum_lnom;
+            // ranges of the quadratics over [z_min, z_max]
+            double Llo = fmin(fma(fma(aL, s.z_min, bL), s.z_min, cL), fma(fma(aL, s.z_max, bL), s.z_max, cL));
+            double Lhi = fmax(fma(fma(aL, s.z_min, bL), s.z_min, cL), fma(fma(aL, s.z_max, bL), s.z_max, cL));
+            double Plo = fmin(fma(fma(aP, s.z_min, bP), s.z_min, cP), fma(fma(aP, s.z_max, bP), s.z_max, cP));
+            if (aL != 0.0) { double zv = -bL / (2.0 * aL); if (zv > s.z_min && zv < s.z_max) { double v = fma(fma(aL, zv, bL), zv, cL); Llo = fmin(Llo, v); Lhi = fmax(Lhi, v); } }
+            if (aP != 0.0) { double zv = -bP / (2.0 * aP); if (zv > s.z_min && zv < s.z_max) { double v = fma(fma(aP, zv, bP), zv, cP); Plo = fmin(Plo, v); } }
+            double dlo = s.lum_min - Lhi, dhi = s.lum_max - Llo;
+            double emax = pow(10.0, dhi);
+            double tlo = LNLN10 + LN10 * Plo + fmin(c1 * dlo, c1 * dhi) - emax + s.lnom_min;
+            lb = fmin(lb, tlo);
+            if (!(emax < 690.0)) lb = -1.0e300;
+            if (!(dlo > -40.0)) lb = -1.0e300;
+        }
+        wp[P_LNPART0 * WS] = lnpart0;
+        if (!(lb > LB_SAFE)) cls = CLS_LIT;
+        // per-column constants for the quadrature: column i <-> zarr_i
+        // (filled by k_zcolumns after classification; needs c1, coefficients only)
+    } else {
+        const int K = a.K;
+        double Lstar = th[0], phistar = th[1];
+        int p = 2;
+        double sal = a.sch_al;
+        if (!a.fix_sch_al) sal = th[p++];
+        // lumfuncmcmc.py:347-354: inclusive boxes on every parameter; parameters not in theta were checked on
+        // the host (fixed_prior_ok)
+        ok = ok && in_box(Lstar, a.Lstar_lims) && in_box(phistar, a.phistar_lims);
+        if (!a.fix_sch_al) ok = ok && in_box(sal, a.sch_al_lims);
+        double alpha_c = 0.0;
+        if (a.model == LF_MODEL_FREE) {
+            for (int k = 0; k < K; ++k) ok = ok && in_box(th[p + k], a.Flim_lims);
+            alpha_c = th[p + K];
+            ok = ok && in_box(alpha_c, a.alpha_lims);
+        }
+        if (!ok) { a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return; }
+        // certain underflow: exp(-10^(lum_max - L*)) == 0 makes Phi == 0 for the brightest source
+        if (exp(-pow(10.0, a.lum_max_all - Lstar)) == 0.0 && a.N > 0) {
+            a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return;
+        }
+        double tenmL = pow(10.0, -Lstar);
+        double c1 = (sal + 1.0) * LN10;
+        double c0 = LNLN10 + phistar * LN10 - Lstar * c1;
+        wp[P_TENML * WS] = tenmL; wp[P_C0 * WS] = c0; wp[P_C1 * WS] = c1;
+        wp[P_LSTAR * WS] = Lstar; wp[P_PHISTAR * WS] = phistar; wp[P_SCHAL * WS] = sal;
+        wp[P_ALPHA * WS] = alpha_c;
+        double lnpart0 = 0.0, lb = 1.0e300;
+        bool range_ok = true;
+        double b = 0.0;
+        if (a.model == LF_MODEL_FREE) {
+            b = -1.0 * sqrt(a.fcA2 * pow(alpha_c, -2.0));   // inverse_fleming, VmaxLumFunc.py:164-165
+            range_ok = alpha_c > 0.0;
+        }
+        for (int k = 0; k < K; ++k) {
+            const FieldStats& s = a.fs[k];
+            double tmin = 0.0, lnom = 0.0;
+            if (a.model == LF_MODEL_FREE) {
+                double F50 = 1.0e-17 * th[p + k];
+                double lgF = log10(F50);
+                double ftau = F50 * pow(10.0, b);
+                wp[(P_FIELD0 + 4 * k + 0) * WS] = -alpha_c * lgF;
+                wp[(P_FIELD0 + 4 * k + 1) * WS] = -1.0 / ftau;
+                wp[(P_FIELD0 + 4 * k + 2) * WS] = F50;
+                wp[(P_FIELD0 + 4 * k + 3) * WS] = ftau;
+                // faintest flux the fast math will see in this field: sources and quadrature points
+                double gmin = fmin(s.n > 0.0 ? s.g_min : 1.0e300, s.grid_g_min);
+                double fmn = fmin(s.n > 0.0 ? s.f_min : 1.0e300, s.grid_f_min);
+                if (!(alpha_c * (gmin - lgF) > N_MIN_SAFE)) range_ok = false;
+                if (a.modified && !(fmn / ftau > X_MIN_SAFE)) range_ok = false;
+                if (s.n > 0.0) tmin = log(fleming_literal(s.f_min, F50, alpha_c, ftau, a.modified != 0));
+                lnom = s.ln_om0;
+            }
+            if (s.n == 0.0) continue;
+            // Schechter exponent S(l) = c0 + c1 l - 10^(l - L*) is concave in l: minimum at an end of the range
+            double s_lo = fmin(c0 + c1 * s.lum_min - pow(10.0, s.lum_min - Lstar),
+                               c0 + c1 * s.lum_max - pow(10.0, s.lum_max - Lstar));
+            if (a.model == LF_MODEL_FREE) {
+                lb = fmin(lb, s_lo + lnom + tmin);
+                lnpart0 += s.n * (c0 + lnom) + c1 * s.sum_lum - tenmL * s.sum_L;
+            } else {
+                lb = fmin(lb, s_lo + s.lnom_min);
+                lnpart0 += s.n * c0 + c1 * s.sum_lum - tenmL * s.sum_L + s.sum_lnom;
+            }
+        }
+        wp[P_LNPART0 * WS] = lnpart0;
+        if (!range_ok || !(lb > LB_SAFE)) cls = CLS_LIT;
+    }
+    if (a.force_literal) cls = CLS_LIT;
+    int pos = atomicAdd(&a.cls_count[cls], 1);
+    (cls == CLS_FAST ? a.list_fast : a.list_lit)[pos] = (int)w;
+}
+
+// Z model: per (column i, walker) constants of the quadrature integrand
+//   colA = ln ln10 + ln10 phi*(z_i) - c1 L*(z_i),   colB = 10^-L*(z_i)
+__global__ void k_zcolumns(KArgs a) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const int nf = a.cls_count[CLS_FAST];
+    if (idx >= (long long)a.S * nf) return;
+    int i = (int)(idx / nf);
+    long long w = a.list_fast[idx % nf];
+    const long long WS = a.Wcap;
+    const double* wp = a.wp + w;
+    double z = a.zarr[i];
+    double Ls = wp[P_AL * WS] * z * z + wp[P_BL * WS] * z + wp[P_CL * WS];     // lumfuncmcmc_z.py:65-66 order
+    double Ps = wp[P_AP * WS] * z * z + wp[P_BP * WS] * z + wp[P_CP * WS];
+    double c1 = wp[P_C1 * WS];
+    a.colA[(long long)i * WS + w] = LNLN10 + LN10 * Ps - c1 * Ls;
+    a.colB[(long long)i * WS + w] = pow(10.0, -Ls);
+}
+
+// ------------------------------------------------------------------------------------------------
+// main kernels: grid of warp work items = (walker group of 32) x (slab of sources | slab of quadrature points)
+// ------------------------------------------------------------------------------------------------
+#define WARPS_PER_BLOCK 8
+#define BLOCK_THREADS (32 * WARPS_PER_BLOCK)
+
+__device__ __forceinline__ int field_of(const KArgs& a, long long i) {
+    int k = 0;
+    while (k + 1 < a.K && i >= a.field_ind[k + 1]) ++k;
+    return k;
+}
+
+template <bool LITERAL>
+__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_main(KArgs a) {
+    __shared__ double s_exp[EXP_TAB_N * EXP_TAB_REP];
+    __shared__ double2 s_log[LOG_TAB_N * LOG_TAB_REP];
+    const int cls = LITERAL ? CLS_LIT : CLS_FAST;
+    const int count = a.cls_count[cls];
+    const int n_wg = (count + 31) >> 5;
+    if (n_wg == 0) return;
+    const int rows = a.n_src_slabs + a.n_quad_slabs;
+    const long long n_items = (long long)n_wg * rows;
+    if ((long long)blockIdx.x * WARPS_PER_BLOCK >= n_items) return;
+    if (!LITERAL) {
+        load_tables(a.tables, s_exp, s_log);
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long item = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
+    if (item >= n_items) return;
+    const int wg = (int)(item % n_wg);
+    const int row = (int)(item / n_wg);
+    const int slot = wg * 32 + lane;
+    const bool active = slot < count;
+    const int* list = LITERAL ? a.list_lit : a.list_fast;
+    const long long w = list[active ? slot : count - 1];       // inactive lanes shadow a valid walker
+    const long long WS = a.Wcap;
+    const double* wp = a.wp + w;
+    const int rep16 = lane & 15, rep8 = lane & 7;
+    double acc0 = 0.0, acc1 = 0.0;
+
+    if (row < a.n_src_slabs) {
+        // ---------------- source slab ----------------
+        long long i0 = (a.N * row) / a.n_src_slabs, i1 = (a.N * (row + 1)) / a.n_src_slabs;
+        if (a.model == LF_MODEL_FREE) {
+            const double alpha = wp[P_ALPHA * WS];
+            int k = field_of(a, i0);
+            while (i0 < i1) {
+                long long seg_end = a.field_ind[k + 1] < i1 ? a.field_ind[k + 1] : i1;
+                if (!LITERAL) {
+                    const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], cinv = wp[(P_FIELD0 + 4 * k + 1) * WS];
+                    long long i = i0;
+                    if (a.modified) {
+                        for (; i + 1 < seg_end; i += 2) {
+                            double2 s0 = __ldg(&a.src2[i]), s1 = __ldg(&a.src2[i + 1]);
+                            double lg0, rd0, lg1, rd1;
+                            fleming_log_parts<true>(s0.x, s0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            fleming_log_parts<true>(s1.x, s1.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg1, rd1);
+                            acc0 = fma(lg0, rd0, acc0);
+                            acc1 = fma(lg1, rd1, acc1);
+                        }
+                        if (i < seg_end) {
+                            double2 s0 = __ldg(&a.src2[i]);
+                            double lg0, rd0;
+                            fleming_log_parts<true>(s0.x, s0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            acc0 = fma(lg0, rd0, acc0);
+                        }
+                    } else {
+                        for (; i < seg_end; ++i) {
+                            double2 s0 = __ldg(&a.src2[i]);
+                            double lg0, rd0;
+                            fleming_log_parts<false>(s0.x, s0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            acc0 += lg0;
+                        }
+                    }
+                } else {
+                    // reference order: log( Phi_i * (int(Omega_0)/sqarcsec * fleming(f_i)) )  (lumfuncmcmc.py:370)
+                    const double F50 = wp[(P_FIELD0 + 4 * k + 2) * WS], ftau = wp[(P_FIELD0 + 4 * k + 3) * WS];
+                    const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
+                    const double om = a.fs[k].om0_over_sq;
+                    for (long long i = i0; i < seg_end; ++i) {
+                        double phi = schechter_literal(__ldg(&a.lum[i]), sal, Lstar, phistar);
+                        double Om = om * fleming_literal(__ldg(&a.flux[i]), F50, alpha, ftau, a.modified != 0);
+                        acc0 += log(phi * Om);
+                    }
+                }
+                i0 = seg_end;
+                ++k;
+            }
+        } else if (a.model == LF_MODEL_FIXED) {
+            // fast class: the whole source sum is in P_LNPART0 (sufficient statistics); literal class sums terms
+            if (LITERAL) {
+                const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
+                for (long long i = i0; i < i1; ++i)                                   // lumfuncmcmc.py:388
+                    acc0 += log(schechter_literal(__ldg(&a.lum[i]), sal, Lstar, phistar) * __ldg(&a.om_arr[i]));
+            }
+        } else {
+            const double aL = wp[P_AL * WS], bL = wp[P_BL * WS], cL = wp[P_CL * WS];
+            if (!LITERAL) {
+                // only sum_i 10^(lum_i - L*(z_i)) needs the walker x source loop; the rest is in P_LNPART0
+                long long i = i0;
+                for (; i + 1 < i1; i += 2) {
+                    double2 s0 = __ldg(&a.src2[i]), s1 = __ldg(&a.src2[i + 1]);
+                    double d0 = s0.x - fma(fma(aL, s0.y, bL), s0.y, cL);
+                    double d1 = s1.x - fma(fma(aL, s1.y, bL), s1.y, cL);
+                    acc0 -= exp_full(d0 * LN10, s_exp, rep16);
+                    acc1 -= exp_full(d1 * LN10, s_exp, rep16);
+                }
+                if (i < i1) {
+                    double2 s0 = __ldg(&a.src2[i]);
+                    double d0 = s0.x - fma(fma(aL, s0.y, bL), s0.y, cL);
+                    acc0 -= exp_full(d0 * LN10, s_exp, rep16);
+                }
+            } else {
+                const double aP = wp[P_AP * WS], bP = wp[P_BP * WS], cP = wp[P_CP * WS], sal = wp[P_SCHAL * WS];
+                for (long long i = i0; i < i1; ++i) {                                 // lumfuncmcmc_z.py:371
+                    double z = __ldg(&a.z[i]);
+                    double ps = aP * z * z + bP * z + cP, Ls = aL * z * z + bL * z + cL;
+                    acc0 += log(schechter_literal(__ldg(&a.lum[i]), sal, Ls, ps) * __ldg(&a.om_arr[i]));
+                }
+            }
+        }
+    } else {
+        // ---------------- quadrature slab: contributes the integral (k_finish subtracts it) ----------------
+        if (a.nshare > 1 && (w % a.nshare) != a.share) {
+            // another rank integrates this walker
+        } else {
+            const int qrow = row - a.n_src_slabs;
+            long long q0 = (a.NQ * qrow) / a.n_quad_slabs, q1 = (a.NQ * (qrow + 1)) / a.n_quad_slabs;
+            const long long SS = (long long)a.S * a.S;
+            if (a.model == LF_MODEL_FREE) {
+                const double alpha = wp[P_ALPHA * WS];
+                const double c0 = wp[P_C0 * WS], c1 = wp[P_C1 * WS], tenmL = wp[P_TENML * WS];
+                const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
+                while (q0 < q1) {
+                    int k = (int)(q0 / SS);
+                    long long seg_end = (k + 1) * SS < q1 ? (k + 1) * SS : q1;
+                    if (!LITERAL) {
+                        const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], cinv = wp[(P_FIELD0 + 4 * k + 1) * WS];
+                        for (long long q = q0; q < seg_end; ++q) {
+                            const QuadPointFree* pt = &a.qpf[q];
+                            double2 gf = __ldg(reinterpret_cast<const double2*>(pt));
+                            double2 xl = __ldg(reinterpret_cast<const double2*>(pt) + 1);
+                            double wt = __ldg(&pt->wt);
+                            double lg, rd;
+                            if (a.modified) fleming_log_parts<true>(gf.x, gf.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg, rd);
+                            else fleming_log_parts<false>(gf.x, gf.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg, rd);
+                            double arg = fma(c1, xl.x, c0);
+                            arg = fma(-xl.y, tenmL, arg);
+                            arg = fma(lg, rd, arg);
+                            acc0 = fma(wt, exp_full(arg, s_exp, rep16), acc0);
+                        }
+                    } else {
+                        const double F50 = wp[(P_FIELD0 + 4 * k + 2) * WS], ftau = wp[(P_FIELD0 + 4 * k + 3) * WS];
+                        for (long long q = q0; q < seg_end; ++q) {                    // lumfuncmcmc.py:375-376
+                            const QuadPointFree* pt = &a.qpf[q];
+                            double y = schechter_literal(__ldg(&pt->x), sal, Lstar, phistar) *
+                                       fleming_literal(__ldg(&pt->f), F50, alpha, ftau, a.modified != 0);
+                            acc0 = fma(__ldg(&pt->wt), y, acc0);
+                        }
+                    }
+                    q0 = seg_end;
+                }
+            } else if (a.model == LF_MODEL_FIXED) {
+                const double c0 = wp[P_C0 * WS], c1 = wp[P_C1 * WS], tenmL = wp[P_TENML * WS];
+                const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
+                for (long long q = q0; q < q1; ++q) {
+                    const QuadPoint* pt = &a.qp[q];
+                    if (!LITERAL) {
+                        double arg = fma(c1, __ldg(&pt->x), c0);
+                        arg = fma(-__ldg(&pt->Lx), tenmL, arg);
+                        acc0 = fma(__ldg(&pt->wt), exp_full(arg, s_exp, rep16), acc0);
+                    } else {                                                          // lumfuncmcmc.py:391
+                        acc0 = fma(__ldg(&pt->wt), schechter_literal(__ldg(&pt->x), sal, Lstar, phistar), acc0);
+                    }
+                }
+            } else {
+                // Z: points are stored column-major: q = (k*S + i)*S + j  (column i <-> zarr_i)
+                const double c1 = wp[P_C1 * WS], sal = wp[P_SCHAL * WS];
+                const double aL = wp[P_AL * WS], bL = wp[P_BL * WS], cL = wp[P_CL * WS];
+                const double aP = wp[P_AP * WS], bP = wp[P_BP * WS], cP = wp[P_CP * WS];
+                while (q0 < q1) {
+                    long long col = q0 / a.S;                    // global column index k*S + i
+                    int i = (int)(col % a.S);
+                    long long seg_end = (col + 1) * a.S < q1 ? (col + 1) * a.S : q1;
+                    if (!LITERAL) {
+                        const double cA = a.colA[(long long)i * WS + w], cB = a.colB[(long long)i * WS + w];
+                        for (long long q = q0; q < seg_end; ++q) {
+                            const QuadPoint* pt = &a.qp[q];
+                            double arg = fma(c1, __ldg(&pt->x), cA);
+                            arg = fma(-__ldg(&pt->Lx), cB, arg);
+                            acc0 = fma(__ldg(&pt->wt), exp_full(arg, s_exp, rep16), acc0);
+                        }
+                    } else {
+                        double z = __ldg(&a.zarr[i]);
+                        double ps = aP * z * z + bP * z + cP, Ls = aL * z * z + bL * z + cL;
+                        for (long long q = q0; q < seg_end; ++q) {                    // lumfuncmcmc_z.py:374
+                            const QuadPoint* pt = &a.qp[q];
+                            acc0 = fma(__ldg(&pt->wt), schechter_literal(__ldg(&pt->x), sal, Ls, ps), acc0);
+                        }
+                    }
+                    q0 = seg_end;
+                }
+            }
+        }
+    }
+    if (active) a.partial[(long long)row * WS + w] = acc0 + acc1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// finish: fixed-order reduction over slabs; lnprob = lnpart - fullint
+// ------------------------------------------------------------------------------------------------
+__global__ void k_finish(KArgs a) {
+    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    int nf = a.cls_count[CLS_FAST], nl = a.cls_count[CLS_LIT];
+    if (idx >= nf + nl) return;
+    bool fast = idx < nf;
+    long long w = fast ? a.list_fast[idx] : a.list_lit[idx - nf];
+    const long long WS = a.Wcap;
+    double lnpart = 0.0, fullint = 0.0;
+    for (int r = 0; r < a.n_src_slabs; ++r) lnpart += a.partial[(long long)r * WS + w];
+    for (int r = a.n_src_slabs; r < a.n_src_slabs + a.n_quad_slabs; ++r) fullint += a.partial[(long long)r * WS + w];
+    if (fast) lnpart += a.wp[P_LNPART0 * WS + w];
+    if (a.nshare > 1 && (w % a.nshare) != a.share) fullint = 0.0;
+    double v = lnpart - fullint;
+    if (v != v) v = neg_inf();            // the engine never returns NaN
+    a.out[w] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// set-up kernels: derived per-source arrays and per-field statistics
+// ------------------------------------------------------------------------------------------------
+__global__ void k_derive_free(long long n, const double* __restrict__ lum, const double* __restrict__ flux,
+                              double2* __restrict__ src2, double* __restrict__ Lsrc) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double f = flux[i];
+    src2[i] = make_double2(log10(f), f);
+    Lsrc[i] = pow(10.0, lum[i]);
+}
+__global__ void k_derive_z(long long n, const double* __restrict__ lum, const double* __restrict__ z,
+                           double2* __restrict__ src2) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    src2[i] = make_double2(lum[i], z[i]);
+}
+__global__ void k_pow10(long long n, const double* __restrict__ lum, double* __restrict__ Lsrc) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Lsrc[i] = pow(10.0, lum[i]);
+}
+__global__ void k_log(long long n, const double* __restrict__ x, double* __restrict__ y) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    y[i] = log(x[i]);
+}
+
+// block partials of (sum, min, max) over a range; host adds the partials in long double
+#define STAT_THREADS 256
+__global__ void k_stats(const double* __restrict__ x, long long i0, long long i1, double* __restrict__ out3) {
+    __shared__ double ss[STAT_THREADS], smin[STAT_THREADS], smax[STAT_THREADS];
+    double s = 0.0, c = 0.0, mn = 1.0e300, mx = -1.0e300;
+    for (long long i = i0 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < i1; i += (long long)gridDim.x * blockDim.x) {
+        double v = x[i];
+        double y = v - c, t = s + y;           // Kahan
+        c = (t - s) - y;
+        s = t;
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+    ss[threadIdx.x] = s; smin[threadIdx.x] = mn; smax[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = STAT_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            ss[threadIdx.x] += ss[threadIdx.x + o];
+            smin[threadIdx.x] = fmin(smin[threadIdx.x], smin[threadIdx.x + o]);
+            smax[threadIdx.x] = fmax(smax[threadIdx.x], smax[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out3[blockIdx.x * 3 + 0] = ss[0]; out3[blockIdx.x * 3 + 1] = smin[0]; out3[blockIdx.x * 3 + 2] = smax[0]; }
+}
+__global__ void k_square(long long n, const double* __restrict__ x, double* __restrict__ y) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = x[i] * x[i];
+}
+__global__ void k_take(long long n, const double2* __restrict__ s, int comp, double* __restrict__ y) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) y[i] = comp ? s[i].y : s[i].x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1/V_eff weights + binned luminosity function  (HBM-bound streaming pass)
+// ------------------------------------------------------------------------------------------------
+#define VEFF_MAX_BINS 1024
+struct VeffArgs {
+    long long n;
+    const double* flux; const double* lum; const double* vol; const unsigned char* valid;
+    double* phi;
+    int K; long long field_ind[LF_MAX_FIELDS + 1]; double F50[LF_MAX_FIELDS]; double ftau[LF_MAX_FIELDS];
+    double alpha, pref, vol_int; int modified;
+    const double* edges; int nbins;
+    unsigned long long* counts; double* sumphi;     // [gridDim.x][nbins] block partials
+    const int* mult;                                 // bootstrap multiplicities (NULL: original sample)
+};
+
+__device__ __forceinline__ int bin_of(double L, const double* e, int nb) {
+    // half-open bins [e_j, e_{j+1}), exact comparisons against the caller's edges (VmaxLumFunc.py:346-348)
+    if (!(L >= e[0]) || !(L < e[nb])) return -1;
+    int j = (int)((L - e[0]) / (e[nb] - e[0]) * nb);
+    j = j < 0 ? 0 : (j > nb - 1 ? nb - 1 : j);
+    while (j > 0 && L < e[j]) --j;
+    while (j < nb - 1 && L >= e[j + 1]) ++j;
+    return j;
+}
+
+template <bool BOOT>
+__global__ void __launch_bounds__(256) k_veff(VeffArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    double* s_edges = reinterpret_cast<double*>(smem_raw);                 // nbins+1
+    double* s_sum = s_edges + (a.nbins + 1);                               // 8 warps x nbins
+    unsigned long long* s_cnt = reinterpret_cast<unsigned long long*>(s_sum + 8 * a.nbins);
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i <= a.nbins; i += blockDim.x) s_edges[i] = a.edges[i];
+    for (int i = threadIdx.x; i < 8 * a.nbins; i += blockDim.x) { s_sum[i] = 0.0; s_cnt[i] = 0ULL; }
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        double phi;
+        unsigned long long m = 1ULL;
+        if (BOOT) {
+            m = (unsigned long long)a.mult[i];
+            if (m == 0ULL) continue;
+            phi = a.phi[i];
+        } else {
+            int k = 0;
+            while (k + 1 < a.K && i >= a.field_ind[k + 1]) ++k;
+            double comp = fleming_literal(a.flux[i], a.F50[k], a.alpha, a.ftau[k], a.modified != 0);
+            double vol = a.vol ? a.vol[i] : a.vol_int;
+            bool ok = a.valid ? (a.valid[i] != 0) : true;
+            phi = ok ? 1.0 / (a.pref * comp * vol) : 0.0;       // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
+            a.phi[i] = phi;
+        }
+        int j = bin_of(a.lum[i], s_edges, a.nbins);
+        if (j >= 0) {
+            atomicAdd(&s_sum[warp * a.nbins + j], BOOT ? phi * (double)m : phi);
+            atomicAdd(&s_cnt[warp * a.nbins + j], m);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < a.nbins; j += blockDim.x) {
+        double s = 0.0; unsigned long long c = 0ULL;
+        for (int wv = 0; wv < 8; ++wv) { s += s_sum[wv * a.nbins + j]; c += s_cnt[wv * a.nbins + j]; }
+        a.sumphi[(long long)blockIdx.x * a.nbins + j] = s;
+        a.counts[(long long)blockIdx.x * a.nbins + j] = c;
+    }
+}
+
+__global__ void k_veff_reduce(int nblocks, int nbins, const unsigned long long* __restrict__ counts,
+                              const double* __restrict__ sumphi, long long* __restrict__ out_c, double* __restrict__ out_s) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nbins) return;
+    double s = 0.0; unsigned long long c = 0ULL;
+    for (int b = 0; b < nblocks; ++b) { s += sumphi[(long long)b * nbins + j]; c += counts[(long long)b * nbins + j]; }
+    out_c[j] = (long long)c;
+    out_s[j] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 pipe micro-benchmark: 8 independent FMA chains per thread, registers only
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double* sink) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1.0e-9;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+            a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+        }
+    }
+    double s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678) sink[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct lf_ctx {
+    lf_config cfg;
+    int device = 0, sm_count = 148;
+    int ndim = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    KArgs ka;
+    // resident
+    long long N = 0, NQ = 0;
+    double* d_lum = nullptr; double* d_flux = nullptr; double* d_z = nullptr; double* d_om = nullptr;
+    double* d_Lsrc = nullptr; double2* d_src2 = nullptr;
+    QuadPointFree* d_qpf = nullptr; QuadPoint* d_qp = nullptr; double* d_zarr = nullptr;
+    Tables* d_tables = nullptr;
+    bool have_sources = false, have_grid = false;
+    // per-call scratch (grown on demand)
+    long long Wcap = 0; int rows_cap = 0;
+    double* d_wp = nullptr; double* d_colA = nullptr; double* d_colB = nullptr; double* d_partial = nullptr;
+    int* d_cls = nullptr; int* d_list_fast = nullptr; int* d_list_lit = nullptr;
+    double* d_thetas = nullptr; double* d_out = nullptr;
+    double* h_thetas = nullptr; double* h_out = nullptr;           // pinned staging
+    long long launches = 0; double last_ms = 0.0;
+    int h_cls[3] = {0, 0, 0};
+    // Veff residency
+    long long vN = 0; double* v_lum = nullptr; double* v_phi = nullptr; double* v_edges = nullptr; int v_nbins = 0;
+    unsigned long long* v_counts = nullptr; double* v_sums = nullptr; long long* v_outc = nullptr; double* v_outs = nullptr;
+    int* v_mult = nullptr; int v_blocks = 0;
+};
+
+static int ndim_of(const lf_config& c) {
+    int free_al = c.fix_sch_al ? 0 : 1;
+    if (c.model == LF_MODEL_FREE) return 2 + free_al + c.nfields + 1;
+    if (c.model == LF_MODEL_FIXED) return 2 + free_al;
+    return 6 + free_al;
+}
+
+extern "C" int lf_ndim(const lf_ctx* ctx) { return ctx ? ctx->ndim : -1; }
+
+static void fill_tables(Tables& t) {
+    for (int j = 0; j < EXP_TAB_N; ++j) t.exp2_frac[j] = (double)exp2l((long double)j / EXP_TAB_N);
+    for (int j = 0; j < LOG_TAB_N; ++j) {
+        long double c = 1.0L + ((long double)j + 0.5L) / LOG_TAB_N;
+        double invc = (double)(1.0L / c);
+        t.log_tab[j].x = invc;
+        t.log_tab[j].y = (double)(-logl((long double)invc));
+    }
+}
+
+extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
+    if (!out || !cfg) return fail("lf_create: null argument");
+    if (cfg->nfields < 1 || cfg->nfields > LF_MAX_FIELDS) return fail("lf_create: nfields out of range");
+    if (cfg->model < 0 || cfg->model > 2) return fail("lf_create: unknown model");
+    if (cfg->precision != LF_PREC_F64) return fail("lf_create: only LF_PREC_F64 is implemented");
+    if (cfg->size_ln < 2) return fail("lf_create: size_ln must be >= 2");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(std::string("lf_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail("lf_create: bad device ordinal");
+    CK(cudaSetDevice(cfg->device));
+    lf_ctx* c = new lf_ctx();
+    c->cfg = *cfg;
+    c->device = cfg->device;
+    c->ndim = ndim_of(*cfg);
+    CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev0));
+    CK(cudaEventCreate(&c->ev1));
+    Tables t;
+    fill_tables(t);
+    CK(cudaMalloc(&c->d_tables, sizeof(Tables)));
+    CK(cudaMemcpy(c->d_tables, &t, sizeof(Tables), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&c->d_cls, 4 * sizeof(int)));
+    memset(&c->ka, 0, sizeof(KArgs));
+    KArgs& a = c->ka;
+    a.model = cfg->model; a.K = cfg->nfields; a.S = cfg->size_ln; a.fix_sch_al = cfg->fix_sch_al;
+    a.fixed_prior_ok = cfg->fixed_prior_ok; a.force_literal = cfg->force_literal;
+    a.modified = (cfg->fcmin != 0.0) ? 1 : 0;
+    a.ndim = c->ndim; a.fcmin = cfg->fcmin;
+    {
+        double aa = (2.0 * cfg->fcmin - 1.0) * (2.0 * cfg->fcmin - 1.0);
+        a.fcA2 = fabs(aa / (1.0 - aa));
+    }
+    a.sch_al = cfg->sch_al;
+    for (int i = 0; i < 2; ++i) {
+        a.Lstar_lims[i] = cfg->Lstar_lims[i]; a.phistar_lims[i] = cfg->phistar_lims[i];
+        a.sch_al_lims[i] = cfg->sch_al_lims[i]; a.Flim_lims[i] = cfg->Flim_lims[i]; a.alpha_lims[i] = cfg->alpha_lims[i];
+    }
+    a.z1 = cfg->z_pivots[0]; a.z2 = cfg->z_pivots[1]; a.z3 = cfg->z_pivots[2];
+    a.share = 0; a.nshare = 1;
+    a.tables = c->d_tables;
+    *out = c;
+    return 0;
+}
+
+template <typename T>
+static void dfree(T*& p) {
+    if (p) cudaFree(p);
+    p = nullptr;
+}
+
+extern "C" void lf_destroy(lf_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    dfree(c->d_lum); dfree(c->d_flux); dfree(c->d_z); dfree(c->d_om); dfree(c->d_Lsrc); dfree(c->d_src2);
+    dfree(c->d_qpf); dfree(c->d_qp); dfree(c->d_zarr); dfree(c->d_tables);
+    dfree(c->d_wp); dfree(c->d_colA); dfree(c->d_colB); dfree(c->d_partial);
+    dfree(c->d_cls); dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_thetas); dfree(c->d_out);
+    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
+    dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult);
+    if (c->h_thetas) cudaFreeHost(c->h_thetas);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// sum / min / max of a device range, deterministic
+static int range_stats(lf_ctx* c, const double* d_x, long long i0, long long i1, double* d_tmp, std::vector<double>& h_tmp,
+                       double& sum, double& mn, double& mx) {
+    sum = 0.0; mn = 1.0e300; mx = -1.0e300;
+    if (i1 <= i0) return 0;
+    int nb = (int)std::min<long long>(1024, (i1 - i0 + STAT_THREADS - 1) / STAT_THREADS);
+    k_stats<<<nb, STAT_THREADS, 0, c->stream>>>(d_x, i0, i1, d_tmp);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_tmp.data(), d_tmp, sizeof(double) * 3 * nb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    long double s = 0.0L;
+    for (int b = 0; b < nb; ++b) {
+        s += h_tmp[3 * b];
+        mn = std::min(mn, h_tmp[3 * b + 1]);
+        mx = std::max(mx, h_tmp[3 * b + 2]);
+    }
+    sum = (double)s;
+    return 0;
+}
+
+extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const double* flux, const double* z,
+                              const double* om_arr, const int64_t* field_ind, const int64_t* omega0_int) {
+    if (!c) return fail("lf_set_sources: null context");
+    if (n < 0 || !field_ind) return fail("lf_set_sources: bad arguments");
+    const int K = c->cfg.nfields, model = c->cfg.model;
+    if (field_ind[0] != 0 || field_ind[K] != n) return fail("lf_set_sources: field_ind must run from 0 to n");
+    for (int k = 0; k < K; ++k)
+        if (field_ind[k + 1] < field_ind[k]) return fail("lf_set_sources: field_ind must be non-decreasing");
+    if (n > 0 && !lum) return fail("lf_set_sources: lum is required");
+    if (model == LF_MODEL_FREE && n > 0 && (!flux || !omega0_int)) return fail("lf_set_sources: FREE model needs flux and omega0_int");
+    if (model != LF_MODEL_FREE && n > 0 && !om_arr) return fail("lf_set_sources: FIXED/Z models need om_arr");
+    if (model == LF_MODEL_Z && n > 0 && !z) return fail("lf_set_sources: Z model needs z");
+    CK(cudaSetDevice(c->device));
+    dfree(c->d_lum); dfree(c->d_flux); dfree(c->d_z); dfree(c->d_om); dfree(c->d_Lsrc); dfree(c->d_src2);
+    c->N = n;
+    KArgs& a = c->ka;
+    a.N = n;
+    for (int k = 0; k <= K; ++k) a.field_ind[k] = field_ind[k];
+    for (int k = 0; k < K; ++k) {
+        FieldStats& s = a.fs[k];
+        double gq = s.grid_g_min, fq = s.grid_f_min;            // keep grid ranges if the grid came first
+        memset(&s, 0, sizeof(FieldStats));
+        s.grid_g_min = c->have_grid ? gq : 1.0e300;
+        s.grid_f_min = c->have_grid ? fq : 1.0e300;
+        s.n = (double)(field_ind[k + 1] - field_ind[k]);
+        if (model == LF_MODEL_FREE && omega0_int) {
+            s.om0_over_sq = (double)omega0_int[k] / SQARCSEC;
+            s.ln_om0 = log(s.om0_over_sq);
+        }
+    }
+    a.lum_max_all = -1.0e300;
+    const size_t nb = sizeof(double) * (size_t)std::max<long long>(n, 1);
+    CK(cudaMalloc(&c->d_lum, nb));
+    CK(cudaMalloc(&c->d_Lsrc, nb));
+    double* d_tmp = nullptr; double* d_scratch = nullptr;
+    CK(cudaMalloc(&d_tmp, sizeof(double) * 3 * 1024));
+    CK(cudaMalloc(&d_scratch, nb));
+    std::vector<double> h_tmp(3 * 1024);
+    const int T = 256;
+    const unsigned G = (unsigned)((n + T - 1) / T);
+    if (n > 0) {
+        CK(cudaMemcpyAsync(c->d_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+        if (model == LF_MODEL_FREE) {
+            CK(cudaMalloc(&c->d_flux, nb));
+            CK(cudaMalloc(&c->d_src2, sizeof(double2) * (size_t)n));
+            CK(cudaMemcpyAsync(c->d_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
+            k_derive_free<<<G, T, 0, c->stream>>>(n, c->d_lum, c->d_flux, c->d_src2, c->d_Lsrc);
+        } else {
+            CK(cudaMalloc(&c->d_om, nb));
+            CK(cudaMemcpyAsync(c->d_om, om_arr, nb, cudaMemcpyHostToDevice, c->stream));
+            k_pow10<<<G, T, 0, c->stream>>>(n, c->d_lum, c->d_Lsrc);
+            if (model == LF_MODEL_Z) {
+                CK(cudaMalloc(&c->d_z, nb));
+                CK(cudaMalloc(&c->d_src2, sizeof(double2) * (size_t)n));
+                CK(cudaMemcpyAsync(c->d_z, z, nb, cudaMemcpyHostToDevice, c->stream));
+                k_derive_z<<<G, T, 0, c->stream>>>(n, c->d_lum, c->d_z, c->d_src2);
+            }
+        }
+        CK(cudaGetLastError());
+        for (int k = 0; k < K; ++k) {
+            FieldStats& s = a.fs[k];
+            long long i0 = field_ind[k], i1 = field_ind[k + 1];
+            if (i1 <= i0) continue;
+            double sm, mn, mx;
+            if (range_stats(c, c->d_lum, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
+            s.sum_lum = sm; s.lum_min = mn; s.lum_max = mx;
+            a.lum_max_all = std::max(a.lum_max_all, mx);
+            if (range_stats(c, c->d_Lsrc, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
+            s.sum_L = sm;
+            if (model == LF_MODEL_FREE) {
+                k_take<<<G, T, 0, c->stream>>>(n, c->d_src2, 0, d_scratch);
+                if (range_stats(c, d_scratch, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
+                s.g_min = mn;
+                if (range_stats(c, c->d_flux, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
+                s.f_min = mn;
+            } else {
+                k_log<<<G, T, 0, c->stream>>>(n, c->d_om, d_scratch);
+                if (range_stats(c, d_scratch, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
+                s.sum_lnom = sm; s.lnom_min = mn;
+                if (!(mn == mn) || !(sm == sm)) { s.lnom_min = -1.0e300; s.sum_lnom = 0.0; }   // Om_arr <= 0: literal only
+                if (model == LF_MODEL_Z) {
+                    if (range_stats(c, c->d_z, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
+                    s.sum_z = sm; s.z_min = mn; s.z_max = mx;
+                    k_square<<<G, T, 0, c->stream>>>(n, c->d_z, d_scratch);
+                    if (range_stats(c, d_scratch, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
+                    s.sum_z2 = sm;
+                }
+            }
+        }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_tmp);
+    cudaFree(d_scratch);
+    a.src2 = c->d_src2; a.lum = c->d_lum; a.flux = c->d_flux; a.z = c->d_z; a.om_arr = c->d_om;
+    c->have_sources = true;
+    return 0;
+}
+
+extern "C" int lf_set_grid(lf_ctx* c, const double* logL, const double* zarr, const double* DL_zarr,
+                           const double* volume_part, const double* integ_part, const double* omega0) {
+    if (!c) return fail("lf_set_grid: null context");
+    const int K = c->cfg.nfields, S = c->cfg.size_ln, model = c->cfg.model;
+    if (!logL || !zarr) return fail("lf_set_grid: logL and zarr are required");
+    if (model == LF_MODEL_FREE && (!DL_zarr || !volume_part || !omega0)) return fail("lf_set_grid: FREE model needs DL_zarr, volume_part, omega0");
+    if (model != LF_MODEL_FREE && !integ_part) return fail("lf_set_grid: FIXED/Z models need integ_part");
+    CK(cudaSetDevice(c->device));
+    dfree(c->d_qpf); dfree(c->d_qp); dfree(c->d_zarr);
+    const long long SS = (long long)S * S, NQ = SS * K;
+    c->NQ = NQ;
+    KArgs& a = c->ka;
+    a.NQ = NQ;
+    // trapezoid weights: trapz(trapz(y, logL, axis=0), zarr) = sum_ji wl_ji wz_i y_ji     (lumfuncmcmc.py:377)
+    std::vector<double> wz(S);
+    for (int i = 0; i < S; ++i) {
+        double wgt = 0.0;
+        if (i + 1 < S) wgt += zarr[i + 1] - zarr[i];
+        if (i > 0) wgt += zarr[i] - zarr[i - 1];
+        wz[i] = 0.5 * wgt;
+    }
+    auto at = [&](const double* arr, int k, int j, int i) { return arr[((long long)k * S + j) * S + i]; };
+    // points are stored column-major: q = (k*S + i)*S + j
+    if (model == LF_MODEL_FREE) {
+        std::vector<QuadPointFree> pts((size_t)NQ);
+        for (int k = 0; k < K; ++k) {
+            double gmin = 1.0e300, fmin_ = 1.0e300;
+            for (int i = 0; i < S; ++i) {
+                double dl = MPC_CM_REF * DL_zarr[i];
+                double den = FOURPI * (dl * dl);
+                for (int j = 0; j < S; ++j) {
+                    double x = at(logL, k, j, i);
+                    double wl = 0.0;
+                    if (j + 1 < S) wl += at(logL, k, j + 1, i) - x;
+                    if (j > 0) wl += x - at(logL, k, j - 1, i);
+                    wl *= 0.5;
+                    QuadPointFree& p = pts[((size_t)k * S + i) * S + j];
+                    p.x = x;
+                    p.Lx = pow(10.0, x);
+                    p.f = p.Lx / den;                                   // lumfuncmcmc.py:69-70
+                    p.g = log10(p.f);
+                    p.wt = wl * wz[i] * volume_part[i] * (omega0[k] / SQARCSEC);
+                    gmin = std::min(gmin, p.g);
+                    fmin_ = std::min(fmin_, p.f);
+                }
+            }
+            a.fs[k].grid_g_min = gmin;
+            a.fs[k].grid_f_min = fmin_;
+        }
+        CK(cudaMalloc(&c->d_qpf, sizeof(QuadPointFree) * (size_t)NQ));
+        CK(cudaMemcpy(c->d_qpf, pts.data(), sizeof(QuadPointFree) * (size_t)NQ, cudaMemcpyHostToDevice));
+    } else {
+        std::vector<QuadPoint> pts((size_t)NQ);
+        for (int k = 0; k < K; ++k)
+            for (int i = 0; i < S; ++i)
+                for (int j = 0; j < S; ++j) {
+                    double x = at(logL, k, j, i);
+                    double wl = 0.0;
+                    if (j + 1 < S) wl += at(logL, k, j + 1, i) - x;
+                    if (j > 0) wl += x - at(logL, k, j - 1, i);
+                    wl *= 0.5;
+                    QuadPoint& p = pts[((size_t)k * S + i) * S + j];
+                    p.x = x;
+                    p.Lx = pow(10.0, x);
+                    p.wt = wl * wz[i] * at(integ_part, k, j, i);
+                }
+        CK(cudaMalloc(&c->d_qp, sizeof(QuadPoint) * (size_t)NQ));
+        CK(cudaMemcpy(c->d_qp, pts.data(), sizeof(QuadPoint) * (size_t)NQ, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMalloc(&c->d_zarr, sizeof(double) * S));
+    CK(cudaMemcpy(c->d_zarr, zarr, sizeof(double) * S, cudaMemcpyHostToDevice));
+    a.qpf = c->d_qpf; a.qp = c->d_qp; a.zarr = c->d_zarr;
+    c->have_grid = true;
+    return 0;
+}
+
+extern "C" int lf_set_quadrature_share(lf_ctx* c, int32_t share, int32_t nshare) {
+    if (!c) return fail("lf_set_quadrature_share: null context");
+    if (nshare < 1 || share < 0 || share >= nshare) return fail("lf_set_quadrature_share: need 0 <= share < nshare");
+    c->ka.share = share;
+    c->ka.nshare = nshare;
+    return 0;
+}
+
+static int ensure_scratch(lf_ctx* c, long long W, int rows) {
+    if (W > c->Wcap) {
+        long long cap = std::max<long long>(64, W);
+        cap = (cap + 31) / 32 * 32;
+        dfree(c->d_wp); dfree(c->d_colA); dfree(c->d_colB); dfree(c->d_partial);
+        dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_thetas); dfree(c->d_out);
+        if (c->h_thetas) { cudaFreeHost(c->h_thetas); c->h_thetas = nullptr; }
+        if (c->h_out) { cudaFreeHost(c->h_out); c->h_out = nullptr; }
+        CK(cudaMalloc(&c->d_wp, sizeof(double) * P_NSLOTS * cap));
+        if (c->cfg.model == LF_MODEL_Z) {
+            CK(cudaMalloc(&c->d_colA, sizeof(double) * c->cfg.size_ln * cap));
+            CK(cudaMalloc(&c->d_colB, sizeof(double) * c->cfg.size_ln * cap));
+        }
+        CK(cudaMalloc(&c->d_list_fast, sizeof(int) * cap));
+        CK(cudaMalloc(&c->d_list_lit, sizeof(int) * cap));
+        CK(cudaMalloc(&c->d_thetas, sizeof(double) * c->ndim * cap));
+        CK(cudaMalloc(&c->d_out, sizeof(double) * cap));
+        CK(cudaMallocHost(&c->h_thetas, sizeof(double) * c->ndim * cap));
+        CK(cudaMallocHost(&c->h_out, sizeof(double) * cap));
+        c->Wcap = cap;
+        c->rows_cap = 0;
+    }
+    if (rows > c->rows_cap) {
+        dfree(c->d_partial);
+        CK(cudaMalloc(&c->d_partial, sizeof(double) * (size_t)rows * c->Wcap));
+        c->rows_cap = rows;
+    }
+    return 0;
+}
+
+// choose slab counts so that one class fills the machine with a few waves of warp items
+static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
+    const long long n_wg = (W + 31) / 32;
+    const long long target_items = (long long)c->sm_count * 16 * 4;
+    long long rows = std::max<long long>(1, target_items / n_wg);
+    const int model = c->cfg.model;
+    // relative cost of a quadrature point vs a source term
+    double src_cost = model == LF_MODEL_FREE ? 1.0 : (model == LF_MODEL_Z ? 0.5 : 0.0);
+    double quad_cost = model == LF_MODEL_FREE ? 1.5 : 0.6;
+    double wsrc = src_cost * (double)c->N, wq = quad_cost * (double)c->NQ;
+    double tot = wsrc + wq;
+    if (tot <= 0.0) { n_src = 1; n_quad = 1; return; }
+    long long rs = (long long)llround((double)rows * wsrc / tot), rq = rows - rs;
+    const long long min_per = 32;
+    rs = std::max<long long>(1, std::min<long long>(rs, std::max<long long>(1, c->N / min_per)));
+    rq = std::max<long long>(1, std::min<long long>(rq, std::max<long long>(1, c->NQ / min_per)));
+    n_src = (int)rs;
+    n_quad = (int)rq;
+}
+
+static int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_out, cudaStream_t st) {
+    if (!c->have_sources || !c->have_grid) return fail("lf_lnprob: call lf_set_sources and lf_set_grid first");
+    if (W <= 0) return 0;
+    int n_src, n_quad;
+    plan_rows(c, W, n_src, n_quad);
+    if (ensure_scratch(c, W, n_src + n_quad)) return 1;
+    KArgs a = c->ka;
+    a.thetas = d_thetas; a.out = d_out; a.W = W; a.Wcap = c->Wcap;
+    a.wp = c->d_wp; a.colA = c->d_colA; a.colB = c->d_colB;
+    a.cls_count = c->d_cls; a.list_fast = c->d_list_fast; a.list_lit = c->d_list_lit;
+    a.partial = c->d_partial; a.n_src_slabs = n_src; a.n_quad_slabs = n_quad;
+    CK(cudaMemsetAsync(c->d_cls, 0, 4 * sizeof(int), st));
+    const int T = 128;
+    k_prologue<<<(unsigned)((W + T - 1) / T), T, 0, st>>>(a);
+    c->launches++;
+    if (c->cfg.model == LF_MODEL_Z) {
+        long long tot = (long long)c->cfg.size_ln * W;
+        k_zcolumns<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(a);
+        c->launches++;
+    }
+    const long long n_wg = (W + 31) / 32;
+    const long long items = n_wg * (n_src + n_quad);
+    const unsigned blocks = (unsigned)((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
+    k_main<false><<<blocks, BLOCK_THREADS, 0, st>>>(a);
+    k_main<true><<<blocks, BLOCK_THREADS, 0, st>>>(a);
+    k_finish<<<(unsigned)((W + T - 1) / T), T, 0, st>>>(a);
+    c->launches += 3;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int lf_lnprob_batch_device(lf_ctx* c, const double* d_thetas, int64_t W, double* d_out, void* stream) {
+    if (!c) return fail("lf_lnprob_batch_device: null context");
+    if (W < 0 || (W > 0 && (!d_thetas || !d_out))) return fail("lf_lnprob_batch_device: bad arguments");
+    CK(cudaSetDevice(c->device));
+    return launch_pipeline(c, d_thetas, W, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int lf_lnprob_batch(lf_ctx* c, const double* thetas, int64_t W, double* out) {
+    if (!c) return fail("lf_lnprob_batch: null context");
+    if (W < 0 || (W > 0 && (!thetas || !out))) return fail("lf_lnprob_batch: bad arguments");
+    if (W == 0) return 0;
+    CK(cudaSetDevice(c->device));
+    if (!c->have_sources || !c->have_grid) return fail("lf_lnprob: call lf_set_sources and lf_set_grid first");
+    int n_src, n_quad;
+    plan_rows(c, W, n_src, n_quad);
+    if (ensure_scratch(c, W, n_src + n_quad)) return 1;
+    memcpy(c->h_thetas, thetas, sizeof(double) * c->ndim * W);
+    CK(cudaMemcpyAsync(c->d_thetas, c->h_thetas, sizeof(double) * c->ndim * W, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (launch_pipeline(c, c->d_thetas, W, c->d_out, c->stream)) return 1;
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaMemcpyAsync(c->h_out, c->d_out, sizeof(double) * W, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(c->h_cls, c->d_cls, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->last_ms = ms;
+    memcpy(out, c->h_out, sizeof(double) * W);
+    return 0;
+}
+
+extern "C" int lf_last_call_info(lf_ctx* c, int64_t counts[3], int64_t* launches) {
+    if (!c) return fail("lf_last_call_info: null context");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(c->h_cls, c->d_cls, 3 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (counts) for (int i = 0; i < 3; ++i) counts[i] = c->h_cls[i];
+    if (launches) *launches = c->launches;
+    return 0;
+}
+
+extern "C" int lf_last_kernel_ms(lf_ctx* c, double* ms) {
+    if (!c || !ms) return fail("lf_last_kernel_ms: null argument");
+    *ms = c->last_ms;
+    return 0;
+}
+
+extern "C" int lf_fp64_peak(lf_ctx* c, int32_t iters, double* dfma_per_s, double* ms_out) {
+    if (!c || !dfma_per_s) return fail("lf_fp64_peak: null argument");
+    CK(cudaSetDevice(c->device));
+    double* sink = nullptr;
+    CK(cudaMalloc(&sink, sizeof(double)));
+    const int blocks = c->sm_count * 8, threads = 256;
+    k_fp64_peak<<<blocks, threads, 0, c->stream>>>(64, 1.0, sink);       // warm-up
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_fp64_peak<<<blocks, threads, 0, c->stream>>>(iters, 1.0, sink);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    cudaFree(sink);
+    c->launches += 2;
+    double n = (double)blocks * threads * (double)iters * 64.0;
+    *dfma_per_s = n / (ms * 1.0e-3);
+    if (ms_out) *ms_out = ms;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Veff host entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const double* lum, const int64_t* field_ind,
+                           int32_t nfields, const double* flim, double alpha, double fcmin, double sum_omega,
+                           double vol_int, const double* vol_per_source, const uint8_t* valid,
+                           const double* edges, int32_t nbins, double* phi_out, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_veff_bin: null context");
+    if (n <= 0 || !flux || !lum || !field_ind || !flim || !edges || !counts || !sumphi) return fail("lf_veff_bin: bad arguments");
+    if (nfields < 1 || nfields > LF_MAX_FIELDS) return fail("lf_veff_bin: nfields out of range");
+    if (nbins < 1 || nbins > VEFF_MAX_BINS) return fail("lf_veff_bin: nbins out of range");
+    if (field_ind[0] != 0 || field_ind[nfields] != n) return fail("lf_veff_bin: field_ind must run from 0 to n");
+    CK(cudaSetDevice(c->device));
+    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
+    dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult);
+    const size_t nb = sizeof(double) * (size_t)n;
+    double* d_flux = nullptr; double* d_vol = nullptr; unsigned char* d_valid = nullptr;
+    CK(cudaMalloc(&d_flux, nb));
+    CK(cudaMalloc(&c->v_lum, nb));
+    CK(cudaMalloc(&c->v_phi, nb));
+    CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
+    const int blocks = (int)std::min<long long>((long long)c->sm_count * 8, (n + 255) / 256);
+    c->v_blocks = blocks; c->v_nbins = nbins; c->vN = n;
+    CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)blocks * nbins));
+    CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)blocks * nbins));
+    CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
+    CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
+    CK(cudaMemcpyAsync(d_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
+    if (vol_per_source) {
+        CK(cudaMalloc(&d_vol, nb));
+        CK(cudaMemcpyAsync(d_vol, vol_per_source, nb, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (valid) {
+        CK(cudaMalloc(&d_valid, (size_t)n));
+        CK(cudaMemcpyAsync(d_valid, valid, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    }
+    VeffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.flux = d_flux; a.lum = c->v_lum; a.vol = d_vol; a.valid = d_valid; a.phi = c->v_phi;
+    a.K = nfields;
+    for (int k = 0; k <= nfields; ++k) a.field_ind[k] = field_ind[k];
+    const bool modified = fcmin != 0.0;
+    double aa = (2.0 * fcmin - 1.0) * (2.0 * fcmin - 1.0);
+    for (int k = 0; k < nfields; ++k) {
+        a.F50[k] = 1.0e-17 * flim[k];
+        // inverse_fleming, reference operation order (VmaxLumFunc.py:164-167)
+        double b = -1.0 * pow(fabs(aa / (1.0 - aa)) * pow(alpha, -2.0), 0.5);
+        a.ftau[k] = a.F50[k] * pow(10.0, b);
+    }
+    a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.vol_int = vol_int; a.modified = modified ? 1 : 0;
+    a.edges = c->v_edges; a.nbins = nbins; a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = nullptr;
+    size_t smem = sizeof(double) * (nbins + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * (size_t)nbins;
+    k_veff<false><<<blocks, 256, smem, c->stream>>>(a);
+    k_veff_reduce<<<(nbins + 127) / 128, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    if (phi_out) CK(cudaMemcpyAsync(phi_out, c->v_phi, nb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_flux);
+    if (d_vol) cudaFree(d_vol);
+    if (d_valid) cudaFree(d_valid);
+    return 0;
+}
+
+extern "C" int lf_boot_bin(lf_ctx* c, const int32_t* mult, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_boot_bin: null context");
+    if (!c->v_phi || c->vN <= 0) return fail("lf_boot_bin: call lf_veff_bin first");
+    if (!mult || !counts || !sumphi) return fail("lf_boot_bin: bad arguments");
+    CK(cudaSetDevice(c->device));
+    if (!c->v_mult) CK(cudaMalloc(&c->v_mult, sizeof(int) * (size_t)c->vN));
+    CK(cudaMemcpyAsync(c->v_mult, mult, sizeof(int) * (size_t)c->vN, cudaMemcpyHostToDevice, c->stream));
+    VeffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
+    a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult;
+    const int nbins = c->v_nbins, blocks = c->v_blocks;
+    size_t smem = sizeof(double) * (nbins + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * (size_t)nbins;
+    k_veff<true><<<blocks, 256, smem, c->stream>>>(a);
+    k_veff_reduce<<<(nbins + 127) / 128, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}

@@ -1,0 +1,206 @@
+"""Python face of the CUDA likelihood engine: NumPy in, NumPy out (or torch device tensors, zero-copy).
+
+``LikelihoodEngine(inputs, kind)`` uploads the arrays the reference's ``lnlike`` reads from ``self``
+(reference lumfuncmcmc.py:360-393, lumfuncmcmc_z.py:364-376; produced once by the set-up chain
+lumfuncmcmc.py:180-235) and then evaluates ``lnprob`` for a whole walker ensemble per call.
+
+``inputs`` keys (float64 arrays unless noted) -- the same dict the oracle consumes:
+  lum, z, zint, DLarr, field_ind (int64, K+1), Omega_0 (K), Flim (K), alpha, fcmin, logL (K,S,S), zarr (S),
+  DL_zarr (S), volume_part (S), [Om_arr (N), integ_part (K,S,S)], the prior boxes ``*_lims``, ``sch_al``,
+  ``fix_sch_al`` and (kind 'z') the pivots z1, z2, z3.
+"""
+import ctypes as C
+
+import numpy as np
+from scipy.interpolate import interp1d
+
+from . import _lib
+
+KINDS = {'free': _lib.LF_MODEL_FREE, 'fixed': _lib.LF_MODEL_FIXED, 'z': _lib.LF_MODEL_Z}
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def source_flux(inp):
+    """Per-source flux as the reference's ``Omega`` derives it from ``lum`` and the *interpolated* D_L
+    (reference lumfuncmcmc.py:69-70 with dLzfunc = interp1d(zint, DLarr), :196) -- walker-independent, so it is
+    evaluated once here instead of once per likelihood call."""
+    z = np.asarray(inp['z'], dtype=np.float64)
+    zint, DLarr = np.asarray(inp['zint']), np.asarray(inp['DLarr'])
+    if z.size and (z.min() < zint[0] or z.max() > zint[-1]):
+        raise ValueError("source redshift outside the D_L interpolation table")
+    # the same SciPy linear interpolant object the reference builds (lumfuncmcmc.py:196), evaluated once
+    DL = interp1d(zint, DLarr)(z)
+    L = 10 ** np.asarray(inp['lum'], dtype=np.float64)
+    return L / (4.0 * np.pi * (3.086e24 * DL) ** 2)
+
+
+class LikelihoodEngine:
+    """One engine context on one GPU holding one shard of sources."""
+
+    def __init__(self, inp, kind, device=0, force_literal=False, quadrature_share=(0, 1)):
+        if kind not in KINDS:
+            raise ValueError("kind must be one of %s" % sorted(KINDS))
+        self.kind = kind
+        self.lib = _lib.load()
+        K = len(inp['Flim'])
+        if K > _lib.LF_MAX_FIELDS:
+            raise ValueError("at most %d fields" % _lib.LF_MAX_FIELDS)
+        S = int(np.asarray(inp['zarr']).shape[0])
+        fix_sch_al = bool(inp.get('fix_sch_al', False))
+        cfg = _lib.LFConfig()
+        cfg.model, cfg.precision, cfg.device = KINDS[kind], _lib.LF_PREC_F64, int(device)
+        cfg.nfields, cfg.size_ln, cfg.fix_sch_al = K, S, int(fix_sch_al)
+        cfg.force_literal = int(bool(force_literal))
+        cfg.fcmin = float(inp['fcmin']) if inp['fcmin'] else 0.0
+        cfg.sch_al = float(inp['sch_al'])
+
+        def box(name, default):
+            lims = inp.get(name, default)
+            return (C.c_double * 2)(float(lims[0]), float(lims[1]))
+
+        cfg.Lstar_lims, cfg.phistar_lims = box('Lstar_lims', (40.0, 45.0)), box('phistar_lims', (-8.0, 5.0))
+        cfg.sch_al_lims = box('sch_al_lims', (-3.0, 1.0))
+        cfg.Flim_lims, cfg.alpha_lims = box('Flim_lims', (1.0, 6.0)), box('alpha_lims', (1.0, 7.0))
+        cfg.z_pivots = (C.c_double * 3)(float(inp.get('z1', 1.20)), float(inp.get('z2', 1.53)), float(inp.get('z3', 1.86)))
+        # the reference's single-z lnprior range-checks the parameters that are NOT sampled as well
+        # (lumfuncmcmc.py:347-354); they are constants here, so the check is done once
+        ok = True
+        if kind != 'z':
+            if fix_sch_al:
+                ok &= cfg.sch_al_lims[0] <= cfg.sch_al <= cfg.sch_al_lims[1]
+            if kind == 'fixed':
+                ok &= all(cfg.Flim_lims[0] <= f <= cfg.Flim_lims[1] for f in np.asarray(inp['Flim'], dtype=np.float64))
+                ok &= cfg.alpha_lims[0] <= float(inp['alpha']) <= cfg.alpha_lims[1]
+        cfg.fixed_prior_ok = int(bool(ok))
+        self._ctx = C.c_void_p()
+        _lib.check(self.lib.lf_create(C.byref(self._ctx), C.byref(cfg)), self.lib)
+        self.ndim = self.lib.lf_ndim(self._ctx)
+        self.device = int(device)
+        self.nfields, self.size_ln = K, S
+
+        # ---- sources -------------------------------------------------------------------------
+        lum = _f64(inp['lum'])
+        fi = np.ascontiguousarray(inp['field_ind'], dtype=np.int64)
+        self.nsources = int(lum.shape[0])
+        flux = zz = om = om0i = None
+        if kind == 'free':
+            flux = _f64(inp['flux_src']) if 'flux_src' in inp else _f64(source_flux(inp))
+            # dtype=int copy of the areas: truncation toward zero (lumfuncmcmc.py:285)
+            om0i = np.ascontiguousarray(np.asarray(inp['Omega_0'], dtype=np.float64).astype(np.int64))
+        else:
+            om = _f64(inp['Om_arr'])
+            if kind == 'z':
+                zz = _f64(inp['z'])
+        _lib.check(self.lib.lf_set_sources(self._ctx, self.nsources, _ptr(lum), _ptr(flux), _ptr(zz), _ptr(om),
+                                           _ptr(fi), _ptr(om0i)), self.lib)
+        # ---- quadrature grid -----------------------------------------------------------------
+        logL = _f64(inp['logL'])
+        if logL.shape != (K, S, S):
+            raise ValueError("logL must have shape (K, S, S)")
+        zarr = _f64(inp['zarr'])
+        if kind == 'free':
+            dlz, vol, om0 = _f64(inp['DL_zarr']), _f64(inp['volume_part']), _f64(inp['Omega_0'])
+            _lib.check(self.lib.lf_set_grid(self._ctx, _ptr(logL), _ptr(zarr), _ptr(dlz), _ptr(vol), None, _ptr(om0)),
+                       self.lib)
+        else:
+            ip = _f64(inp['integ_part'])
+            if ip.shape != (K, S, S):
+                raise ValueError("integ_part must have shape (K, S, S)")
+            _lib.check(self.lib.lf_set_grid(self._ctx, _ptr(logL), _ptr(zarr), None, None, _ptr(ip), None), self.lib)
+        if tuple(quadrature_share) != (0, 1):
+            self.set_quadrature_share(*quadrature_share)
+
+    # ------------------------------------------------------------------------------------------
+    def set_quadrature_share(self, share, nshare):
+        _lib.check(self.lib.lf_set_quadrature_share(self._ctx, int(share), int(nshare)), self.lib)
+
+    def lnprob(self, thetas):
+        """thetas: (ndim,) or (W, ndim) host array -> float or (W,) array.  H2D, kernels, D2H, sync."""
+        th = np.asarray(thetas, dtype=np.float64)
+        scalar = th.ndim == 1
+        th = np.ascontiguousarray(np.atleast_2d(th))
+        if th.shape[1] != self.ndim:
+            raise ValueError("theta has %d parameters, this model takes %d" % (th.shape[1], self.ndim))
+        out = np.empty(th.shape[0], dtype=np.float64)
+        _lib.check(self.lib.lf_lnprob_batch(self._ctx, _ptr(th), th.shape[0], _ptr(out)), self.lib)
+        return float(out[0]) if scalar else out
+
+    def lnprob_device(self, d_thetas, d_out=None, stream=None):
+        """torch CUDA float64 tensors, asynchronous on ``stream`` (default: torch's current stream)."""
+        import torch
+        if d_thetas.dtype != torch.float64 or not d_thetas.is_cuda or not d_thetas.is_contiguous():
+            raise ValueError("d_thetas must be a contiguous CUDA float64 tensor")
+        W = d_thetas.shape[0]
+        if d_thetas.dim() != 2 or d_thetas.shape[1] != self.ndim:
+            raise ValueError("d_thetas must have shape (W, %d)" % self.ndim)
+        if d_out is None:
+            d_out = torch.empty(W, dtype=torch.float64, device=d_thetas.device)
+        st = torch.cuda.current_stream(d_thetas.device) if stream is None else stream
+        _lib.check(self.lib.lf_lnprob_batch_device(self._ctx, C.c_void_p(d_thetas.data_ptr()), W,
+                                                   C.c_void_p(d_out.data_ptr()), C.c_void_p(st.cuda_stream)), self.lib)
+        return d_out
+
+    def last_call_info(self):
+        counts = (C.c_int64 * 3)()
+        launches = C.c_int64()
+        _lib.check(self.lib.lf_last_call_info(self._ctx, counts, C.byref(launches)), self.lib)
+        return dict(rejected=counts[0], fast=counts[1], literal=counts[2], launches=launches.value)
+
+    def last_kernel_ms(self):
+        ms = C.c_double()
+        _lib.check(self.lib.lf_last_kernel_ms(self._ctx, C.byref(ms)), self.lib)
+        return ms.value
+
+    def fp64_peak(self, iters=20000):
+        """Measured register-only DFMA rate of this GPU (thread-instructions per second) and the run time in ms."""
+        rate, ms = C.c_double(), C.c_double()
+        _lib.check(self.lib.lf_fp64_peak(self._ctx, int(iters), C.byref(rate), C.byref(ms)), self.lib)
+        return rate.value, ms.value
+
+    # ------------------------------------------------------------------------------------------
+    def veff_bin(self, flux, lum, field_ind, flim, alpha, fcmin, sum_omega, vol_int, edges, vol_per_source=None,
+                 valid=None, want_phi=True):
+        """1/V_eff weights and the binned LF of the original sample (reference lumfuncmcmc.py:515-525,
+        VmaxLumFunc.py:336-350).  Returns (phi or None, counts int64[nbins], sumphi float64[nbins])."""
+        flux, lum, edges, flim = _f64(flux), _f64(lum), _f64(edges), _f64(flim)
+        fi = np.ascontiguousarray(field_ind, dtype=np.int64)
+        n, nb = flux.shape[0], edges.shape[0] - 1
+        vps = None if vol_per_source is None else _f64(vol_per_source)
+        val = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        phi = np.empty(n, dtype=np.float64) if want_phi else None
+        self._veff_nbins = nb
+        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
+        _lib.check(self.lib.lf_veff_bin(self._ctx, n, _ptr(flux), _ptr(lum), _ptr(fi), len(flim), _ptr(flim),
+                                        float(alpha), float(fcmin) if fcmin else 0.0, float(sum_omega), float(vol_int),
+                                        _ptr(vps), _ptr(val), _ptr(edges), nb, _ptr(phi), _ptr(counts), _ptr(sums)),
+                   self.lib)
+        return phi, counts, sums
+
+    def boot_bin(self, mult):
+        """One bootstrap replicate on the sample left resident by :meth:`veff_bin`."""
+        mult = np.ascontiguousarray(mult, dtype=np.int32)
+        nb = self._nbins_resident()
+        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
+        _lib.check(self.lib.lf_boot_bin(self._ctx, _ptr(mult), _ptr(counts), _ptr(sums)), self.lib)
+        return counts, sums
+
+    def _nbins_resident(self):
+        return getattr(self, '_veff_nbins', 0)
+
+    def close(self):
+        if getattr(self, '_ctx', None) is not None and self._ctx.value:
+            self.lib.lf_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,216 @@
+"""GPU parity: the CUDA engine (through the C ABI) against the reference's golden lnprob values and the oracle.
+
+Tolerances (BASELINE.json north_star): |gpu - ref| / |ref| <= 1e-10 for finite values in FP64; -inf <-> -inf.
+"""
+import numpy as np
+import pytest
+
+from lumfuncmcmc_b200 import synth
+from oracle import lf_oracle
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+CASES = [('free_k5_n2000', 'free'), ('free_k3_fixal', 'free'), ('free_k2_mcf50', 'free'),
+         ('fixed_k2_n800', 'fixed'), ('fixed_k2_fixal', 'fixed'), ('z_k2_n800', 'z'), ('z_k2_fixal', 'z')]
+
+
+def _engine(inp, kind, **kw):
+    from lumfuncmcmc_b200.engine import LikelihoodEngine
+    return LikelihoodEngine(inp, kind, device=0, **kw)
+
+
+def _assert_parity(got, ref, rtol=RTOL):
+    assert not np.isnan(got).any(), "engine returned NaN"
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref)), \
+        "-inf sets differ at rows %s" % np.nonzero(np.isneginf(got) != np.isneginf(ref))[0]
+    fin = np.isfinite(ref)
+    rel = np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])
+    assert rel.max() <= rtol, "max rel diff %.3e at row %d" % (rel.max(), np.nonzero(fin)[0][rel.argmax()])
+    return rel.max()
+
+
+@pytest.mark.parametrize('name,kind', CASES)
+@pytest.mark.parametrize('literal', [False, True])
+def test_golden_lnprob(golden, name, kind, literal):
+    g = golden(name)
+    eng = _engine(g, kind, force_literal=literal)
+    got = eng.lnprob(g['thetas'])
+    info = eng.last_call_info()
+    _assert_parity(got, g['lnprob_ref'])
+    assert info['rejected'] + info['fast'] + info['literal'] == len(g['thetas'])
+    if literal:
+        assert info['fast'] == 0
+    else:
+        assert info['fast'] > 0          # the optimised kernels are the ones exercised
+    eng.close()
+
+
+@pytest.mark.parametrize('name,kind', [('free_k5_n2000', 'free'), ('z_k2_n800', 'z'), ('fixed_k2_n800', 'fixed')])
+def test_scalar_call_equals_batch_row(golden, name, kind):
+    g = golden(name)
+    eng = _engine(g, kind)
+    batch = eng.lnprob(g['thetas'][:6])
+    for i in range(6):
+        one = eng.lnprob(g['thetas'][i])
+        assert isinstance(one, float)
+        assert one == batch[i] or (np.isneginf(one) and np.isneginf(batch[i]))
+    eng.close()
+
+
+def test_device_api_matches_host_api(golden):
+    import torch
+    g = golden('free_k5_n2000')
+    eng = _engine(g, 'free')
+    host = eng.lnprob(g['thetas'])
+    d_th = torch.from_numpy(np.ascontiguousarray(g['thetas'])).cuda()
+    d_out = eng.lnprob_device(d_th)
+    torch.cuda.synchronize()
+    dev = d_out.cpu().numpy()
+    assert np.array_equal(host, dev, equal_nan=True)
+    eng.close()
+
+
+def _shard(inp, lo_frac, hi_frac):
+    """Take the same fraction of every field (source sharding keeps field membership)."""
+    fi = np.asarray(inp['field_ind'])
+    keep, new_fi = [], [0]
+    for k in range(len(fi) - 1):
+        n = fi[k + 1] - fi[k]
+        a, b = fi[k] + int(n * lo_frac), fi[k] + int(n * hi_frac)
+        keep.append(np.arange(a, b))
+        new_fi.append(new_fi[-1] + (b - a))
+    keep = np.concatenate(keep)
+    out = dict(inp)
+    for key in ('lum', 'z', 'Om_arr', 'flux'):
+        if key in inp and inp[key] is not None:
+            out[key] = np.asarray(inp[key])[keep]
+    out['field_ind'] = np.array(new_fi, dtype=np.int64)
+    return out
+
+
+@pytest.mark.parametrize('name,kind', [('free_k5_n2000', 'free'), ('z_k2_n800', 'z'), ('fixed_k2_n800', 'fixed')])
+def test_additivity_over_source_shards(golden, name, kind):
+    """lnprob is a plain sum over sources: two shards (each integrating half of the walkers) add up to the whole."""
+    g = golden(name)
+    th = g['thetas']
+    full = _engine(g, kind)
+    whole = full.lnprob(th)
+    parts = []
+    for r, (a, b) in enumerate([(0.0, 0.37), (0.37, 1.0)]):
+        e = _engine(_shard(g, a, b), kind, quadrature_share=(r, 2))
+        parts.append(e.lnprob(th))
+        e.close()
+    with np.errstate(invalid='ignore'):
+        total = parts[0] + parts[1]
+    _assert_parity(total, whole, rtol=1e-12)
+    _assert_parity(total, g['lnprob_ref'])
+    full.close()
+
+
+def test_permutation_invariance_within_field(golden):
+    g = golden('free_k5_n2000')
+    rng = np.random.default_rng(3)
+    fi = g['field_ind']
+    perm = np.concatenate([fi[k] + rng.permutation(fi[k + 1] - fi[k]) for k in range(len(fi) - 1)])
+    p = dict(g)
+    p['lum'], p['z'] = g['lum'][perm], g['z'][perm]
+    a, b = _engine(g, 'free'), _engine(p, 'free')
+    _assert_parity(b.lnprob(g['thetas']), a.lnprob(g['thetas']), rtol=1e-13)
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize('kind', ['free', 'fixed', 'z'])
+def test_midsize_synthetic_against_oracle(kind):
+    """N = 2e5 sources, W = 96 walkers (mixed near-truth / prior draws); oracle on every walker."""
+    cat = synth.make_catalogue(200000, seed=21, evolve=(0.3, -0.2) if kind == 'z' else None)
+    inp = synth.direct_inputs(cat, nknots=2048, size_ln=101 if kind == 'free' else 201, tabulated=(kind != 'free'))
+    th = np.concatenate([synth.draw_thetas(inp, kind, 64, seed=5, mode='near', scale=0.02),
+                         synth.draw_thetas(inp, kind, 32, seed=6, mode='prior')])
+    eng = _engine(inp, kind)
+    got = eng.lnprob(th)
+    ref = lf_oracle.lnprob_batch(inp, kind, th)
+    rel = _assert_parity(got, ref)
+    info = eng.last_call_info()
+    assert info['fast'] >= 64
+    print(kind, 'max rel', rel, info)
+    eng.close()
+
+
+def test_plain_fleming_curve_when_fcmin_is_zero():
+    cat = synth.make_catalogue(5000, seed=8, nfields=3, fcmin=0.0)
+    inp = synth.direct_inputs(cat, nknots=512)
+    assert inp['fcmin'] == 0.0
+    th = np.concatenate([synth.draw_thetas(inp, 'free', 24, seed=1), synth.draw_thetas(inp, 'free', 8, seed=2, mode='prior')])
+    for literal in (False, True):
+        eng = _engine(inp, 'free', force_literal=literal)
+        _assert_parity(eng.lnprob(th), lf_oracle.lnprob_batch(inp, 'free', th))
+        eng.close()
+
+
+def test_empty_and_ragged_fields():
+    """A field with no sources and a single-source field (ragged field_ind) are legal inputs."""
+    cat = synth.make_catalogue(400, seed=9, nfields=3)
+    inp = synth.direct_inputs(cat, nknots=256)
+    fi = inp['field_ind']
+    keep = np.concatenate([np.arange(fi[0], fi[1]), np.arange(fi[2], fi[2] + 1)])      # field 1 empty, field 2 one source
+    inp = dict(inp)
+    inp['lum'], inp['z'] = inp['lum'][keep], inp['z'][keep]
+    inp['field_ind'] = np.array([0, fi[1], fi[1], fi[1] + 1], dtype=np.int64)
+    th = synth.draw_thetas(inp, 'free', 16, seed=1)
+    eng = _engine(inp, 'free')
+    _assert_parity(eng.lnprob(th), lf_oracle.lnprob_batch(inp, 'free', th))
+    eng.close()
+
+
+def test_veff_weights_and_bit_exact_bin_counts(golden):
+    g = golden('veff_k3_n400')
+    from lumfuncmcmc_b200.engine import LikelihoodEngine
+    eng = LikelihoodEngine(golden('free_k3_fixal'), 'free', device=0)
+    K = len(g['Flim'])
+    phi, counts, sums = eng.veff_bin(g['flux'], g['lum'], g['field_ind'], g['Flim'], g['alpha'], g['fcmin'],
+                                     g['sum_omega'], g['vol_int'], g['edges'])
+    np.testing.assert_allclose(phi, g['phifunc'], rtol=1e-13)
+    assert np.array_equal(counts, g['counts'])                      # integers: bit-exact
+    dL = g['Lavg'][1] - g['Lavg'][0]
+    np.testing.assert_allclose(sums / dL, g['lfbinorig'], rtol=1e-12)
+    # one bootstrap replicate with the reference's RNG stream (VmaxLumFunc.py:353)
+    np.random.seed(int(g['seed']))
+    boot = np.random.randint(len(phi), size=len(phi))
+    mult = np.bincount(boot, minlength=len(phi))
+    bc, bs = eng.boot_bin(mult)
+    Lb, pb = g['lum'][boot], g['phifunc'][boot]
+    want_c = lf_oracle.binned_lf_counts(Lb, g['edges'])
+    assert np.array_equal(bc, want_c)
+    want_s = np.array([pb[(Lb >= g['edges'][j]) & (Lb < g['edges'][j + 1])].sum() for j in range(len(want_c))])
+    np.testing.assert_allclose(bs, want_s, rtol=1e-12)
+    assert K == 3
+    eng.close()
+
+
+def test_veff_bit_exact_counts_large():
+    """1e6 sources, 50 bins: integer counts identical to NumPy's mask counts on the exact linspace edges."""
+    rng = np.random.default_rng(4)
+    n = 1000000
+    lum = rng.uniform(40.9, 44.0, n)
+    lum[:1000] = lum[1000:2000]                    # ties
+    flux = 10 ** rng.uniform(-17.2, -14.5, n)
+    fi = np.array([0, n // 3, n // 2, n], dtype=np.int64)
+    edges = np.linspace(lum.min() * 1.001, lum.max(), 51)
+    lum[5000:5050] = edges[:50]                    # values exactly on the edges
+    from lumfuncmcmc_b200.engine import LikelihoodEngine
+    eng = LikelihoodEngine(synth.direct_inputs(synth.make_catalogue(300, seed=1, nfields=3), nknots=64), 'free', device=0)
+    flim = [2.72, 3.61, 2.55]
+    phi, counts, sums = eng.veff_bin(flux, lum, fi, flim, 4.56, 0.1, 1.0e6, 3.0e10, edges)
+    want = np.histogram(lum[(lum >= edges[0]) & (lum < edges[-1])], bins=edges)[0]
+    # np.histogram closes the last bin on the right; with the mask above both conventions agree
+    assert np.array_equal(counts, want)
+    flims_arr = np.repeat(flim, np.diff(fi))
+    ref_phi = lf_oracle.veff_weights(flux, flims_arr, 4.56, 0.1, 1.0e6, 3.0e10, 0.0)
+    np.testing.assert_allclose(phi, ref_phi, rtol=1e-13)
+    j = np.searchsorted(edges, lum, side='right') - 1
+    ok = (lum >= edges[0]) & (lum < edges[-1])
+    want_s = np.bincount(j[ok], weights=ref_phi[ok], minlength=50)[:50]
+    np.testing.assert_allclose(sums, want_s, rtol=1e-12)
+    eng.close()
