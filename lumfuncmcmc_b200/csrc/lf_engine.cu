@@ -77,8 +77,9 @@ struct FieldStats {          // per-field sufficient statistics and ranges of th
     double om0_over_sq;                 // int(Omega_0)/sqarcsec                            (FREE)
 };
 
-struct QuadPointFree { double g, f, x, Lx, wt; };   // log10 flux, flux, logL, 10^logL, trapezoid*volume*area weight
-struct QuadPoint { double x, Lx, wt; };             // FIXED / Z (weight carries integ_part)
+// 16-byte aligned so a point is fetched with LDG.128s
+struct __align__(16) QuadPointFree { double g, f, x, Lx, wt, pad; };   // log10 flux, flux, logL, 10^logL, trapezoid*volume*area weight
+struct __align__(16) QuadPoint { double x, Lx, wt, pad; };             // FIXED / Z (weight carries integ_part)
 
 struct KArgs {
     int model, K, S, fix_sch_al, fixed_prior_ok, force_literal, modified;
@@ -444,7 +445,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_main(KArgs a) {
                             const QuadPointFree* pt = &a.qpf[q];
                             double2 gf = __ldg(reinterpret_cast<const double2*>(pt));
                             double2 xl = __ldg(reinterpret_cast<const double2*>(pt) + 1);
-                            double wt = __ldg(&pt->wt);
+                            double wt = __ldg(reinterpret_cast<const double2*>(pt) + 2).x;
                             double lg, rd;
                             if (a.modified) fleming_log_parts<true>(gf.x, gf.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg, rd);
                             else fleming_log_parts<false>(gf.x, gf.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg, rd);
@@ -470,9 +471,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_main(KArgs a) {
                 for (long long q = q0; q < q1; ++q) {
                     const QuadPoint* pt = &a.qp[q];
                     if (!LITERAL) {
-                        double arg = fma(c1, __ldg(&pt->x), c0);
-                        arg = fma(-__ldg(&pt->Lx), tenmL, arg);
-                        acc0 = fma(__ldg(&pt->wt), exp_full(arg, s_exp, rep16), acc0);
+                        double2 xl = __ldg(reinterpret_cast<const double2*>(pt));
+                        double wt = __ldg(reinterpret_cast<const double2*>(pt) + 1).x;
+                        double arg = fma(c1, xl.x, c0);
+                        arg = fma(-xl.y, tenmL, arg);
+                        acc0 = fma(wt, exp_full(arg, s_exp, rep16), acc0);
                     } else {                                                          // lumfuncmcmc.py:391
                         acc0 = fma(__ldg(&pt->wt), schechter_literal(__ldg(&pt->x), sal, Lstar, phistar), acc0);
                     }
@@ -490,9 +493,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_main(KArgs a) {
                         const double cA = a.colA[(long long)i * WS + w], cB = a.colB[(long long)i * WS + w];
                         for (long long q = q0; q < seg_end; ++q) {
                             const QuadPoint* pt = &a.qp[q];
-                            double arg = fma(c1, __ldg(&pt->x), cA);
-                            arg = fma(-__ldg(&pt->Lx), cB, arg);
-                            acc0 = fma(__ldg(&pt->wt), exp_full(arg, s_exp, rep16), acc0);
+                            double2 xl = __ldg(reinterpret_cast<const double2*>(pt));
+                            double wt = __ldg(reinterpret_cast<const double2*>(pt) + 1).x;
+                            double arg = fma(c1, xl.x, cA);
+                            arg = fma(-xl.y, cB, arg);
+                            acc0 = fma(wt, exp_full(arg, s_exp, rep16), acc0);
                         }
                     } else {
                         double z = __ldg(&a.zarr[i]);
@@ -966,6 +971,7 @@ extern "C" int lf_set_grid(lf_ctx* c, const double* logL, const double* zarr, co
                     p.f = p.Lx / den;                                   // lumfuncmcmc.py:69-70
                     p.g = log10(p.f);
                     p.wt = wl * wz[i] * volume_part[i] * (omega0[k] / SQARCSEC);
+                    p.pad = 0.0;
                     gmin = std::min(gmin, p.g);
                     fmin_ = std::min(fmin_, p.f);
                 }
@@ -989,6 +995,7 @@ extern "C" int lf_set_grid(lf_ctx* c, const double* logL, const double* zarr, co
                     p.x = x;
                     p.Lx = pow(10.0, x);
                     p.wt = wl * wz[i] * at(integ_part, k, j, i);
+                    p.pad = 0.0;
                 }
         CK(cudaMalloc(&c->d_qp, sizeof(QuadPoint) * (size_t)NQ));
         CK(cudaMemcpy(c->d_qp, pts.data(), sizeof(QuadPoint) * (size_t)NQ, cudaMemcpyHostToDevice));
