@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- walker x source lnL terms/s of the batched lnprob on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched under torchrun, one rank per GPU)
+    python bench.py --impl reference ...                     (the reference algorithm on the host cores)
+
+Workload (BASELINE.json configs[1], the corner the target is quoted on): free-completeness single-z model
+(ndim 9, K = 5 fields, S = 101), 10^7 synthetic sources PER GPU x 1024 walkers, FP64.  A "step" is one batched
+lnprob call over the whole ensemble (what a vectorised emcee hands over per half-step, here the full ensemble).
+At N GPUs sources are sharded (weak scaling: 10^7 per GPU), walkers replicated, the quadrature split by walker,
+one NCCL all-reduce of W doubles per step.
+
+value  : terms/s, inputs resident in HBM (theta on the device), CUDA events on the launching stream, max over ranks.
+e2e    : same metric through the public host API (ShardedLikelihood.lnprob: pinned-host theta -> H2D -> kernels
+         -> all-reduce -> D2H of W doubles -> sync), host wall clock, max over ranks.
+roofline: the loop is FP64-FMA-pipe bound (no tensor cores, HBM traffic ~0.02 B/term): achieved = terms/s/GPU x 32
+         FP64-pipe instructions per term (counted in the SASS of k_main<false>) x 2 FLOP, against the register-only
+         DFMA rate measured live on the same GPU (lf_fp64_peak) x 2 FLOP.  HBM figures are reported beside it.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FP64_INSTR_PER_TERM = 32          # DFMA/DADD/DMUL per (walker, source) term in k_main<false> (profiles/)
+BYTES_PER_SOURCE = 16             # (log10 flux, flux) per source per sweep
+METRIC = "walker x source lnL terms/sec (batched lnprob, free-completeness single-z, FP64)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='engine', choices=['engine', 'reference'])
+    ap.add_argument('--nsources', type=float, default=1.0e7, help='sources per GPU')
+    ap.add_argument('--walkers', type=int, default=1024)
+    ap.add_argument('--kind', default='free', choices=['free', 'fixed', 'z'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--prior-draws', action='store_true', help='walkers ~ U(prior) instead of a converged ensemble')
+    return ap.parse_args()
+
+
+def build_inputs(n, kind, seed):
+    from lumfuncmcmc_b200 import synth
+    cat = synth.make_catalogue(n, seed=seed, evolve=(0.3, -0.2) if kind == 'z' else None)
+    return synth.direct_inputs(cat, nknots=4096, size_ln=101 if kind == 'free' else 201, tabulated=(kind != 'free'))
+
+
+def sample_inputs(inp, n_sample):
+    """Bounded sample of the same workload for the CPU legs: the first n_sample/N of every field."""
+    from lumfuncmcmc_b200.dist import shard_inputs
+    n = len(inp['lum'])
+    if n_sample >= n:
+        return inp
+    world = max(1, int(round(n / n_sample)))
+    return shard_inputs(inp, 0, world)
+
+
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.proc, self.path = gpu, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix='.csv')
+            os.close(fd)
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '50'],
+                                         stdout=open(self.path, 'w'), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.06)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(',')]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_baseline_serial(inp_full, kind, thetas, budget_s=15.0):
+    """The oracle (restatement of the reference) driven the way the reference runs: one walker at a time, 1 core."""
+    from oracle import lf_oracle
+    inp = sample_inputs(inp_full, 1000000)
+    n = len(inp['lum'])
+    model = lf_oracle.make_model(inp, kind)
+    model.lnprob(thetas[0])                                   # warm-up (interp1d set-up, page-in)
+    t0 = time.perf_counter()
+    done = 0
+    for t in thetas[1:]:
+        model.lnprob(t)
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": n * done / dt, "unit": "terms/s", "cores": 1, "kind": "port",
+            "sample": "oracle/lf_oracle.py (NumPy restatement, bit-identical to the reference on the golden "
+                      "fixtures), serial as the reference runs emcee: %d sources (1/%d of rank 0's shard, every field) "
+                      "x %d walkers in %.1f s" % (n, max(1, round(len(inp_full['lum']) / n)), done, dt)}
+
+
+_POOL_STATE = {}
+
+
+def _pool_eval(theta):
+    return _POOL_STATE['model'].lnprob(theta)
+
+
+def run_reference(args):
+    """Reference arm: the reference's own algorithm (NumPy oracle port; the Python reference cannot travel to the
+    GPU box) on all host cores, walkers fanned out over a fork pool."""
+    import multiprocessing as mp
+    from oracle import lf_oracle
+    from lumfuncmcmc_b200 import synth
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = min(cores, 64)
+    n_sample = 250000
+    inp = build_inputs(n_sample, args.kind, seed=1000)
+    W = 8 * procs
+    thetas = synth.draw_thetas(inp, args.kind, W, seed=7, mode='near', scale=0.02)
+    _POOL_STATE['model'] = lf_oracle.make_model(inp, args.kind)
+    ctx = mp.get_context('fork')
+    with ctx.Pool(procs) as pool:
+        for _ in range(args.warmup):
+            pool.map(_pool_eval, list(thetas), chunksize=2)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_pool_eval, list(thetas), chunksize=2)
+        dt = time.perf_counter() - t0
+    value = n_sample * W * args.steps / dt
+    sample = ("%d sources x %d walkers per step (bounded sample of the %g x %d workload), fork Pool(%d) over walkers"
+              % (n_sample, W, args.nsources, args.walkers, procs))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "terms/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "terms/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    return ("lnprob throughput: %s-completeness model, %g sources per GPU x %d walkers, FP64 "
+            "(BASELINE.json configs[1]; source-sharded over GPUs as configs[4])" %
+            (args.kind, args.nsources, args.walkers))
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if rank == 0:
+        __graft_entry__.build()
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+        dist.barrier()
+    from lumfuncmcmc_b200 import synth
+    from lumfuncmcmc_b200.dist import ShardedLikelihood
+
+    n = int(args.nsources)
+    W = args.walkers
+    inp = build_inputs(n, args.kind, seed=1000 + rank)        # this rank's shard
+    like = ShardedLikelihood(inp, args.kind, device=local_rank)
+    eng = like.engine
+    mode = 'prior' if args.prior_draws else 'near'
+    thetas = synth.draw_thetas(inp, args.kind, W, seed=7, mode=mode, scale=0.02)     # same on every rank
+    d_th = torch.from_numpy(thetas).cuda()
+    d_out = torch.empty(W, dtype=torch.float64, device='cuda')
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # live FP64-pipe peak of this GPU (roofline denominator; not in MEASURED_PEAKS.json)
+    peak_dfma, _ = eng.fp64_peak(100000)
+
+    # ---- device-resident timing ------------------------------------------------------------------
+    for _ in range(max(3, args.warmup)):
+        like.lnprob_device(d_th, d_out)
+    sync_all()
+    launches0 = eng.last_call_info()['launches']
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for _ in range(args.steps):
+        like.lnprob_device(d_th, d_out)
+    ev1.record()
+    sync_all()
+    clocks = sampler.stop()
+    ms_dev = ev0.elapsed_time(ev1)
+    info = eng.last_call_info()
+    launches = info['launches'] - launches0
+    result_dev = d_out.cpu().numpy()
+
+    # ---- end to end through the public host API ----------------------------------------------------
+    for _ in range(2):
+        like.lnprob(thetas)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        result_e2e = like.lnprob(thetas)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    assert np.array_equal(result_e2e, result_dev, equal_nan=True)
+
+    t = torch.tensor([ms_dev, t_e2e * 1e3], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+
+    if rank == 0:
+        terms_per_step = float(n) * world * W
+        value = terms_per_step * args.steps / (ms_dev * 1e-3)
+        e2e_value = terms_per_step * args.steps / (ms_e2e * 1e-3)
+        per_gpu = value / world
+        step_s = ms_dev * 1e-3 / args.steps
+        hbm_peak = 6452.8
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs']
+            hbm_src = 'MEASURED_PEAKS.json'
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, 'fallback'
+        alg_bytes = n * BYTES_PER_SOURCE + W * like.ndim * 8 + W * 8
+        achieved_tf = per_gpu * FP64_INSTR_PER_TERM * 2 / 1e12
+        peak_tf = peak_dfma * 2 / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": "terms/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args), "kind": args.kind, "sources_per_gpu": n, "walkers": W,
+                       "ndim": like.ndim, "nfields": eng.nfields, "size_ln": eng.size_ln,
+                       "walker_draws": mode, "walker_classes_last_step": info,
+                       "l2": "source arrays (%.0f MB per GPU) exceed the 126 MB L2; no flush needed" % (n * 16 / 1e6)
+                       if n * 16 > 126e6 else "inputs fit in L2 (resident by design: re-swept by every walker group)",
+                       "parallelism": "sources sharded x%d, walkers replicated, NCCL all-reduce of %d B/step" % (world, W * 8)},
+            "e2e": {"value": e2e_value, "unit": "terms/s", "h2d_bytes_per_step": W * like.ndim * 8,
+                    "d2h_bytes_per_step": W * 8, "ms_per_step": ms_e2e / args.steps,
+                    "timing": "host wall clock around ShardedLikelihood.lnprob (pinned theta H2D, kernels, all-reduce, D2H, sync), max over ranks"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf, "traffic": None,
+                         "note": "FP64-FMA-pipe bound kernel k_main<false>: achieved = terms/s/GPU x %d FP64-pipe "
+                                 "instr/term x 2 FLOP; peak = register-only DFMA rate measured live on this GPU "
+                                 "(lf_fp64_peak: %.3e DFMA/s) x 2 FLOP" % (FP64_INSTR_PER_TERM, peak_dfma),
+                         "hbm": {"achieved": alg_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": alg_bytes / step_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                                 "algorithmic_bytes_per_step": alg_bytes}},
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_serial(inp, args.kind, thetas)
+        print(json.dumps(line))
+    like.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -12,7 +12,7 @@ LF_MODEL_FREE, LF_MODEL_FIXED, LF_MODEL_Z = 0, 1, 2
 LF_PREC_F64, LF_PREC_F32 = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'liblfengine.so')
+LIB_PATH = os.environ.get('LF_ENGINE_LIB', os.path.join(_HERE, 'csrc', 'liblfengine.so'))
 
 #: every symbol include/lf_engine.h declares (checked by tests/test_abi.py)
 EXPORTS = ['lf_ndim', 'lf_create', 'lf_destroy', 'lf_set_sources', 'lf_set_grid', 'lf_set_quadrature_share',

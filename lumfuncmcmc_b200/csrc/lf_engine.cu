@@ -78,7 +78,7 @@ struct FieldStats {          // per-field sufficient statistics and ranges of th
 };
 
 // 16-byte aligned so a point is fetched with LDG.128s
-struct __align__(16) QuadPointFree { double g, f, x, Lx, wt, pad; };   // log10 flux, flux, logL, 10^logL, trapezoid*volume*area weight
+struct __align__(16) QuadPointFree { double g, f, x, Lx, wt, ftrue; };   // log10 flux, flux, logL, 10^logL, trapezoid*volume*area weight
 struct __align__(16) QuadPoint { double x, Lx, wt, pad; };             // FIXED / Z (weight carries integ_part)
 
 struct KArgs {
@@ -91,6 +91,7 @@ struct KArgs {
     long long field_ind[LF_MAX_FIELDS + 1];
     FieldStats fs[LF_MAX_FIELDS];
     double lum_max_all;
+    double fcap;                       // cap of the flux copy used in the decay argument (see k_derive_free)
     // resident arrays
     const double2* src2;               // FREE: (log10 flux, flux)   Z: (lum, z)
     const double* lum;
@@ -108,7 +109,7 @@ struct KArgs {
     double* wp;
     double* colA;                      // Z: per (column, walker) ln-amplitude  [K? no: S][Wcap]
     double* colB;                      // Z: per (column, walker) 10^-L*(z_col)
-    int* cls_count;                    // [3]
+    int* cls_count;                    // [0..2] walkers per class, [3] / [4] work-item counters of k_main<fast/literal>
     int* list_fast;
     int* list_lit;
     double* partial;                   // [rows][Wcap]
@@ -261,6 +262,7 @@ __global__ void k_prologue(KArgs a) {
                 double fmn = fmin(s.n > 0.0 ? s.f_min : 1.0e300, s.grid_f_min);
                 if (!(alpha_c * (gmin - lgF) > N_MIN_SAFE)) range_ok = false;
                 if (a.modified && !(fmn / ftau > X_MIN_SAFE)) range_ok = false;
+                if (a.modified && !(a.fcap / ftau < 1.0e7)) range_ok = false;      // exp range reduction stays in int32
                 if (s.n > 0.0) tmin = log(fleming_literal(s.f_min, F50, alpha_c, ftau, a.modified != 0));
                 lnom = s.ln_om0;
             }
@@ -305,7 +307,13 @@ __global__ void k_zcolumns(KArgs a) {
 // ------------------------------------------------------------------------------------------------
 // main kernels: grid of warp work items = (walker group of 32) x (slab of sources | slab of quadrature points)
 // ------------------------------------------------------------------------------------------------
-#define WARPS_PER_BLOCK 8
+#ifndef LF_WARPS_PER_BLOCK
+#define LF_WARPS_PER_BLOCK 8
+#endif
+#ifndef LF_MIN_BLOCKS
+#define LF_MIN_BLOCKS 2
+#endif
+#define WARPS_PER_BLOCK LF_WARPS_PER_BLOCK
 #define BLOCK_THREADS (32 * WARPS_PER_BLOCK)
 
 __device__ __forceinline__ int field_of(const KArgs& a, long long i) {
@@ -315,7 +323,7 @@ __device__ __forceinline__ int field_of(const KArgs& a, long long i) {
 }
 
 template <bool LITERAL>
-__global__ void __launch_bounds__(BLOCK_THREADS, 2) k_main(KArgs a) {
+__global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) {
     __shared__ double s_exp[EXP_TAB_N * EXP_TAB_REP];
     __shared__ double2 s_log[LOG_TAB_N * LOG_TAB_REP];
     const int cls = LITERAL ? CLS_LIT : CLS_FAST;
@@ -324,23 +332,29 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_main(KArgs a) {
     if (n_wg == 0) return;
     const int rows = a.n_src_slabs + a.n_quad_slabs;
     const long long n_items = (long long)n_wg * rows;
-    if ((long long)blockIdx.x * WARPS_PER_BLOCK >= n_items) return;
     if (!LITERAL) {
         load_tables(a.tables, s_exp, s_log);
         __syncthreads();
     }
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long item = (long long)blockIdx.x * WARPS_PER_BLOCK + warp;
-    if (item >= n_items) return;
+    // persistent warps: every warp pulls (walker group, slab) items from a global counter until none are left.
+    // Items are small (tens per warp slot), so SMs finish within one item of each other (no wave tail), and each
+    // item owns its own partial[] row, so the result does not depend on which warp ran it.
+    const int lane = threadIdx.x & 31;
+    const int rep16 = lane & 15, rep8 = lane & 7;
+    const long long WS = a.Wcap;
+    const int* list = LITERAL ? a.list_lit : a.list_fast;
+    int* counter = a.cls_count + (LITERAL ? 4 : 3);
+  for (;;) {
+    long long item = 0;
+    if (lane == 0) item = atomicAdd(counter, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= n_items) break;
     const int wg = (int)(item % n_wg);
     const int row = (int)(item / n_wg);
     const int slot = wg * 32 + lane;
     const bool active = slot < count;
-    const int* list = LITERAL ? a.list_lit : a.list_fast;
     const long long w = list[active ? slot : count - 1];       // inactive lanes shadow a valid walker
-    const long long WS = a.Wcap;
     const double* wp = a.wp + w;
-    const int rep16 = lane & 15, rep8 = lane & 7;
     double acc0 = 0.0, acc1 = 0.0;
 
     if (row < a.n_src_slabs) {
@@ -355,16 +369,28 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_main(KArgs a) {
                     const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], cinv = wp[(P_FIELD0 + 4 * k + 1) * WS];
                     long long i = i0;
                     if (a.modified) {
-                        for (; i + 1 < seg_end; i += 2) {
-                            double2 s0 = __ldg(&a.src2[i]), s1 = __ldg(&a.src2[i + 1]);
+                        // 32-bit trip counter; four sources per trip as two independent pairs (two FP64 dependency
+                        // chains in flight per thread), each pair loaded one half-trip ahead of its use
+                        const double2* __restrict__ ps = a.src2 + i;
+                        const int cnt = (int)(seg_end - i);
+                        auto pair = [&](const double2& u0, const double2& u1) {
                             double lg0, rd0, lg1, rd1;
-                            fleming_log_parts<true>(s0.x, s0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
-                            fleming_log_parts<true>(s1.x, s1.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg1, rd1);
+                            fleming_log_parts<true>(u0.x, u0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            fleming_log_parts<true>(u1.x, u1.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg1, rd1);
                             acc0 = fma(lg0, rd0, acc0);
                             acc1 = fma(lg1, rd1, acc1);
+                        };
+                        int j = 0;
+                        double2 A0 = make_double2(0.0, 1.0), A1 = A0, B0 = A0, B1 = A0;
+                        if (cnt >= 4) { A0 = __ldg(ps); A1 = __ldg(ps + 1); }
+                        for (; j + 4 <= cnt; j += 4) {
+                            B0 = __ldg(ps + j + 2); B1 = __ldg(ps + j + 3);
+                            pair(A0, A1);
+                            if (j + 8 <= cnt) { A0 = __ldg(ps + j + 4); A1 = __ldg(ps + j + 5); }
+                            pair(B0, B1);
                         }
-                        if (i < seg_end) {
-                            double2 s0 = __ldg(&a.src2[i]);
+                        for (; j < cnt; ++j) {
+                            double2 s0 = __ldg(ps + j);
                             double lg0, rd0;
                             fleming_log_parts<true>(s0.x, s0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
                             acc0 = fma(lg0, rd0, acc0);
@@ -459,7 +485,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_main(KArgs a) {
                         for (long long q = q0; q < seg_end; ++q) {                    // lumfuncmcmc.py:375-376
                             const QuadPointFree* pt = &a.qpf[q];
                             double y = schechter_literal(__ldg(&pt->x), sal, Lstar, phistar) *
-                                       fleming_literal(__ldg(&pt->f), F50, alpha, ftau, a.modified != 0);
+                                       fleming_literal(__ldg(&pt->ftrue), F50, alpha, ftau, a.modified != 0);
                             acc0 = fma(__ldg(&pt->wt), y, acc0);
                         }
                     }
@@ -513,6 +539,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, 2) k_main(KArgs a) {
         }
     }
     if (active) a.partial[(long long)row * WS + w] = acc0 + acc1;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -539,11 +566,13 @@ __global__ void k_finish(KArgs a) {
 // set-up kernels: derived per-source arrays and per-field statistics
 // ------------------------------------------------------------------------------------------------
 __global__ void k_derive_free(long long n, const double* __restrict__ lum, const double* __restrict__ flux,
-                              double2* __restrict__ src2, double* __restrict__ Lsrc) {
+                              double2* __restrict__ src2, double* __restrict__ Lsrc, double fcap) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double f = flux[i];
-    src2[i] = make_double2(log10(f), f);
+    // the decay argument f/ftau only matters below ~46 (exp(-46) = 1e-20 against 1) and ftau < F50 <= prior
+    // maximum, so the flux copy used for it is capped at 64 x that maximum: bit-identical results, bounded range
+    src2[i] = make_double2(log10(f), fmin(f, fcap));
     Lsrc[i] = pow(10.0, lum[i]);
 }
 __global__ void k_derive_z(long long n, const double* __restrict__ lum, const double* __restrict__ z,
@@ -697,6 +726,7 @@ __global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, doubl
 struct lf_ctx {
     lf_config cfg;
     int device = 0, sm_count = 148;
+    int occ_fast = 2, occ_lit = 2;     // resident blocks per SM of the persistent main kernels
     int ndim = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -765,7 +795,11 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     fill_tables(t);
     CK(cudaMalloc(&c->d_tables, sizeof(Tables)));
     CK(cudaMemcpy(c->d_tables, &t, sizeof(Tables), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&c->d_cls, 4 * sizeof(int)));
+    CK(cudaMalloc(&c->d_cls, 8 * sizeof(int)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_fast, k_main<false>, BLOCK_THREADS, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lit, k_main<true>, BLOCK_THREADS, 0));
+    if (c->occ_fast < 1) c->occ_fast = 1;
+    if (c->occ_lit < 1) c->occ_lit = 1;
     memset(&c->ka, 0, sizeof(KArgs));
     KArgs& a = c->ka;
     a.model = cfg->model; a.K = cfg->nfields; a.S = cfg->size_ln; a.fix_sch_al = cfg->fix_sch_al;
@@ -783,6 +817,7 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     }
     a.z1 = cfg->z_pivots[0]; a.z2 = cfg->z_pivots[1]; a.z3 = cfg->z_pivots[2];
     a.share = 0; a.nshare = 1;
+    a.fcap = 64.0e-17 * cfg->Flim_lims[1];
     a.tables = c->d_tables;
     *out = c;
     return 0;
@@ -877,7 +912,7 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
             CK(cudaMalloc(&c->d_flux, nb));
             CK(cudaMalloc(&c->d_src2, sizeof(double2) * (size_t)n));
             CK(cudaMemcpyAsync(c->d_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
-            k_derive_free<<<G, T, 0, c->stream>>>(n, c->d_lum, c->d_flux, c->d_src2, c->d_Lsrc);
+            k_derive_free<<<G, T, 0, c->stream>>>(n, c->d_lum, c->d_flux, c->d_src2, c->d_Lsrc, c->ka.fcap);
         } else {
             CK(cudaMalloc(&c->d_om, nb));
             CK(cudaMemcpyAsync(c->d_om, om_arr, nb, cudaMemcpyHostToDevice, c->stream));
@@ -890,6 +925,7 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
             }
         }
         CK(cudaGetLastError());
+        bool took = false;
         for (int k = 0; k < K; ++k) {
             FieldStats& s = a.fs[k];
             long long i0 = field_ind[k], i1 = field_ind[k + 1];
@@ -901,7 +937,7 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
             if (range_stats(c, c->d_Lsrc, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
             s.sum_L = sm;
             if (model == LF_MODEL_FREE) {
-                k_take<<<G, T, 0, c->stream>>>(n, c->d_src2, 0, d_scratch);
+                if (!took) { k_take<<<G, T, 0, c->stream>>>(n, c->d_src2, 0, d_scratch); took = true; }
                 if (range_stats(c, d_scratch, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
                 s.g_min = mn;
                 if (range_stats(c, c->d_flux, i0, i1, d_tmp, h_tmp, sm, mn, mx)) return 1;
@@ -970,10 +1006,11 @@ extern "C" int lf_set_grid(lf_ctx* c, const double* logL, const double* zarr, co
                     p.Lx = pow(10.0, x);
                     p.f = p.Lx / den;                                   // lumfuncmcmc.py:69-70
                     p.g = log10(p.f);
+                    p.ftrue = p.f;
+                    p.f = std::min(p.f, a.fcap);                        // decay-argument copy, see k_derive_free
                     p.wt = wl * wz[i] * volume_part[i] * (omega0[k] / SQARCSEC);
-                    p.pad = 0.0;
                     gmin = std::min(gmin, p.g);
-                    fmin_ = std::min(fmin_, p.f);
+                    fmin_ = std::min(fmin_, p.ftrue);
                 }
             }
             a.fs[k].grid_g_min = gmin;
@@ -1048,7 +1085,7 @@ static int ensure_scratch(lf_ctx* c, long long W, int rows) {
 // choose slab counts so that one class fills the machine with a few waves of warp items
 static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
     const long long n_wg = (W + 31) / 32;
-    const long long target_items = (long long)c->sm_count * 16 * 4;
+    const long long target_items = (long long)c->sm_count * 16 * 24;   // ~24 items per resident warp
     long long rows = std::max<long long>(1, target_items / n_wg);
     const int model = c->cfg.model;
     // relative cost of a quadrature point vs a source term
@@ -1076,7 +1113,7 @@ static int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, doubl
     a.wp = c->d_wp; a.colA = c->d_colA; a.colB = c->d_colB;
     a.cls_count = c->d_cls; a.list_fast = c->d_list_fast; a.list_lit = c->d_list_lit;
     a.partial = c->d_partial; a.n_src_slabs = n_src; a.n_quad_slabs = n_quad;
-    CK(cudaMemsetAsync(c->d_cls, 0, 4 * sizeof(int), st));
+    CK(cudaMemsetAsync(c->d_cls, 0, 8 * sizeof(int), st));
     const int T = 128;
     k_prologue<<<(unsigned)((W + T - 1) / T), T, 0, st>>>(a);
     c->launches++;
@@ -1087,9 +1124,11 @@ static int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, doubl
     }
     const long long n_wg = (W + 31) / 32;
     const long long items = n_wg * (n_src + n_quad);
-    const unsigned blocks = (unsigned)((items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK);
-    k_main<false><<<blocks, BLOCK_THREADS, 0, st>>>(a);
-    k_main<true><<<blocks, BLOCK_THREADS, 0, st>>>(a);
+    const long long need = (items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;      // never more blocks than items
+    const unsigned bf = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_fast);
+    const unsigned bl = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_lit);
+    k_main<false><<<bf, BLOCK_THREADS, 0, st>>>(a);
+    k_main<true><<<bl, BLOCK_THREADS, 0, st>>>(a);
     k_finish<<<(unsigned)((W + T - 1) / T), T, 0, st>>>(a);
     c->launches += 3;
     CK(cudaGetLastError());

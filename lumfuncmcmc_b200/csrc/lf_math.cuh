@@ -28,6 +28,24 @@ constexpr double MPC_CM_REF = 3.086e24;                             // the refer
 constexpr int EXP_TAB_N = 64, EXP_TAB_REP = 16;   // doubles:  64*16*8  =  8 KB
 constexpr int LOG_TAB_N = 256, LOG_TAB_REP = 8;   // double2: 256*8*16  = 32 KB
 
+// polynomial / reduction constants live in the constant bank: DFMA reads them as c[3][off] operands, which keeps
+// the inner loop free of the IMAD.MOV/UMOV pairs ptxas otherwise emits to materialise 64-bit immediates
+__constant__ double KC[16] = {
+    64.0 * LOG2E,          // 0
+    -LN2 / 64.0,           // 1
+    1.0 / 120.0,           // 2
+    1.0 / 24.0,            // 3
+    1.0 / 6.0,             // 4
+    LN2,                   // 5
+    0.2,                   // 6
+    1.0 / 3.0,             // 7
+    4503601774854144.0,    // 8   2^52 + 2^31
+    MAGIC52,               // 9
+    -0x1.62e42fefa38p-7,   // 10  -(ln2/64) high part
+    -0x1.ef35793c7673p-51, // 11  -(ln2/64) low part
+    LN10,                  // 12
+    0.0, 0.0, 0.0};
+
 struct Tables {                 // device-global master copies (filled by the host at lf_create)
     double exp2_frac[EXP_TAB_N];        // 2^(j/64)
     double2 log_tab[LOG_TAB_N];         // (invc_j, -log(invc_j)),  c_j = 1 + (j+0.5)/256
@@ -58,18 +76,19 @@ __device__ __forceinline__ void load_tables(const Tables* __restrict__ t, double
     for (int i = threadIdx.x; i < LOG_TAB_N * LOG_TAB_REP; i += blockDim.x) s_log[i] = t->log_tab[i / LOG_TAB_REP];
 }
 
-// exp(x) - 1 pieces for x in [-46, 0]:  returns Ts = 2^K * 2^(j/64) and q = expm1(r), exp(x) = Ts*(1+q)
+// exp(x) - 1 pieces for x in (-2e7, 0]:  returns Ts = 2^K * 2^(j/64) and q = expm1(r), exp(x) = Ts*(1+q)
 // 1 reduction FMA suffices here because only ABSOLUTE accuracy of exp(x) <= 1 is needed.
 // FP64 instructions: 3 (t, kf, r) + 5 (q)
 __device__ __forceinline__ void exp_neg_parts(double x, const double* s_exp, int rep, double& Ts, double& q) {
-    double t = fma(x, 64.0 * LOG2E, MAGIC52);
+    double t = fma(x, KC[0], KC[9]);
     int k = __double2loint(t);
-    double kf = t - MAGIC52;
-    double r = fma(kf, -LN2 / 64.0, x);
+    double kf = t - KC[9];
+    double r = fma(kf, KC[1], x);
     double T = s_exp[(k & 63) * EXP_TAB_REP + rep];
-    Ts = __hiloint2double(__double2hiint(T) + ((k >> 6) << 20), __double2loint(T));
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(r, p, 1.0 / 6.0);
+    int K = max(k >> 6, -1000);                 // exp(x) < 2^-1000 is 0 against 1; keeps the exponent field valid
+    Ts = __hiloint2double(__double2hiint(T) + (K << 20), __double2loint(T));
+    double p = fma(r, KC[2], KC[3]);
+    p = fma(r, p, KC[4]);
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
     q = p * r;
@@ -78,20 +97,17 @@ __device__ __forceinline__ void exp_neg_parts(double x, const double* s_exp, int
 // full-range exp(x) with RELATIVE accuracy for x in [-708, 709]; below -708 returns 0.
 // FP64 instructions: 4 (t, kf, r hi, r lo) + 5 (q) + 1 (Ts*q+Ts)
 __device__ __forceinline__ double exp_full(double x, const double* s_exp, int rep) {
-    // clamp through the integer pipe: x < -708 -> result forced to 0 at the end
     bool under = x < -708.0;
     x = under ? -708.0 : x;
-    double t = fma(x, 64.0 * LOG2E, MAGIC52);
+    double t = fma(x, KC[0], KC[9]);
     int k = __double2loint(t);
-    double kf = t - MAGIC52;
-    constexpr double C_HI = 0x1.62e42fefa38p-7;            // ln2/64 with 11 trailing zero bits
-    constexpr double C_LO = 0x1.ef35793c7673p-51;         // ln2/64 - C_HI
-    double r = fma(kf, -C_HI, x);
-    r = fma(kf, -C_LO, r);
+    double kf = t - KC[9];
+    double r = fma(kf, KC[10], x);
+    r = fma(kf, KC[11], r);
     double T = s_exp[(k & 63) * EXP_TAB_REP + rep];
     double Ts = __hiloint2double(__double2hiint(T) + ((k >> 6) << 20), __double2loint(T));
-    double p = fma(r, 1.0 / 120.0, 1.0 / 24.0);
-    p = fma(r, p, 1.0 / 6.0);
+    double p = fma(r, KC[2], KC[3]);
+    p = fma(r, p, KC[4]);
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
     double q = p * r;
@@ -107,10 +123,10 @@ __device__ __forceinline__ double log_fast(double v, const double2* s_log, int r
     double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, lo);
     double2 tb = s_log[j * LOG_TAB_REP + rep];
     double eps = fma(m, tb.x, -1.0);
-    double Ed = __hiloint2double(0x43300000, E ^ 0x80000000) - 4503601774854144.0;   // int -> double
-    double base = fma(Ed, LN2, tb.y);
-    double a = fma(eps, 0.2, -0.25);
-    a = fma(eps, a, 1.0 / 3.0);
+    double Ed = __hiloint2double(0x43300000, E ^ 0x80000000) - KC[8];   // int -> double
+    double base = fma(Ed, KC[5], tb.y);
+    double a = fma(eps, KC[6], -0.25);
+    a = fma(eps, a, KC[7]);
     a = fma(eps, a, -0.5);
     a = fma(eps, a, 1.0);
     return fma(eps, a, base);
@@ -138,9 +154,7 @@ __device__ __forceinline__ void fleming_log_parts(double g, double f, double alp
     double fc = fma(0.5, q, 0.5);
     lg = log_fast(fc, s_log, rep8);
     if (MODIFIED) {
-        double x = f * cinv;                                  // <= 0
-        // clamp x >= -46 on the integer pipe (exp(-46) = 1e-20 is already 0 against 1)
-        if ((unsigned)__double2hiint(x) > 0xC0470000u) x = -46.0;
+        double x = f * cinv;                                  // <= 0; |x| < 2e7 guaranteed by the classifier
         double Ts, qx;
         exp_neg_parts(x, s_exp, rep16, Ts, qx);
         double omT = 1.0 - Ts;
