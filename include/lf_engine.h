@@ -91,6 +91,10 @@ int lf_set_grid(lf_ctx* ctx, const double* logL, const double* zarr, const doubl
  * summed (all-reduce) to give lnprob. */
 int lf_set_quadrature_share(lf_ctx* ctx, int32_t share, int32_t nshare);
 
+/* enabled = 1 (default): lf_lnprob_* returns -inf outside the prior box (lnprob).  enabled = 0: the prior is
+ * not consulted, i.e. the call evaluates lnlike() at the given parameters (lumfuncmcmc.py:360-393). */
+int lf_set_prior_gate(lf_ctx* ctx, int32_t enabled);
+
 /* Batched log-posterior, HOST buffers: thetas[W][ndim] -> out[W].  Includes H2D, kernels, D2H, sync. */
 int lf_lnprob_batch(lf_ctx* ctx, const double* thetas, int64_t W, double* out);
 
@@ -110,6 +114,12 @@ int lf_veff_bin(lf_ctx* ctx, int64_t n, const double* flux, const double* lum, c
                 int32_t nfields, const double* flim, double alpha, double fcmin, double sum_omega,
                 double vol_int, const double* vol_per_source, const uint8_t* valid_or_null,
                 const double* edges, int32_t nbins, double* phi_out, int64_t* counts, double* sumphi);
+
+/* Bin caller-provided weights: counts[j], sumphi[j] of (lum_i, phi_i) over [edges[j], edges[j+1]); keeps lum/phi
+ * resident for lf_boot_bin.  This is the original-sample pass of V.getBootErrLog when phi is an input
+ * (VmaxLumFunc.py:345-350). */
+int lf_bin_weights(lf_ctx* ctx, int64_t n, const double* lum, const double* phi, const double* edges,
+                   int32_t nbins, int64_t* counts, double* sumphi);
 
 /* One bootstrap replicate on the resident sample: mult[i] = how many times source i was drawn.
  * sumphi[j] = sum_i mult[i] * phi_i over bin j; counts[j] = sum_i mult[i]. */

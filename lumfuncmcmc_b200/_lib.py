@@ -15,8 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('LF_ENGINE_LIB', os.path.join(_HERE, 'csrc', 'liblfengine.so'))
 
 #: every symbol include/lf_engine.h declares (checked by tests/test_abi.py)
-EXPORTS = ['lf_ndim', 'lf_create', 'lf_destroy', 'lf_set_sources', 'lf_set_grid', 'lf_set_quadrature_share',
-           'lf_lnprob_batch', 'lf_lnprob_batch_device', 'lf_last_call_info', 'lf_veff_bin', 'lf_boot_bin',
+EXPORTS = ['lf_ndim', 'lf_create', 'lf_destroy', 'lf_set_sources', 'lf_set_grid', 'lf_set_quadrature_share', 'lf_set_prior_gate',
+           'lf_lnprob_batch', 'lf_lnprob_batch_device', 'lf_last_call_info', 'lf_veff_bin', 'lf_bin_weights', 'lf_boot_bin',
            'lf_fp64_peak', 'lf_last_kernel_ms', 'lf_last_error', 'lf_version']
 
 
@@ -54,11 +54,13 @@ def load():
     lib.lf_set_sources.argtypes = [vp, i64, vp, vp, vp, vp, vp, vp]
     lib.lf_set_grid.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.lf_set_quadrature_share.argtypes = [vp, C.c_int32, C.c_int32]
+    lib.lf_set_prior_gate.argtypes = [vp, C.c_int32]
     lib.lf_lnprob_batch.argtypes = [vp, vp, i64, vp]
     lib.lf_lnprob_batch_device.argtypes = [vp, vp, i64, vp, vp]
     lib.lf_last_call_info.argtypes = [vp, ip, ip]
     lib.lf_veff_bin.argtypes = [vp, i64, vp, vp, vp, C.c_int32, vp, C.c_double, C.c_double, C.c_double, C.c_double,
                                 vp, vp, vp, C.c_int32, vp, vp, vp]
+    lib.lf_bin_weights.argtypes = [vp, i64, vp, vp, vp, C.c_int32, vp, vp]
     lib.lf_boot_bin.argtypes = [vp, vp, vp, vp]
     lib.lf_fp64_peak.argtypes = [vp, C.c_int32, dp, dp]
     lib.lf_last_kernel_ms.argtypes = [vp, dp]

@@ -82,7 +82,7 @@ struct __align__(16) QuadPointFree { double g, f, x, Lx, wt, ftrue; };   // log1
 struct __align__(16) QuadPoint { double x, Lx, wt, pad; };             // FIXED / Z (weight carries integ_part)
 
 struct KArgs {
-    int model, K, S, fix_sch_al, fixed_prior_ok, force_literal, modified;
+    int model, K, S, fix_sch_al, fixed_prior_ok, force_literal, modified, prior_gate;
     int ndim;
     double fcmin, fcA2;                // fcA2 = |a/(1-a)|, a = (2 fcmin - 1)^2        (VmaxLumFunc.py:164-165)
     double sch_al;
@@ -170,6 +170,7 @@ __global__ void k_prologue(KArgs a) {
     const double NINF = neg_inf();
     int cls = CLS_FAST;
     bool ok = a.fixed_prior_ok != 0;
+    const bool gate = a.prior_gate != 0;      // lnlike() (no prior) vs lnprob()
 
     if (a.model == LF_MODEL_Z) {
         double L1 = th[0], L2 = th[1], L3 = th[2], p1 = th[3], p2 = th[4], p3 = th[5];
@@ -178,7 +179,7 @@ __global__ void k_prologue(KArgs a) {
         if (!a.fix_sch_al) ok = ok && in_box(sal, a.sch_al_lims);
         ok = ok && in_box_strict(L1, a.Lstar_lims) && in_box_strict(L2, a.Lstar_lims) && in_box_strict(L3, a.Lstar_lims);
         ok = ok && in_box_strict(p1, a.phistar_lims) && in_box_strict(p2, a.phistar_lims) && in_box_strict(p3, a.phistar_lims);
-        if (!ok) { a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return; }
+        if (gate && !ok) { a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return; }
         double aL, bL, cL, aP, bP, cP;
         quad_coef(L1, L2, L3, a.z1, a.z2, a.z3, aL, bL, cL);
         quad_coef(p1, p2, p3, a.z1, a.z2, a.z3, aP, bP, cP);
@@ -228,7 +229,7 @@ __global__ void k_prologue(KArgs a) {
             alpha_c = th[p + K];
             ok = ok && in_box(alpha_c, a.alpha_lims);
         }
-        if (!ok) { a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return; }
+        if (gate && !ok) { a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return; }
         // certain underflow: exp(-10^(lum_max - L*)) == 0 makes Phi == 0 for the brightest source
         if (exp(-pow(10.0, a.lum_max_all - Lstar)) == 0.0 && a.N > 0) {
             a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return;
@@ -651,8 +652,11 @@ __device__ __forceinline__ int bin_of(double L, const double* e, int nb) {
     return j;
 }
 
-template <bool BOOT>
+// MODE 0: compute phi from the completeness and bin; MODE 1: bootstrap replicate (multiplicities) on resident
+// lum/phi; MODE 2: bin caller-provided (resident) phi
+template <int MODE>
 __global__ void __launch_bounds__(256) k_veff(VeffArgs a) {
+    constexpr bool BOOT = MODE == 1;
     extern __shared__ unsigned char smem_raw[];
     double* s_edges = reinterpret_cast<double*>(smem_raw);                 // nbins+1
     double* s_sum = s_edges + (a.nbins + 1);                               // 8 warps x nbins
@@ -667,6 +671,8 @@ __global__ void __launch_bounds__(256) k_veff(VeffArgs a) {
         if (BOOT) {
             m = (unsigned long long)a.mult[i];
             if (m == 0ULL) continue;
+            phi = a.phi[i];
+        } else if (MODE == 2) {
             phi = a.phi[i];
         } else {
             int k = 0;
@@ -816,7 +822,7 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
         a.sch_al_lims[i] = cfg->sch_al_lims[i]; a.Flim_lims[i] = cfg->Flim_lims[i]; a.alpha_lims[i] = cfg->alpha_lims[i];
     }
     a.z1 = cfg->z_pivots[0]; a.z2 = cfg->z_pivots[1]; a.z3 = cfg->z_pivots[2];
-    a.share = 0; a.nshare = 1;
+    a.share = 0; a.nshare = 1; a.prior_gate = 1;
     a.fcap = 64.0e-17 * cfg->Flim_lims[1];
     a.tables = c->d_tables;
     *out = c;
@@ -1044,6 +1050,12 @@ extern "C" int lf_set_grid(lf_ctx* c, const double* logL, const double* zarr, co
     return 0;
 }
 
+extern "C" int lf_set_prior_gate(lf_ctx* c, int32_t enabled) {
+    if (!c) return fail("lf_set_prior_gate: null context");
+    c->ka.prior_gate = enabled ? 1 : 0;
+    return 0;
+}
+
 extern "C" int lf_set_quadrature_share(lf_ctx* c, int32_t share, int32_t nshare) {
     if (!c) return fail("lf_set_quadrature_share: null context");
     if (nshare < 1 || share < 0 || share >= nshare) return fail("lf_set_quadrature_share: need 0 <= share < nshare");
@@ -1257,7 +1269,7 @@ extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const doubl
     a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.vol_int = vol_int; a.modified = modified ? 1 : 0;
     a.edges = c->v_edges; a.nbins = nbins; a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = nullptr;
     size_t smem = sizeof(double) * (nbins + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * (size_t)nbins;
-    k_veff<false><<<blocks, 256, smem, c->stream>>>(a);
+    k_veff<0><<<blocks, 256, smem, c->stream>>>(a);
     k_veff_reduce<<<(nbins + 127) / 128, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
     c->launches += 2;
     CK(cudaGetLastError());
@@ -1268,6 +1280,42 @@ extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const doubl
     cudaFree(d_flux);
     if (d_vol) cudaFree(d_vol);
     if (d_valid) cudaFree(d_valid);
+    return 0;
+}
+
+extern "C" int lf_bin_weights(lf_ctx* c, int64_t n, const double* lum, const double* phi, const double* edges,
+                              int32_t nbins, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_bin_weights: null context");
+    if (n <= 0 || !lum || !phi || !edges || !counts || !sumphi) return fail("lf_bin_weights: bad arguments");
+    if (nbins < 1 || nbins > VEFF_MAX_BINS) return fail("lf_bin_weights: nbins out of range");
+    CK(cudaSetDevice(c->device));
+    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
+    dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult);
+    const size_t nb = sizeof(double) * (size_t)n;
+    CK(cudaMalloc(&c->v_lum, nb));
+    CK(cudaMalloc(&c->v_phi, nb));
+    CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
+    const int blocks = (int)std::min<long long>((long long)c->sm_count * 8, (n + 255) / 256);
+    c->v_blocks = blocks; c->v_nbins = nbins; c->vN = n;
+    CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)blocks * nbins));
+    CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)blocks * nbins));
+    CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
+    CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
+    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_phi, phi, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
+    VeffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = nbins;
+    a.counts = c->v_counts; a.sumphi = c->v_sums;
+    size_t smem = sizeof(double) * (nbins + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * (size_t)nbins;
+    k_veff<2><<<blocks, 256, smem, c->stream>>>(a);
+    k_veff_reduce<<<(nbins + 127) / 128, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    c->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
@@ -1284,7 +1332,7 @@ extern "C" int lf_boot_bin(lf_ctx* c, const int32_t* mult, int64_t* counts, doub
     a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult;
     const int nbins = c->v_nbins, blocks = c->v_blocks;
     size_t smem = sizeof(double) * (nbins + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * (size_t)nbins;
-    k_veff<true><<<blocks, 256, smem, c->stream>>>(a);
+    k_veff<1><<<blocks, 256, smem, c->stream>>>(a);
     k_veff_reduce<<<(nbins + 127) / 128, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
     c->launches += 2;
     CK(cudaGetLastError());

@@ -41,7 +41,73 @@ def source_flux(inp):
     return L / (4.0 * np.pi * (3.086e24 * DL) ** 2)
 
 
-class LikelihoodEngine:
+class _VeffOps:
+    """1/V_eff weights, binned LF and bootstrap replicates on a context (``self._ctx`` / ``self.lib``)."""
+
+    def veff_bin(self, flux, lum, field_ind, flim, alpha, fcmin, sum_omega, vol_int, edges, vol_per_source=None,
+                 valid=None, want_phi=True):
+        """1/V_eff weights and the binned LF of the original sample (reference lumfuncmcmc.py:515-525,
+        VmaxLumFunc.py:336-350).  Returns (phi or None, counts int64[nbins], sumphi float64[nbins])."""
+        flux, lum, edges, flim = _f64(flux), _f64(lum), _f64(edges), _f64(flim)
+        fi = np.ascontiguousarray(field_ind, dtype=np.int64)
+        n, nb = flux.shape[0], edges.shape[0] - 1
+        vps = None if vol_per_source is None else _f64(vol_per_source)
+        val = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
+        phi = np.empty(n, dtype=np.float64) if want_phi else None
+        self._veff_nbins = nb
+        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
+        _lib.check(self.lib.lf_veff_bin(self._ctx, n, _ptr(flux), _ptr(lum), _ptr(fi), len(flim), _ptr(flim),
+                                        float(alpha), float(fcmin) if fcmin else 0.0, float(sum_omega), float(vol_int),
+                                        _ptr(vps), _ptr(val), _ptr(edges), nb, _ptr(phi), _ptr(counts), _ptr(sums)),
+                   self.lib)
+        return phi, counts, sums
+
+    def boot_bin(self, mult):
+        """One bootstrap replicate on the sample left resident by :meth:`veff_bin`."""
+        mult = np.ascontiguousarray(mult, dtype=np.int32)
+        nb = self._nbins_resident()
+        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
+        _lib.check(self.lib.lf_boot_bin(self._ctx, _ptr(mult), _ptr(counts), _ptr(sums)), self.lib)
+        return counts, sums
+
+    def _nbins_resident(self):
+        return getattr(self, '_veff_nbins', 0)
+
+    def bin_weights(self, lum, phi, edges):
+        """Counts and sum of caller-provided weights per half-open bin (reference VmaxLumFunc.py:345-350)."""
+        lum, phi, edges = _f64(lum), _f64(phi), _f64(edges)
+        nb = edges.shape[0] - 1
+        self._veff_nbins = nb
+        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
+        _lib.check(self.lib.lf_bin_weights(self._ctx, lum.shape[0], _ptr(lum), _ptr(phi), _ptr(edges), nb,
+                                           _ptr(counts), _ptr(sums)), self.lib)
+        return counts, sums
+
+    def close(self):
+        if getattr(self, '_ctx', None) is not None and self._ctx.value:
+            self.lib.lf_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VeffEngine(_VeffOps):
+    """A bare context (no likelihood inputs) for the 1/V_eff kernels."""
+
+    def __init__(self, device=0):
+        self.lib = _lib.load()
+        cfg = _lib.LFConfig()
+        cfg.model, cfg.precision, cfg.device, cfg.nfields, cfg.size_ln = _lib.LF_MODEL_FREE, _lib.LF_PREC_F64, int(device), 1, 2
+        self._ctx = C.c_void_p()
+        _lib.check(self.lib.lf_create(C.byref(self._ctx), C.byref(cfg)), self.lib)
+        self.device = int(device)
+
+
+class LikelihoodEngine(_VeffOps):
     """One engine context on one GPU holding one shard of sources."""
 
     def __init__(self, inp, kind, device=0, force_literal=False, quadrature_share=(0, 1)):
@@ -121,6 +187,14 @@ class LikelihoodEngine:
     def set_quadrature_share(self, share, nshare):
         _lib.check(self.lib.lf_set_quadrature_share(self._ctx, int(share), int(nshare)), self.lib)
 
+    def lnlike(self, thetas):
+        """Like :meth:`lnprob` but without the prior gate (the reference's ``lnlike`` never consults the prior)."""
+        _lib.check(self.lib.lf_set_prior_gate(self._ctx, 0), self.lib)
+        try:
+            return self.lnprob(thetas)
+        finally:
+            _lib.check(self.lib.lf_set_prior_gate(self._ctx, 1), self.lib)
+
     def lnprob(self, thetas):
         """thetas: (ndim,) or (W, ndim) host array -> float or (W,) array.  H2D, kernels, D2H, sync."""
         th = np.asarray(thetas, dtype=np.float64)
@@ -163,44 +237,3 @@ class LikelihoodEngine:
         rate, ms = C.c_double(), C.c_double()
         _lib.check(self.lib.lf_fp64_peak(self._ctx, int(iters), C.byref(rate), C.byref(ms)), self.lib)
         return rate.value, ms.value
-
-    # ------------------------------------------------------------------------------------------
-    def veff_bin(self, flux, lum, field_ind, flim, alpha, fcmin, sum_omega, vol_int, edges, vol_per_source=None,
-                 valid=None, want_phi=True):
-        """1/V_eff weights and the binned LF of the original sample (reference lumfuncmcmc.py:515-525,
-        VmaxLumFunc.py:336-350).  Returns (phi or None, counts int64[nbins], sumphi float64[nbins])."""
-        flux, lum, edges, flim = _f64(flux), _f64(lum), _f64(edges), _f64(flim)
-        fi = np.ascontiguousarray(field_ind, dtype=np.int64)
-        n, nb = flux.shape[0], edges.shape[0] - 1
-        vps = None if vol_per_source is None else _f64(vol_per_source)
-        val = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
-        phi = np.empty(n, dtype=np.float64) if want_phi else None
-        self._veff_nbins = nb
-        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
-        _lib.check(self.lib.lf_veff_bin(self._ctx, n, _ptr(flux), _ptr(lum), _ptr(fi), len(flim), _ptr(flim),
-                                        float(alpha), float(fcmin) if fcmin else 0.0, float(sum_omega), float(vol_int),
-                                        _ptr(vps), _ptr(val), _ptr(edges), nb, _ptr(phi), _ptr(counts), _ptr(sums)),
-                   self.lib)
-        return phi, counts, sums
-
-    def boot_bin(self, mult):
-        """One bootstrap replicate on the sample left resident by :meth:`veff_bin`."""
-        mult = np.ascontiguousarray(mult, dtype=np.int32)
-        nb = self._nbins_resident()
-        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
-        _lib.check(self.lib.lf_boot_bin(self._ctx, _ptr(mult), _ptr(counts), _ptr(sums)), self.lib)
-        return counts, sums
-
-    def _nbins_resident(self):
-        return getattr(self, '_veff_nbins', 0)
-
-    def close(self):
-        if getattr(self, '_ctx', None) is not None and self._ctx.value:
-            self.lib.lf_destroy(self._ctx)
-            self._ctx = C.c_void_p()
-
-    def __del__(self):
-        try:
-            self.close()
-        except Exception:
-            pass

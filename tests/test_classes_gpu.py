@@ -1,0 +1,123 @@
+"""GPU: the drop-in classes end to end (constructor -> engine -> lnprob / fit_model / VeffLF) against the reference's
+golden values and the oracle."""
+import numpy as np
+import pytest
+
+from oracle import lf_oracle
+from tests.test_host_setup import _build
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def _check(got, ref):
+    assert np.array_equal(np.isneginf(got), np.isneginf(ref))
+    fin = np.isfinite(ref)
+    assert np.max(np.abs(got[fin] - ref[fin]) / np.abs(ref[fin])) <= RTOL
+
+
+@pytest.mark.parametrize('name,kind,args', [
+    ('free_k5_n2000', 'free', dict(n=2000, nfields=5, seed=11)),
+    ('free_k3_fixal', 'free', dict(n=900, nfields=3, seed=12, fix_sch_al=True)),
+    ('fixed_k2_n800', 'fixed', dict(n=800, nfields=2, seed=14)),
+    ('fixed_k2_fixal', 'fixed', dict(n=500, nfields=2, seed=15, fix_sch_al=True)),
+    ('z_k2_n800', 'z', dict(n=800, nfields=2, seed=16, evolve=(0.3, -0.2))),
+    ('z_k2_fixal', 'z', dict(n=500, nfields=2, seed=17, fix_sch_al=True)),
+])
+def test_class_lnprob_matches_reference(golden, name, kind, args):
+    g = golden(name)
+    m = _build(kind, **args)
+    fn = m.lnprob_fix_comp if kind == 'fixed' else m.lnprob
+    th, ref = g['thetas'], g['lnprob_ref']
+    _check(fn(th), ref)                                           # whole ensemble, one call
+    for i in (0, 3, len(th) - 1):                                 # scalar API: float, and self is updated
+        v = fn(th[i])
+        assert isinstance(v, float)
+        assert (np.isneginf(v) and np.isneginf(ref[i])) or abs(v - ref[i]) <= RTOL * abs(ref[i])
+        if kind == 'z':
+            assert np.array_equal([m.L1, m.phi3], [th[i][0], th[i][5]], equal_nan=True)
+        else:
+            assert np.array_equal([m.Lstar, m.phistar], [th[i][0], th[i][1]], equal_nan=True)
+    # lnlike() evaluates at the current attributes and ignores the prior
+    m.set_parameters_from_list(th[0])
+    model = lf_oracle.make_model(g, kind)
+    model.unpack(th[0])
+    want = model.lnlike_fix_comp() if kind == 'fixed' else model.lnlike()
+    got = m.lnlike_fix_comp() if kind == 'fixed' else m.lnlike()
+    assert abs(got - want) <= RTOL * abs(want)
+    m.close()
+
+
+def test_veff_lf_matches_reference(golden):
+    g = golden('veff_k3_n400')
+    from lumfuncmcmc_b200 import configLF, synth
+    from lumfuncmcmc_b200.lumfuncmcmc import LumFuncMCMC
+    cat = synth.make_catalogue(400, seed=18, nfields=3)
+    m = LumFuncMCMC(cat['z'], flux=cat['flux'], flux_e=cat['flux_e'], Flim=list(cat['Flim']), alpha=cat['alpha'],
+                    Omega_0=list(cat['Omega_0']), Flim_lims=configLF.Flim_lims, alpha_lims=configLF.alpha_lims,
+                    sch_al=configLF.sch_al, Lstar=configLF.Lstar, phistar=configLF.phistar, fcmin=cat['fcmin'],
+                    min_comp_frac=0.0, field_names=cat['field_names'], field_ind=cat['field_ind'], nbins=20, nboot=30)
+    np.random.seed(int(g['seed']))
+    m.VeffLF()
+    np.testing.assert_allclose(m.phifunc, g['phifunc'], rtol=1e-13)
+    assert np.array_equal(m.bincounts, g['counts'])
+    np.testing.assert_array_equal(m.Lavg, g['Lavg'])
+    np.testing.assert_allclose(m.lfbinorig, g['lfbinorig'], rtol=1e-12)
+    np.testing.assert_allclose(m.var, g['var'], rtol=1e-9)         # same RNG stream -> same resamples
+    m.close()
+
+
+def test_veff_lf_with_minimum_completeness(golden):
+    """min_comp_frac > 0: per-source upper redshift limit and volume (reference lumfuncmcmc.py:522-524)."""
+    g = golden('veff_k2_mcf50')
+    from lumfuncmcmc_b200 import configLF, synth
+    from lumfuncmcmc_b200.lumfuncmcmc import LumFuncMCMC
+    cat = synth.make_catalogue(250, seed=19, nfields=2)
+    m = LumFuncMCMC(cat['z'], flux=cat['flux'], flux_e=cat['flux_e'], Flim=list(cat['Flim']), alpha=cat['alpha'],
+                    Omega_0=list(cat['Omega_0']), Flim_lims=configLF.Flim_lims, alpha_lims=configLF.alpha_lims,
+                    sch_al=configLF.sch_al, Lstar=configLF.Lstar, phistar=configLF.phistar, fcmin=cat['fcmin'],
+                    min_comp_frac=0.5, field_names=cat['field_names'], field_ind=cat['field_ind'], nbins=20, nboot=30)
+    np.random.seed(int(g['seed']))
+    m.VeffLF()
+    assert np.array_equal(m.phifunc == 0.0, g['phifunc'] == 0.0)
+    nz = g['phifunc'] != 0
+    np.testing.assert_allclose(m.phifunc[nz], g['phifunc'][nz], rtol=1e-7)   # QUADPACK tolerance of the reference
+    assert np.array_equal(m.bincounts, g['counts'])
+    np.testing.assert_allclose(m.lfbinorig, g['lfbinorig'], rtol=1e-7)
+    m.close()
+
+
+def test_fit_model_small_run_and_chain_replay():
+    """Same sampler code and seed driven by the engine and by the oracle: identical accept/reject decisions, so
+    identical chains; posterior summaries follow."""
+    from lumfuncmcmc_b200.sampler import EnsembleSampler
+    m = _build('free', n=600, nfields=2, seed=31)
+    m.nwalkers, m.nsteps = 16, 25
+    inp = m.engine_inputs()
+    np.random.seed(77)
+    truth = np.array([42.5, -3.2, -1.49] + list(m.Flim) + [m.alpha])
+    pos = truth + 0.01 * np.random.randn(m.nwalkers, len(truth))
+    state = np.random.get_state()
+    eng = EnsembleSampler(m.nwalkers, len(truth), m.lnprob, vectorize=True)
+    eng.run_mcmc(pos, m.nsteps, rstate0=state)
+    ora = EnsembleSampler(m.nwalkers, len(truth), lambda th: lf_oracle.lnprob_batch(inp, 'free', th), vectorize=True)
+    ora.run_mcmc(pos, m.nsteps, rstate0=state)
+    assert np.array_equal(eng.chain, ora.chain)
+    np.testing.assert_allclose(eng.lnprobability, ora.lnprobability, rtol=RTOL)
+    # the class's own driver
+    np.random.seed(78)
+    m.fit_model()
+    assert m.samples.shape[1] == len(truth) + 1 and np.isfinite(m.samples[:, -1]).all()
+    assert m.chain.shape == (16, 25, len(truth))
+    from lumfuncmcmc_b200.tableio import Table
+    names = m.get_param_names()
+    labels = ['Line'] + [n + '_%02d' % p for n in names for p in (16, 50, 84)]
+    m.table = Table(names=labels, dtype=['S10'] + ['f8'] * (len(labels) - 1))
+    m.table.add_row(['OIII'] + [0.] * (len(labels) - 1))
+    m.add_fitinfo_to_table([16, 50, 84])
+    med = np.array([m.table[-1][2 + 3 * j] for j in range(len(names))])
+    assert np.all(np.isfinite(med)) and abs(med[0] - 42.5) < 1.0
+    m.nboot, m.nbins = 5, 10
+    m.set_median_fit(rndsamples=20)
+    assert m.medianLF.shape == m.lum.shape and len(m.Lavg) == 10 and np.all(m.var > 0)
+    m.close()
