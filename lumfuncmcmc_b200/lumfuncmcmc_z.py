@@ -171,24 +171,32 @@ class LumFuncMCMCz(LFBase):
         """1/V_eff binned LF with bootstrap errors (reference lumfuncmcmc_z.py:470-478)."""
         self._veff(self.roots_arr)
 
-    def set_median_fit(self, rndsamples=200, lnprobcut=7.5, zmin=None, zmax=None, nz=None):
-        """Median model LF at the sample's luminosities / redshifts over random posterior draws, then ``VeffLF``
-        (reference lumfuncmcmc_z.py:480-515)."""
+    def _median_matrix(self, nsamples, lo_pad, hi_pad, zlen, Llen):
+        """Model LF at the posterior-median parameters on a (redshift, luminosity) mesh -> ``Lout``, ``zout``,
+        ``medianLF[zlen, Llen]``, then the 1/V_eff LF (reference lumfuncmcmc_z.py:507-515, 524-533)."""
+        self.Lout = np.linspace(min(self.lum) - lo_pad, max(self.lum) + hi_pad, Llen)
+        self.zout = np.linspace(self.zmin, self.zmax, zlen)
+        self.medianLF = np.zeros((zlen, Llen))
+        self.set_parameters_from_list(np.percentile(nsamples, 50.0, axis=0))
+        for i in np.arange(zlen):
+            self.medianLF[i] = schechter_z(self.Lout, self.zout[i], self.sch_al, self.L1, self.L2, self.L3, self.phi1,
+                                           self.phi2, self.phi3, self.z1, self.z2, self.z3)
+        self.VeffLF()
+
+    def set_median_fit(self, lnprobcut=7.5, zlen=100, Llen=100):
+        """Posterior-median model on a mesh and the 1/V_eff LF, without a figure (reference lumfuncmcmc_z.py:480-515)."""
+        nsamples = self._lnprob_selection(lnprobcut, drop_lnprob=True)
+        self.log.info("Shape of nsamples (with a lnprobcut applied)")
+        self.log.info(nsamples.shape)
+        self._median_matrix(nsamples, 0.2, 0.2, zlen, Llen)
+
+    def triangle_plot(self, outname, lnprobcut=7.5, imgtype='png'):
+        """Corner plot with the LF-vs-redshift panel (reference lumfuncmcmc_z.py:524-593).  The data products
+        (``Lout``, ``zout``, ``medianLF``, ``VeffLF``) are always computed; the figure needs matplotlib + corner."""
         nsamples = self._lnprob_selection(lnprobcut, drop_lnprob=False)
         self.log.info("Shape of nsamples (with a lnprobcut applied)")
         self.log.info(nsamples.shape)
-        lf = []
-        for _ in np.arange(rndsamples):
-            ind = np.random.randint(0, nsamples.shape[0])
-            self.set_parameters_from_list(nsamples[ind, :])
-            lf.append(schechter_z(self.lum, self.z, self.sch_al, self.L1, self.L2, self.L3, self.phi1, self.phi2,
-                                  self.phi3, self.z1, self.z2, self.z3))
-        self.medianLF = np.median(np.array(lf), axis=0)
-        self.VeffLF()
-
-    def triangle_plot(self, outname, lnprobcut=7.5, imgtype='png'):
-        """Corner plot (needs matplotlib + corner); its data products are computed either way."""
-        self.set_median_fit(lnprobcut=lnprobcut)
+        self._median_matrix(nsamples, 0.08, 0.01, 100, 100)
         try:
             import matplotlib
             matplotlib.use("Agg")
@@ -197,10 +205,26 @@ class LumFuncMCMCz(LFBase):
         except ImportError:
             self.log.info("matplotlib/corner not available: skipping the figure")
             return
-        nsamples = self._lnprob_selection(lnprobcut, drop_lnprob=False)
         names = self.get_param_names()
-        fs = 11 + int(round(0.75 * len(nsamples[0])))
+        nd = len(nsamples[0])
+        fs = 11 + int(round(0.75 * nd))
         fig = corner.corner(nsamples[:, :-1], labels=names, range=[.95] * len(names), label_kwargs={"fontsize": fs},
                             show_titles=True, title_kwargs={"fontsize": fs - 2}, quantiles=[0.16, 0.5, 0.84], bins=30)
+        w = fig.get_figwidth()
+        if nd >= 4:
+            fig.set_figwidth(w - (nd - 13) * 0.025 * w)
+            box = [0.44 - 0.008 * (nd - 4), 0.78 - 0.001 * (nd - 4), 0.48 + 0.008 * (nd - 4), 0.19 + 0.001 * (nd - 4)]
+        else:
+            box = [0.67, 0.75, 0.32, 0.23]
+        ax = fig.add_subplot(3, 1, 1)
+        ax.set_position(box)
+        ax.set_yscale('log')
+        ax.set_xlabel(r"$\log$ L (erg s$^{-1}$)")
+        ax.set_ylabel(r"$\phi_{\rm{true}}$ (Mpc$^{-3}$ dex$^{-1}$)")
+        LL, zz = np.meshgrid(self.Lout, self.zout)
+        im = ax.pcolormesh(LL, self.medianLF, zz, shading='auto', cmap='viridis')
+        xmax = min(max(self.L1, self.L2, self.L3) + 0.5, self.Lout.max())
+        ax.set_xlim(right=xmax)
+        fig.colorbar(im, ax=ax, label='Redshift')
         fig.savefig("%s.%s" % (outname, imgtype), dpi=200)
         plt.close(fig)

@@ -121,3 +121,37 @@ def test_fit_model_small_run_and_chain_replay():
     m.set_median_fit(rndsamples=20)
     assert m.medianLF.shape == m.lum.shape and len(m.Lavg) == 10 and np.all(m.var > 0)
     m.close()
+
+
+@pytest.mark.parametrize('evolving', [False, True])
+def test_driver_end_to_end_writes_the_reference_outputs(tmp_path, monkeypatch, evolving):
+    """Config-1 in miniature through the unchanged command line: catalogue file in, fitposterior / bestfitLF / VeffLF /
+    parameter table / .args out (reference run_lumfuncmcmc.py:297-330)."""
+    import os
+    from lumfuncmcmc_b200 import synth
+    from lumfuncmcmc_b200.tableio import Table
+    from tests.test_driver_cpu import _write_catalogue
+    cat = synth.make_catalogue(1500, seed=51, evolve=(0.3, -0.2) if evolving else None)
+    _write_catalogue(str(tmp_path / 'cat.dat'), cat)
+    monkeypatch.chdir(tmp_path)
+    np.random.seed(5)
+    if evolving:
+        import run_lumfuncmcmc_z as drv
+        out, nd = 'LFMCMCzOut', 7
+    else:
+        import run_lumfuncmcmc as drv
+        out, nd = 'LFMCMCOut', 9
+    m = drv.main(['-f', 'cat.dat', '-o', 'fit.dat', '-nw', '20', '-ns', '30', '-nboot', '5', '-nbins', '12'])
+    tag = 'fit_nb12_nw20_ns30_mcf0'
+    for stem in ('fitposterior_%s.dat' % tag, 'bestfitLF_%s.dat' % tag, 'VeffLF_%s.dat' % tag, 'fit.dat', 'fit.dat.args'):
+        assert os.path.isfile(os.path.join(out, stem)), stem
+    post = Table.read(os.path.join(out, 'fitposterior_%s.dat' % tag))
+    assert post.colnames[-1] == 'Ln Prob' and len(post.colnames) == nd + 1
+    assert np.array_equal(post.as_array(), m.samples)
+    veff = Table.read(os.path.join(out, 'VeffLF_%s.dat' % tag))
+    assert len(veff) == 12 and np.all(veff['BinLFErr'] > 0)
+    # second invocation hits the result cache and only re-summarises
+    m2 = drv.main(['-f', 'cat.dat', '-o', 'fit.dat', '-nw', '20', '-ns', '30', '-nboot', '5', '-nbins', '12'])
+    assert np.array_equal(m2.samples, m.samples) and not hasattr(m2, 'chain')
+    m.close()
+    m2.close()
