@@ -13,7 +13,7 @@ one NCCL all-reduce of W doubles per step.
 value  : terms/s, inputs resident in HBM (theta on the device), CUDA events on the launching stream, max over ranks.
 e2e    : same metric through the public host API (ShardedLikelihood.lnprob: pinned-host theta -> H2D -> kernels
          -> all-reduce -> D2H of W doubles -> sync), host wall clock, max over ranks.
-roofline: the loop is FP64-FMA-pipe bound (no tensor cores, HBM traffic ~0.02 B/term): achieved = terms/s/GPU x 32
+roofline: the loop is FP64-FMA-pipe bound (no tensor cores, HBM traffic ~0.02 B/term): achieved = terms/s/GPU x 28
          FP64-pipe instructions per term (counted in the SASS of k_main<false>) x 2 FLOP, against the register-only
          DFMA rate measured live on the same GPU (lf_fp64_peak) x 2 FLOP.  HBM figures are reported beside it.
 """
@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FP64_INSTR_PER_TERM = 32          # DFMA/DADD/DMUL per (walker, source) term in k_main<false> (profiles/)
+FP64_INSTR_PER_TERM = 28          # DFMA/DADD/DMUL per (walker, source) term in k_main<false> (tools/sass_fp64_operands.py)
 BYTES_PER_SOURCE = 16             # (log10 flux, flux) per source per sweep
 METRIC = "walker x source lnL terms/sec (batched lnprob, free-completeness single-z, FP64)"
 

@@ -158,7 +158,7 @@ __device__ __forceinline__ void quad_coef(double y1, double y2, double y3, doubl
 // product-then-log is provably >= exp(-700) (normal range, 8 above the denormal boundary) and every fast-math
 // argument stays inside its validated range.
 #define LB_SAFE (-700.0)
-#define N_MIN_SAFE (-30.0)
+#define N_MIN_SAFE (-28.0)      /* fc >= 3.2e-4 > 2^-12, the lower end of the log table */
 #define X_MIN_SAFE (1.0e-4)
 
 __global__ void k_prologue(KArgs a) {
@@ -263,7 +263,7 @@ __global__ void k_prologue(KArgs a) {
                 double fmn = fmin(s.n > 0.0 ? s.f_min : 1.0e300, s.grid_f_min);
                 if (!(alpha_c * (gmin - lgF) > N_MIN_SAFE)) range_ok = false;
                 if (a.modified && !(fmn / ftau > X_MIN_SAFE)) range_ok = false;
-                if (a.modified && !(a.fcap / ftau < 1.0e7)) range_ok = false;      // exp range reduction stays in int32
+                if (a.modified && !(a.fcap / ftau < 5.0e6)) range_ok = false;      // exp range reduction stays in int32
                 if (s.n > 0.0) tmin = log(fleming_literal(s.f_min, F50, alpha_c, ftau, a.modified != 0));
                 lnom = s.ln_om0;
             }
@@ -308,14 +308,19 @@ __global__ void k_zcolumns(KArgs a) {
 // ------------------------------------------------------------------------------------------------
 // main kernels: grid of warp work items = (walker group of 32) x (slab of sources | slab of quadrature points)
 // ------------------------------------------------------------------------------------------------
+// one 16-warp block per SM: the shared-memory tables (130 KB) are filled once per SM
 #ifndef LF_WARPS_PER_BLOCK
-#define LF_WARPS_PER_BLOCK 8
+#define LF_WARPS_PER_BLOCK 16
 #endif
 #ifndef LF_MIN_BLOCKS
-#define LF_MIN_BLOCKS 2
+#define LF_MIN_BLOCKS 1
+#endif
+#ifndef LF_ILP
+#define LF_ILP 2
 #endif
 #define WARPS_PER_BLOCK LF_WARPS_PER_BLOCK
 #define BLOCK_THREADS (32 * WARPS_PER_BLOCK)
+static const size_t SMEM_TABLE_BYTES = sizeof(double2) * LOG_TAB_N * LOG_TAB_REP + sizeof(double) * EXP_TAB_N * EXP_TAB_REP;
 
 __device__ __forceinline__ int field_of(const KArgs& a, long long i) {
     int k = 0;
@@ -325,8 +330,9 @@ __device__ __forceinline__ int field_of(const KArgs& a, long long i) {
 
 template <bool LITERAL>
 __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) {
-    __shared__ double s_exp[EXP_TAB_N * EXP_TAB_REP];
-    __shared__ double2 s_log[LOG_TAB_N * LOG_TAB_REP];
+    extern __shared__ __align__(16) unsigned char smem_tables[];       // fast kernels only (SMEM_TABLE_BYTES)
+    double2* s_log = reinterpret_cast<double2*>(smem_tables);
+    double* s_exp = reinterpret_cast<double*>(s_log + LOG_TAB_N * LOG_TAB_REP);
     const int cls = LITERAL ? CLS_LIT : CLS_FAST;
     const int count = a.cls_count[cls];
     const int n_wg = (count + 31) >> 5;
@@ -341,7 +347,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
     // Items are small (tens per warp slot), so SMs finish within one item of each other (no wave tail), and each
     // item owns its own partial[] row, so the result does not depend on which warp ran it.
     const int lane = threadIdx.x & 31;
-    const int rep16 = lane & 15, rep8 = lane & 7;
+    const int rep16 = lane & (EXP_TAB_REP - 1), rep8 = lane & (LOG_TAB_REP - 1);   // table replica of this lane
     const long long WS = a.Wcap;
     const int* list = LITERAL ? a.list_lit : a.list_fast;
     int* counter = a.cls_count + (LITERAL ? 4 : 3);
@@ -382,6 +388,27 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                             acc1 = fma(lg1, rd1, acc1);
                         };
                         int j = 0;
+#if LF_ILP == 4
+                        // four independent chains per thread, the next four sources prefetched a trip ahead
+                        auto quad = [&](const double2& u0, const double2& u1, const double2& u2, const double2& u3) {
+                            double lg0, rd0, lg1, rd1, lg2, rd2, lg3, rd3;
+                            fleming_log_parts<true>(u0.x, u0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            fleming_log_parts<true>(u1.x, u1.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg1, rd1);
+                            fleming_log_parts<true>(u2.x, u2.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg2, rd2);
+                            fleming_log_parts<true>(u3.x, u3.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg3, rd3);
+                            acc0 = fma(lg0, rd0, acc0);
+                            acc1 = fma(lg1, rd1, acc1);
+                            acc0 = fma(lg2, rd2, acc0);
+                            acc1 = fma(lg3, rd3, acc1);
+                        };
+                        double2 A0 = make_double2(0.0, 1.0), A1 = A0, A2 = A0, A3 = A0;
+                        if (cnt >= 4) { A0 = __ldg(ps); A1 = __ldg(ps + 1); A2 = __ldg(ps + 2); A3 = __ldg(ps + 3); }
+                        for (; j + 4 <= cnt; j += 4) {
+                            double2 c0 = A0, c1 = A1, c2 = A2, c3 = A3;
+                            if (j + 8 <= cnt) { A0 = __ldg(ps + j + 4); A1 = __ldg(ps + j + 5); A2 = __ldg(ps + j + 6); A3 = __ldg(ps + j + 7); }
+                            quad(c0, c1, c2, c3);
+                        }
+#else
                         double2 A0 = make_double2(0.0, 1.0), A1 = A0, B0 = A0, B1 = A0;
                         if (cnt >= 4) { A0 = __ldg(ps); A1 = __ldg(ps + 1); }
                         for (; j + 4 <= cnt; j += 4) {
@@ -390,6 +417,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                             if (j + 8 <= cnt) { A0 = __ldg(ps + j + 4); A1 = __ldg(ps + j + 5); }
                             pair(B0, B1);
                         }
+#endif
                         for (; j < cnt; ++j) {
                             double2 s0 = __ldg(ps + j);
                             double lg0, rd0;
@@ -769,12 +797,16 @@ extern "C" int lf_ndim(const lf_ctx* ctx) { return ctx ? ctx->ndim : -1; }
 
 static void fill_tables(Tables& t) {
     for (int j = 0; j < EXP_TAB_N; ++j) t.exp2_frac[j] = (double)exp2l((long double)j / EXP_TAB_N);
-    for (int j = 0; j < LOG_TAB_N; ++j) {
-        long double c = 1.0L + ((long double)j + 0.5L) / LOG_TAB_N;
-        double invc = (double)(1.0L / c);
-        t.log_tab[j].x = invc;
-        t.log_tab[j].y = (double)(-logl((long double)invc));
+    const int M = 1 << LOG_MANT_BITS;
+    for (int b = 0; b < LOG_OCTAVES * M; ++b) {
+        int E = -LOG_OCTAVES + b / M, j = b % M;
+        long double cm = 1.0L + ((long double)j + 0.5L) / M;          // bin centre of the mantissa
+        double invc = ldexp((double)(1.0L / cm), -E);                    // 1 / (cm * 2^E), power-of-two scaling is exact
+        t.log_tab[b].x = invc;
+        t.log_tab[b].y = (double)(-logl((long double)invc));             // consistent with the rounded 1/c
     }
+    t.log_tab[LOG_OCTAVES * M].x = 1.0;  t.log_tab[LOG_OCTAVES * M].y = 0.0;       // argument exactly 1
+    t.log_tab[LOG_OCTAVES * M + 1] = t.log_tab[LOG_OCTAVES * M];
 }
 
 extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
@@ -802,7 +834,8 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     CK(cudaMalloc(&c->d_tables, sizeof(Tables)));
     CK(cudaMemcpy(c->d_tables, &t, sizeof(Tables), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&c->d_cls, 8 * sizeof(int)));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_fast, k_main<false>, BLOCK_THREADS, 0));
+    CK(cudaFuncSetAttribute(k_main<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TABLE_BYTES));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_fast, k_main<false>, BLOCK_THREADS, SMEM_TABLE_BYTES));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lit, k_main<true>, BLOCK_THREADS, 0));
     if (c->occ_fast < 1) c->occ_fast = 1;
     if (c->occ_lit < 1) c->occ_lit = 1;
@@ -1139,7 +1172,7 @@ static int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, doubl
     const long long need = (items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;      // never more blocks than items
     const unsigned bf = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_fast);
     const unsigned bl = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_lit);
-    k_main<false><<<bf, BLOCK_THREADS, 0, st>>>(a);
+    k_main<false><<<bf, BLOCK_THREADS, SMEM_TABLE_BYTES, st>>>(a);
     k_main<true><<<bl, BLOCK_THREADS, 0, st>>>(a);
     k_finish<<<(unsigned)((W + T - 1) / T), T, 0, st>>>(a);
     c->launches += 3;
