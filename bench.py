@@ -255,10 +255,40 @@ def main():
     t_e2e = time.perf_counter() - t0
     assert np.array_equal(result_e2e, result_dev, equal_nan=True)
 
-    t = torch.tensor([ms_dev, t_e2e * 1e3], dtype=torch.float64, device='cuda')
+    # ---- ensemble steps/s (second half of BASELINE.json's metric): the vectorised stretch-move sampler drives the
+    # public API; one step = two half-ensemble lnprob calls + host proposal/accept work.  Every rank runs the same
+    # seeded sampler in lockstep (same proposals; the all-reduce inside lnprob keeps them identical).
+    from lumfuncmcmc_b200.sampler import EnsembleSampler
+    rs = np.random.RandomState(11)
+    n_samp_steps = max(3, min(args.steps, 10))
+    smp = EnsembleSampler(W, like.ndim, like.lnprob, vectorize=True)
+    smp.run_mcmc(thetas, 1, rstate0=rs.get_state())
+    sync_all()
+    t0 = time.perf_counter()
+    smp.run_mcmc(smp.chain[:, -1, :], n_samp_steps)
+    torch.cuda.synchronize()
+    t_steps = time.perf_counter() - t0
+    # config-1 size on one GPU (rank 0): 10^4 sources x 100 walkers, launch/host-bound regime
+    small = None
+    if rank == 0:
+        inp_s = build_inputs(10000, args.kind, seed=4242)
+        like_s = ShardedLikelihood.__new__(ShardedLikelihood)
+        from lumfuncmcmc_b200.engine import LikelihoodEngine
+        eng_s = LikelihoodEngine(inp_s, args.kind, device=local_rank)
+        th_s = synth.draw_thetas(inp_s, args.kind, 100, seed=9, mode=mode, scale=0.02)
+        smp_s = EnsembleSampler(100, eng_s.ndim, eng_s.lnprob, vectorize=True)
+        smp_s.run_mcmc(th_s, 20, rstate0=rs.get_state())
+        t0 = time.perf_counter()
+        smp_s.run_mcmc(smp_s.chain[:, -1, :], 200)
+        dt_s = time.perf_counter() - t0
+        small = {"workload": "BASELINE.json configs[0] size: 1e4 sources x 100 walkers, 1 GPU", "steps_per_s": 200 / dt_s,
+                 "lnprob_calls_per_s": 400 / dt_s, "acceptance": float(np.mean(smp_s.acceptance_fraction))}
+        eng_s.close()
+
+    t = torch.tensor([ms_dev, t_e2e * 1e3, t_steps * 1e3], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    ms_dev, ms_e2e, ms_steps = float(t[0]), float(t[1]), float(t[2])
 
     if rank == 0:
         terms_per_step = float(n) * world * W
@@ -289,6 +319,10 @@ def main():
                     "d2h_bytes_per_step": W * 8, "ms_per_step": ms_e2e / args.steps,
                     "timing": "host wall clock around ShardedLikelihood.lnprob (pinned theta H2D, kernels, all-reduce, D2H, sync), max over ranks"},
             "gpu_launches": int(launches),
+            "ensemble_steps": {"value": n_samp_steps / (ms_steps * 1e-3), "unit": "ensemble steps/s",
+                               "workload": "%d walkers x %g sources per GPU x %d GPU(s): stretch move, 2 half-ensemble "
+                                           "lnprob calls per step through the public host API" % (W, args.nsources, world),
+                               "steps_timed": n_samp_steps, "small": small},
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": None,

@@ -574,16 +574,32 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
 // ------------------------------------------------------------------------------------------------
 // finish: fixed-order reduction over slabs; lnprob = lnpart - fullint
 // ------------------------------------------------------------------------------------------------
-__global__ void k_finish(KArgs a) {
-    long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    int nf = a.cls_count[CLS_FAST], nl = a.cls_count[CLS_LIT];
-    if (idx >= nf + nl) return;
-    bool fast = idx < nf;
-    long long w = fast ? a.list_fast[idx] : a.list_lit[idx - nf];
+#define FIN_GROUPS 8
+__global__ void __launch_bounds__(32 * FIN_GROUPS) k_finish(KArgs a) {
+    // one block per 32 walkers; FIN_GROUPS row-groups read the slab partials in parallel (coalesced along walkers),
+    // each in ascending row order, and are combined in a fixed order: deterministic, no atomics
+    __shared__ double s_src[FIN_GROUPS][32], s_quad[FIN_GROUPS][32];
+    const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int nf = a.cls_count[CLS_FAST], nl = a.cls_count[CLS_LIT];
+    const long long idx = (long long)blockIdx.x * 32 + lane;
+    if ((long long)blockIdx.x * 32 >= nf + nl) return;
+    const bool valid = idx < nf + nl;
+    const bool fast = idx < nf;
+    long long w = 0;
+    if (valid) w = fast ? a.list_fast[idx] : a.list_lit[idx - nf];
     const long long WS = a.Wcap;
     double lnpart = 0.0, fullint = 0.0;
-    for (int r = 0; r < a.n_src_slabs; ++r) lnpart += a.partial[(long long)r * WS + w];
-    for (int r = a.n_src_slabs; r < a.n_src_slabs + a.n_quad_slabs; ++r) fullint += a.partial[(long long)r * WS + w];
+    if (valid) {
+        for (int r = g; r < a.n_src_slabs; r += FIN_GROUPS) lnpart += a.partial[(long long)r * WS + w];
+        for (int r = a.n_src_slabs + g; r < a.n_src_slabs + a.n_quad_slabs; r += FIN_GROUPS)
+            fullint += a.partial[(long long)r * WS + w];
+    }
+    s_src[g][lane] = lnpart;
+    s_quad[g][lane] = fullint;
+    __syncthreads();
+    if (g != 0 || !valid) return;
+    lnpart = 0.0; fullint = 0.0;
+    for (int k = 0; k < FIN_GROUPS; ++k) { lnpart += s_src[k][lane]; fullint += s_quad[k][lane]; }
     if (fast) lnpart += a.wp[P_LNPART0 * WS + w];
     if (a.nshare > 1 && (w % a.nshare) != a.share) fullint = 0.0;
     double v = lnpart - fullint;
@@ -1131,7 +1147,7 @@ static int ensure_scratch(lf_ctx* c, long long W, int rows) {
 static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
     const long long n_wg = (W + 31) / 32;
     const long long target_items = (long long)c->sm_count * 16 * 24;   // ~24 items per resident warp
-    long long rows = std::max<long long>(1, target_items / n_wg);
+    long long rows = std::min<long long>(4096, std::max<long long>(1, target_items / n_wg));
     const int model = c->cfg.model;
     // relative cost of a quadrature point vs a source term
     double src_cost = model == LF_MODEL_FREE ? 1.0 : (model == LF_MODEL_Z ? 0.5 : 0.0);
@@ -1174,7 +1190,7 @@ static int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, doubl
     const unsigned bl = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_lit);
     k_main<false><<<bf, BLOCK_THREADS, SMEM_TABLE_BYTES, st>>>(a);
     k_main<true><<<bl, BLOCK_THREADS, 0, st>>>(a);
-    k_finish<<<(unsigned)((W + T - 1) / T), T, 0, st>>>(a);
+    k_finish<<<(unsigned)((W + 31) / 32), 32 * FIN_GROUPS, 0, st>>>(a);
     c->launches += 3;
     CK(cudaGetLastError());
     return 0;
@@ -1302,14 +1318,17 @@ extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const doubl
     a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.vol_int = vol_int; a.modified = modified ? 1 : 0;
     a.edges = c->v_edges; a.nbins = nbins; a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = nullptr;
     size_t smem = sizeof(double) * (nbins + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * (size_t)nbins;
+    CK(cudaEventRecord(c->ev0, c->stream));
     k_veff<0><<<blocks, 256, smem, c->stream>>>(a);
     k_veff_reduce<<<(nbins + 127) / 128, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    CK(cudaEventRecord(c->ev1, c->stream));
     c->launches += 2;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
     if (phi_out) CK(cudaMemcpyAsync(phi_out, c->v_phi, nb, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms; }
     cudaFree(d_flux);
     if (d_vol) cudaFree(d_vol);
     if (d_valid) cudaFree(d_valid);
@@ -1349,6 +1368,7 @@ extern "C" int lf_bin_weights(lf_ctx* c, int64_t n, const double* lum, const dou
     CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (cudaEventQuery(c->ev1) == cudaSuccess) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
     return 0;
 }
 
@@ -1365,12 +1385,15 @@ extern "C" int lf_boot_bin(lf_ctx* c, const int32_t* mult, int64_t* counts, doub
     a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult;
     const int nbins = c->v_nbins, blocks = c->v_blocks;
     size_t smem = sizeof(double) * (nbins + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * (size_t)nbins;
+    CK(cudaEventRecord(c->ev0, c->stream));
     k_veff<1><<<blocks, 256, smem, c->stream>>>(a);
     k_veff_reduce<<<(nbins + 127) / 128, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    CK(cudaEventRecord(c->ev1, c->stream));
     c->launches += 2;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (cudaEventQuery(c->ev1) == cudaSuccess) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
     return 0;
 }

@@ -73,6 +73,11 @@ class _VeffOps:
     def _nbins_resident(self):
         return getattr(self, '_veff_nbins', 0)
 
+    def last_kernel_ms(self):
+        ms = C.c_double()
+        _lib.check(self.lib.lf_last_kernel_ms(self._ctx, C.byref(ms)), self.lib)
+        return ms.value
+
     def bin_weights(self, lum, phi, edges):
         """Counts and sum of caller-provided weights per half-open bin (reference VmaxLumFunc.py:345-350)."""
         lum, phi, edges = _f64(lum), _f64(phi), _f64(edges)
@@ -226,11 +231,6 @@ class LikelihoodEngine(_VeffOps):
         launches = C.c_int64()
         _lib.check(self.lib.lf_last_call_info(self._ctx, counts, C.byref(launches)), self.lib)
         return dict(rejected=counts[0], fast=counts[1], literal=counts[2], launches=launches.value)
-
-    def last_kernel_ms(self):
-        ms = C.c_double()
-        _lib.check(self.lib.lf_last_kernel_ms(self._ctx, C.byref(ms)), self.lib)
-        return ms.value
 
     def fp64_peak(self, iters=20000):
         """Measured register-only DFMA rate of this GPU (thread-instructions per second) and the run time in ms."""

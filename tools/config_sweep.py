@@ -1,0 +1,67 @@
+"""BASELINE.json configs 2-4 on one GPU: device throughput table (not the bench line).
+    python tools/config_sweep.py [quick]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lumfuncmcmc_b200 import synth                           # noqa: E402
+from lumfuncmcmc_b200.engine import LikelihoodEngine, VeffEngine   # noqa: E402
+
+quick = len(sys.argv) > 1
+
+
+def run(kind, n, walkers):
+    cat = synth.make_catalogue(n, seed=1, evolve=(0.3, -0.2) if kind == 'z' else None)
+    inp = synth.direct_inputs(cat, nknots=4096, size_ln=101 if kind == 'free' else 201, tabulated=(kind != 'free'))
+    eng = LikelihoodEngine(inp, kind)
+    for W in walkers:
+        th = synth.draw_thetas(inp, kind, W, seed=3, mode='near', scale=0.02)
+        for _ in range(3):
+            eng.lnprob(th)
+        ts, ws = [], []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            eng.lnprob(th)
+            ws.append(time.perf_counter() - t0)
+            ts.append(eng.last_kernel_ms() * 1e-3)
+        k, w = min(ts), min(ws)
+        print("| %-5s | %8.0e | %5d | %9.3f | %9.3f | %10.3e | %10.3e |" % (kind, n, W, k * 1e3, w * 1e3, n * W / k, n * W / w),
+              flush=True)
+    eng.close()
+
+
+print("| model | sources | walkers | kernel ms | host-call ms | terms/s (kernels) | terms/s (host API) |")
+print("|---|---|---|---|---|---|---|")
+sizes = [100000, 1000000] if quick else [100000, 1000000, 10000000]
+for n in sizes:
+    run('free', n, [64, 256, 1024, 4096])
+run('z', 1000000, [512])
+run('fixed', 1000000, [512])
+run('free', 10000, [100])
+
+# config 4: 1/V_eff binned LF
+n = 1000000 if quick else 10000000
+rng = np.random.default_rng(4)
+lum = rng.uniform(40.9, 44.0, n)
+flux = 10 ** rng.uniform(-17.2, -14.5, n)
+fi = np.array([0, n // 5, 2 * n // 5, 3 * n // 5, 4 * n // 5, n], dtype=np.int64)
+edges = np.linspace(lum.min() * 1.001, lum.max(), 51)
+ve = VeffEngine()
+for _ in range(2):
+    t0 = time.perf_counter()
+    phi, counts, sums = ve.veff_bin(flux, lum, fi, [2.72, 3.61, 2.55, 3.31, 3.30], 4.56, 0.1, 1.9e6, 3.0e10, edges)
+    wall = time.perf_counter() - t0
+kms = ve.last_kernel_ms()
+want = np.histogram(lum[(lum >= edges[0]) & (lum < edges[-1])], bins=edges)[0]
+print("\nVeff: N=%d nbins=50  kernel %.3f ms (%.3e sources/s, %.1f GB/s of 24 B/source)  host call %.1f ms  counts bit-exact: %s"
+      % (n, kms, n / (kms * 1e-3), 24.0 * n / (kms * 1e-3) / 1e9, wall * 1e3, np.array_equal(counts, want)))
+mult = np.bincount(rng.integers(0, n, n), minlength=n)
+t0 = time.perf_counter()
+bc, bs = ve.boot_bin(mult)
+wall = time.perf_counter() - t0
+kms = ve.last_kernel_ms()
+print("bootstrap replicate: kernel %.3f ms (%.1f GB/s of 20 B/source)  host call %.1f ms  counts sum %d" % (
+    kms, 20.0 * n / (kms * 1e-3) / 1e9, wall * 1e3, bc.sum()))
