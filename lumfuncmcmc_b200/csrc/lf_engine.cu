@@ -496,8 +496,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                     long long seg_end = (k + 1) * SS < q1 ? (k + 1) * SS : q1;
                     if (!LITERAL) {
                         const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], cinv = wp[(P_FIELD0 + 4 * k + 1) * WS];
-                        for (long long q = q0; q < seg_end; ++q) {
-                            const QuadPointFree* pt = &a.qpf[q];
+                        // one quadrature point: weight * exp(Schechter exponent + ln completeness)
+                        auto point = [&](const QuadPointFree* pt, double& acc) {
                             double2 gf = __ldg(reinterpret_cast<const double2*>(pt));
                             double2 xl = __ldg(reinterpret_cast<const double2*>(pt) + 1);
                             double wt = __ldg(reinterpret_cast<const double2*>(pt) + 2).x;
@@ -507,8 +507,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                             double arg = fma(c1, xl.x, c0);
                             arg = fma(-xl.y, tenmL, arg);
                             arg = fma(lg, rd, arg);
-                            acc0 = fma(wt, exp_full(arg, s_exp, rep16), acc0);
+                            acc = fma(wt, exp_full(arg, s_exp, rep16), acc);
+                        };
+                        long long q = q0;
+                        for (; q + 1 < seg_end; q += 2) {        // two independent chains per thread
+                            point(&a.qpf[q], acc0);
+                            point(&a.qpf[q + 1], acc1);
                         }
+                        if (q < seg_end) point(&a.qpf[q], acc0);
                     } else {
                         const double F50 = wp[(P_FIELD0 + 4 * k + 2) * WS], ftau = wp[(P_FIELD0 + 4 * k + 3) * WS];
                         for (long long q = q0; q < seg_end; ++q) {                    // lumfuncmcmc.py:375-376
@@ -574,7 +580,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
 // ------------------------------------------------------------------------------------------------
 // finish: fixed-order reduction over slabs; lnprob = lnpart - fullint
 // ------------------------------------------------------------------------------------------------
-#define FIN_GROUPS 8
+#define FIN_GROUPS 32
 __global__ void __launch_bounds__(32 * FIN_GROUPS) k_finish(KArgs a) {
     // one block per 32 walkers; FIN_GROUPS row-groups read the slab partials in parallel (coalesced along walkers),
     // each in ascending row order, and are combined in a fixed order: deterministic, no atomics
@@ -590,9 +596,12 @@ __global__ void __launch_bounds__(32 * FIN_GROUPS) k_finish(KArgs a) {
     const long long WS = a.Wcap;
     double lnpart = 0.0, fullint = 0.0;
     if (valid) {
-        for (int r = g; r < a.n_src_slabs; r += FIN_GROUPS) lnpart += a.partial[(long long)r * WS + w];
+        const double* col = a.partial + w;
+#pragma unroll 4
+        for (int r = g; r < a.n_src_slabs; r += FIN_GROUPS) lnpart += col[(long long)r * WS];
+#pragma unroll 4
         for (int r = a.n_src_slabs + g; r < a.n_src_slabs + a.n_quad_slabs; r += FIN_GROUPS)
-            fullint += a.partial[(long long)r * WS + w];
+            fullint += col[(long long)r * WS];
     }
     s_src[g][lane] = lnpart;
     s_quad[g][lane] = fullint;
@@ -1156,7 +1165,7 @@ static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
     double tot = wsrc + wq;
     if (tot <= 0.0) { n_src = 1; n_quad = 1; return; }
     long long rs = (long long)llround((double)rows * wsrc / tot), rq = rows - rs;
-    const long long min_per = 32;
+    const long long min_per = 64;       // at least this many sources / points per work item
     rs = std::max<long long>(1, std::min<long long>(rs, std::max<long long>(1, c->N / min_per)));
     rq = std::max<long long>(1, std::min<long long>(rq, std::max<long long>(1, c->NQ / min_per)));
     n_src = (int)rs;
