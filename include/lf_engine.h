@@ -39,7 +39,7 @@ enum { LF_MODEL_FREE = 0,   /* lnlike: completeness parameters sampled   (lumfun
        LF_MODEL_FIXED = 1,  /* lnlike_fix_comp: tabulated Omega          (lumfuncmcmc.py:380-393) */
        LF_MODEL_Z = 2 };    /* LumFuncMCMCz.lnlike: evolving L*, phi*    (lumfuncmcmc_z.py:364-376) */
 
-/* arithmetic of the walker x source loop */
+/* arithmetic of the walker x source loop (statistics, quadrature, prior and the literal kernels stay FP64) */
 enum { LF_PREC_F64 = 0, LF_PREC_F32 = 1 };
 
 typedef struct lf_ctx lf_ctx;
@@ -127,6 +127,9 @@ int lf_boot_bin(lf_ctx* ctx, const int32_t* mult, int64_t* counts, double* sumph
 
 /* Register-only FP64 FMA micro-benchmark on the context's device: sustained DFMA thread-instructions / s. */
 int lf_fp64_peak(lf_ctx* ctx, int32_t iters, double* dfma_per_s, double* ms);
+
+/* Same for the MUFU (SFU) pipe: sustained ex2.approx.f32 thread-instructions / s (roofline of LF_PREC_F32). */
+int lf_mufu_peak(lf_ctx* ctx, int32_t iters, double* mufu_per_s, double* ms);
 
 /* Device time (ms, CUDA events on the engine's stream) of the kernels of the last lf_lnprob_batch call. */
 int lf_last_kernel_ms(lf_ctx* ctx, double* ms);

@@ -94,6 +94,8 @@ struct KArgs {
     double fcap;                       // cap of the flux copy used in the decay argument (see k_derive_free)
     // resident arrays
     const double2* src2;               // FREE: (log10 flux, flux)   Z: (lum, z)
+    const float2* src2f;               // LF_PREC_F32 copy: FREE (log10 f + 17, f * 1e17)   Z: (lum - 42, z - z2)
+    int precision;                     // LF_PREC_F64 | LF_PREC_F32 (arithmetic of the walker x source loop only)
     const double* lum;
     const double* flux;
     const double* z;
@@ -149,6 +151,26 @@ __device__ __forceinline__ void quad_coef(double y1, double y2, double y3, doubl
         (z3 * z3 - z1 * z1 + (z2 * z2 - z1 * z1) * (z1 - z3) / (z2 - z1));
     b = (y2 - y1 - a * (z2 * z2 - z1 * z1)) / (z2 - z1);
     c = y1 - a * z1 * z1 - b * z1;
+}
+
+// ---- FP32 mode of the walker x source loop: MUFU (SFU) transcendentals, FP32 FMA pipe, chunked accumulation ----
+__device__ __forceinline__ float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+
+// log2 of the modified Fleming completeness: 8 FP32-pipe instructions + 4 MUFU per (walker, source) term.
+//   gs = log10 f + 17, fs = f * 1e17, aFs = -alpha * log10(F50 * 1e17), c2 = -log2(e) / (ftau * 1e17)
+template <bool MODIFIED>
+__device__ __forceinline__ float fleming_log2_f32(float gs, float fs, float alpha, float aFs, float c2) {
+    float n = fmaf(alpha, gs, aFs);
+    float y = fmaf(n, n, 1.0f);
+    float q = n * mufu_rsq(y);
+    float fc = fmaf(0.5f, q, 0.5f);
+    float l2 = mufu_lg2(fc);
+    if (!MODIFIED) return l2;
+    float dec = 1.0f - mufu_ex2(fs * c2);
+    return l2 * mufu_rcp(dec);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -261,7 +283,7 @@ __global__ void k_prologue(KArgs a) {
                 // faintest flux the fast math will see in this field: sources and quadrature points
                 double gmin = fmin(s.n > 0.0 ? s.g_min : 1.0e300, s.grid_g_min);
                 double fmn = fmin(s.n > 0.0 ? s.f_min : 1.0e300, s.grid_f_min);
-                if (!(alpha_c * (gmin - lgF) > N_MIN_SAFE)) range_ok = false;
+                if (!(alpha_c * (gmin - lgF) > (a.precision == LF_PREC_F32 ? -12.0 : N_MIN_SAFE))) range_ok = false;
                 if (a.modified && !(fmn / ftau > X_MIN_SAFE)) range_ok = false;
                 if (a.modified && !(a.fcap / ftau < 5.0e6)) range_ok = false;      // exp range reduction stays in int32
                 if (s.n > 0.0) tmin = log(fleming_literal(s.f_min, F50, alpha_c, ftau, a.modified != 0));
@@ -372,7 +394,35 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
             int k = field_of(a, i0);
             while (i0 < i1) {
                 long long seg_end = a.field_ind[k + 1] < i1 ? a.field_ind[k + 1] : i1;
-                if (!LITERAL) {
+                if (!LITERAL && a.precision == LF_PREC_F32) {
+                    // FP32 mode: MUFU transcendentals; partial sums in FP32 over 64-source chunks, flushed to FP64
+                    const double aFd = wp[(P_FIELD0 + 4 * k + 0) * WS];           // -alpha*log10(F50)
+                    const float af = (float)alpha;
+                    const float aFs = (float)(aFd - 17.0 * alpha);                 // -alpha*log10(F50*1e17)
+                    const float c2 = (float)(wp[(P_FIELD0 + 4 * k + 1) * WS] * (1.0e-17 * LOG2E));
+                    const float2* __restrict__ pf = a.src2f + i0;
+                    const int cnt = (int)(seg_end - i0);
+                    double sum = 0.0;
+                    for (int j0 = 0; j0 < cnt; j0 += 64) {
+                        const int j1 = min(j0 + 64, cnt);
+                        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+                        int j = j0;
+                        if (a.modified) {
+                            for (; j + 4 <= j1; j += 4) {
+                                float2 u0 = __ldg(pf + j), u1 = __ldg(pf + j + 1), u2 = __ldg(pf + j + 2), u3 = __ldg(pf + j + 3);
+                                f0 += fleming_log2_f32<true>(u0.x, u0.y, af, aFs, c2);
+                                f1 += fleming_log2_f32<true>(u1.x, u1.y, af, aFs, c2);
+                                f2 += fleming_log2_f32<true>(u2.x, u2.y, af, aFs, c2);
+                                f3 += fleming_log2_f32<true>(u3.x, u3.y, af, aFs, c2);
+                            }
+                            for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += fleming_log2_f32<true>(u0.x, u0.y, af, aFs, c2); }
+                        } else {
+                            for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += fleming_log2_f32<false>(u0.x, u0.y, af, aFs, c2); }
+                        }
+                        sum += (double)((f0 + f1) + (f2 + f3));
+                    }
+                    acc0 = fma(sum, LN2, acc0);
+                } else if (!LITERAL) {
                     const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], cinv = wp[(P_FIELD0 + 4 * k + 1) * WS];
                     long long i = i0;
                     if (a.modified) {
@@ -455,7 +505,29 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
             }
         } else {
             const double aL = wp[P_AL * WS], bL = wp[P_BL * WS], cL = wp[P_CL * WS];
-            if (!LITERAL) {
+            if (!LITERAL && a.precision == LF_PREC_F32) {
+                // FP32 mode: L*(z) re-centred on the middle pivot and on 42 so the float polynomial keeps ~1e-7 dex
+                const double z2 = a.z2;
+                const float q2 = (float)aL, q1 = (float)(bL + 2.0 * aL * z2);
+                const float q0 = (float)((fma(fma(aL, z2, bL), z2, cL) - 42.0));
+                const float L2T = 3.3219280948873623f;                              // log2(10)
+                const float2* __restrict__ pf = a.src2f + i0;
+                const long long cnt = i1 - i0;
+                double sum = 0.0;
+                for (long long j0 = 0; j0 < cnt; j0 += 64) {
+                    const long long j1 = j0 + 64 < cnt ? j0 + 64 : cnt;
+                    float f0 = 0.f, f1 = 0.f;
+                    long long j = j0;
+                    for (; j + 2 <= j1; j += 2) {
+                        float2 u0 = __ldg(pf + j), u1 = __ldg(pf + j + 1);
+                        f0 += mufu_ex2((u0.x - fmaf(fmaf(q2, u0.y, q1), u0.y, q0)) * L2T);
+                        f1 += mufu_ex2((u1.x - fmaf(fmaf(q2, u1.y, q1), u1.y, q0)) * L2T);
+                    }
+                    if (j < j1) { float2 u0 = __ldg(pf + j); f0 += mufu_ex2((u0.x - fmaf(fmaf(q2, u0.y, q1), u0.y, q0)) * L2T); }
+                    sum += (double)(f0 + f1);
+                }
+                acc0 -= sum;
+            } else if (!LITERAL) {
                 // only sum_i 10^(lum_i - L*(z_i)) needs the walker x source loop; the rest is in P_LNPART0
                 long long i = i0;
                 for (; i + 1 < i1; i += 2) {
@@ -620,19 +692,21 @@ __global__ void __launch_bounds__(32 * FIN_GROUPS) k_finish(KArgs a) {
 // set-up kernels: derived per-source arrays and per-field statistics
 // ------------------------------------------------------------------------------------------------
 __global__ void k_derive_free(long long n, const double* __restrict__ lum, const double* __restrict__ flux,
-                              double2* __restrict__ src2, double* __restrict__ Lsrc, double fcap) {
+                              double2* __restrict__ src2, double* __restrict__ Lsrc, double fcap, float2* __restrict__ src2f) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     double f = flux[i];
+    if (src2f) src2f[i] = make_float2((float)(log10(f) + 17.0), (float)(fmin(f, fcap) * 1.0e17));
     // the decay argument f/ftau only matters below ~46 (exp(-46) = 1e-20 against 1) and ftau < F50 <= prior
     // maximum, so the flux copy used for it is capped at 64 x that maximum: bit-identical results, bounded range
     src2[i] = make_double2(log10(f), fmin(f, fcap));
     Lsrc[i] = pow(10.0, lum[i]);
 }
 __global__ void k_derive_z(long long n, const double* __restrict__ lum, const double* __restrict__ z,
-                           double2* __restrict__ src2) {
+                           double2* __restrict__ src2, float2* __restrict__ src2f, double zref) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (src2f) src2f[i] = make_float2((float)(lum[i] - 42.0), (float)(z[i] - zref));
     src2[i] = make_double2(lum[i], z[i]);
 }
 __global__ void k_pow10(long long n, const double* __restrict__ lum, double* __restrict__ Lsrc) {
@@ -779,6 +853,22 @@ __global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, doubl
     if (s == 12345.678) sink[0] = s;
 }
 
+// MUFU (SFU) micro-benchmark: 8 independent ex2 chains per thread
+__global__ void __launch_bounds__(256) k_mufu_peak(int iters, float seed, float* sink) {
+    float a0 = seed + threadIdx.x * 1e-3f, a1 = a0 + 0.1f, a2 = a0 + 0.2f, a3 = a0 + 0.3f, a4 = a0 + 0.4f, a5 = a0 + 0.5f, a6 = a0 + 0.6f, a7 = a0 + 0.7f;
+#pragma unroll 1
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            a0 = mufu_ex2(a0); a1 = mufu_ex2(a1); a2 = mufu_ex2(a2); a3 = mufu_ex2(a3);
+            a4 = mufu_ex2(a4); a5 = mufu_ex2(a5); a6 = mufu_ex2(a6); a7 = mufu_ex2(a7);
+            a0 -= 1.0f; a1 -= 1.0f; a2 -= 1.0f; a3 -= 1.0f; a4 -= 1.0f; a5 -= 1.0f; a6 -= 1.0f; a7 -= 1.0f;
+        }
+    }
+    float s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (s == 12345.678f) sink[0] = s;
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -793,7 +883,7 @@ struct lf_ctx {
     // resident
     long long N = 0, NQ = 0;
     double* d_lum = nullptr; double* d_flux = nullptr; double* d_z = nullptr; double* d_om = nullptr;
-    double* d_Lsrc = nullptr; double2* d_src2 = nullptr;
+    double* d_Lsrc = nullptr; double2* d_src2 = nullptr; float2* d_src2f = nullptr;
     QuadPointFree* d_qpf = nullptr; QuadPoint* d_qp = nullptr; double* d_zarr = nullptr;
     Tables* d_tables = nullptr;
     bool have_sources = false, have_grid = false;
@@ -838,7 +928,7 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     if (!out || !cfg) return fail("lf_create: null argument");
     if (cfg->nfields < 1 || cfg->nfields > LF_MAX_FIELDS) return fail("lf_create: nfields out of range");
     if (cfg->model < 0 || cfg->model > 2) return fail("lf_create: unknown model");
-    if (cfg->precision != LF_PREC_F64) return fail("lf_create: only LF_PREC_F64 is implemented");
+    if (cfg->precision != LF_PREC_F64 && cfg->precision != LF_PREC_F32) return fail("lf_create: unknown precision");
     if (cfg->size_ln < 2) return fail("lf_create: size_ln must be >= 2");
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -869,7 +959,7 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     a.model = cfg->model; a.K = cfg->nfields; a.S = cfg->size_ln; a.fix_sch_al = cfg->fix_sch_al;
     a.fixed_prior_ok = cfg->fixed_prior_ok; a.force_literal = cfg->force_literal;
     a.modified = (cfg->fcmin != 0.0) ? 1 : 0;
-    a.ndim = c->ndim; a.fcmin = cfg->fcmin;
+    a.ndim = c->ndim; a.fcmin = cfg->fcmin; a.precision = cfg->precision;
     {
         double aa = (2.0 * cfg->fcmin - 1.0) * (2.0 * cfg->fcmin - 1.0);
         a.fcA2 = fabs(aa / (1.0 - aa));
@@ -896,7 +986,7 @@ static void dfree(T*& p) {
 extern "C" void lf_destroy(lf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    dfree(c->d_lum); dfree(c->d_flux); dfree(c->d_z); dfree(c->d_om); dfree(c->d_Lsrc); dfree(c->d_src2);
+    dfree(c->d_lum); dfree(c->d_flux); dfree(c->d_z); dfree(c->d_om); dfree(c->d_Lsrc); dfree(c->d_src2); dfree(c->d_src2f);
     dfree(c->d_qpf); dfree(c->d_qp); dfree(c->d_zarr); dfree(c->d_tables);
     dfree(c->d_wp); dfree(c->d_colA); dfree(c->d_colB); dfree(c->d_partial);
     dfree(c->d_cls); dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_thetas); dfree(c->d_out);
@@ -943,7 +1033,7 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
     if (model != LF_MODEL_FREE && n > 0 && !om_arr) return fail("lf_set_sources: FIXED/Z models need om_arr");
     if (model == LF_MODEL_Z && n > 0 && !z) return fail("lf_set_sources: Z model needs z");
     CK(cudaSetDevice(c->device));
-    dfree(c->d_lum); dfree(c->d_flux); dfree(c->d_z); dfree(c->d_om); dfree(c->d_Lsrc); dfree(c->d_src2);
+    dfree(c->d_lum); dfree(c->d_flux); dfree(c->d_z); dfree(c->d_om); dfree(c->d_Lsrc); dfree(c->d_src2); dfree(c->d_src2f);
     c->N = n;
     KArgs& a = c->ka;
     a.N = n;
@@ -975,8 +1065,9 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
         if (model == LF_MODEL_FREE) {
             CK(cudaMalloc(&c->d_flux, nb));
             CK(cudaMalloc(&c->d_src2, sizeof(double2) * (size_t)n));
+            if (c->cfg.precision == LF_PREC_F32) CK(cudaMalloc(&c->d_src2f, sizeof(float2) * (size_t)n));
             CK(cudaMemcpyAsync(c->d_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
-            k_derive_free<<<G, T, 0, c->stream>>>(n, c->d_lum, c->d_flux, c->d_src2, c->d_Lsrc, c->ka.fcap);
+            k_derive_free<<<G, T, 0, c->stream>>>(n, c->d_lum, c->d_flux, c->d_src2, c->d_Lsrc, c->ka.fcap, c->d_src2f);
         } else {
             CK(cudaMalloc(&c->d_om, nb));
             CK(cudaMemcpyAsync(c->d_om, om_arr, nb, cudaMemcpyHostToDevice, c->stream));
@@ -984,8 +1075,9 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
             if (model == LF_MODEL_Z) {
                 CK(cudaMalloc(&c->d_z, nb));
                 CK(cudaMalloc(&c->d_src2, sizeof(double2) * (size_t)n));
+                if (c->cfg.precision == LF_PREC_F32) CK(cudaMalloc(&c->d_src2f, sizeof(float2) * (size_t)n));
                 CK(cudaMemcpyAsync(c->d_z, z, nb, cudaMemcpyHostToDevice, c->stream));
-                k_derive_z<<<G, T, 0, c->stream>>>(n, c->d_lum, c->d_z, c->d_src2);
+                k_derive_z<<<G, T, 0, c->stream>>>(n, c->d_lum, c->d_z, c->d_src2, c->d_src2f, c->cfg.z_pivots[1]);
             }
         }
         CK(cudaGetLastError());
@@ -1024,7 +1116,7 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
     CK(cudaStreamSynchronize(c->stream));
     cudaFree(d_tmp);
     cudaFree(d_scratch);
-    a.src2 = c->d_src2; a.lum = c->d_lum; a.flux = c->d_flux; a.z = c->d_z; a.om_arr = c->d_om;
+    a.src2 = c->d_src2; a.src2f = c->d_src2f; a.lum = c->d_lum; a.flux = c->d_flux; a.z = c->d_z; a.om_arr = c->d_om;
     c->have_sources = true;
     return 0;
 }
@@ -1269,6 +1361,27 @@ extern "C" int lf_fp64_peak(lf_ctx* c, int32_t iters, double* dfma_per_s, double
     c->launches += 2;
     double n = (double)blocks * threads * (double)iters * 64.0;
     *dfma_per_s = n / (ms * 1.0e-3);
+    if (ms_out) *ms_out = ms;
+    return 0;
+}
+
+extern "C" int lf_mufu_peak(lf_ctx* c, int32_t iters, double* mufu_per_s, double* ms_out) {
+    if (!c || !mufu_per_s) return fail("lf_mufu_peak: null argument");
+    CK(cudaSetDevice(c->device));
+    float* sink = nullptr;
+    CK(cudaMalloc(&sink, sizeof(float)));
+    const int blocks = c->sm_count * 8, threads = 256;
+    k_mufu_peak<<<blocks, threads, 0, c->stream>>>(64, 0.25f, sink);       // warm-up
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_mufu_peak<<<blocks, threads, 0, c->stream>>>(iters, 0.25f, sink);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    cudaFree(sink);
+    c->launches += 2;
+    *mufu_per_s = (double)blocks * threads * (double)iters * 64.0 / (ms * 1.0e-3);
     if (ms_out) *ms_out = ms;
     return 0;
 }

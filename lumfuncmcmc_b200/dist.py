@@ -49,7 +49,7 @@ class ShardedLikelihood:
 
     ``inp`` is THIS rank's shard (already split, e.g. by :func:`shard_inputs`)."""
 
-    def __init__(self, inp, kind, device=None, group=None):
+    def __init__(self, inp, kind, device=None, group=None, precision='f64'):
         import torch
         import torch.distributed as dist
         from .engine import LikelihoodEngine
@@ -58,7 +58,8 @@ class ShardedLikelihood:
         self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.device = torch.cuda.current_device() if device is None else int(device)
-        self.engine = LikelihoodEngine(inp, kind, device=self.device, quadrature_share=(self.rank, self.world))
+        self.engine = LikelihoodEngine(inp, kind, device=self.device, quadrature_share=(self.rank, self.world),
+                                       precision=precision)
         self.ndim = self.engine.ndim
         self._cap = 0
 

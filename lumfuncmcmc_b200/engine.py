@@ -115,7 +115,10 @@ class VeffEngine(_VeffOps):
 class LikelihoodEngine(_VeffOps):
     """One engine context on one GPU holding one shard of sources."""
 
-    def __init__(self, inp, kind, device=0, force_literal=False, quadrature_share=(0, 1)):
+    def __init__(self, inp, kind, device=0, force_literal=False, quadrature_share=(0, 1), precision='f64'):
+        if precision not in ('f64', 'f32'):
+            raise ValueError("precision must be 'f64' or 'f32'")
+        self.precision = precision
         if kind not in KINDS:
             raise ValueError("kind must be one of %s" % sorted(KINDS))
         self.kind = kind
@@ -126,7 +129,8 @@ class LikelihoodEngine(_VeffOps):
         S = int(np.asarray(inp['zarr']).shape[0])
         fix_sch_al = bool(inp.get('fix_sch_al', False))
         cfg = _lib.LFConfig()
-        cfg.model, cfg.precision, cfg.device = KINDS[kind], _lib.LF_PREC_F64, int(device)
+        cfg.model, cfg.device = KINDS[kind], int(device)
+        cfg.precision = _lib.LF_PREC_F32 if precision == 'f32' else _lib.LF_PREC_F64
         cfg.nfields, cfg.size_ln, cfg.fix_sch_al = K, S, int(fix_sch_al)
         cfg.force_literal = int(bool(force_literal))
         cfg.fcmin = float(inp['fcmin']) if inp['fcmin'] else 0.0
@@ -231,6 +235,12 @@ class LikelihoodEngine(_VeffOps):
         launches = C.c_int64()
         _lib.check(self.lib.lf_last_call_info(self._ctx, counts, C.byref(launches)), self.lib)
         return dict(rejected=counts[0], fast=counts[1], literal=counts[2], launches=launches.value)
+
+    def mufu_peak(self, iters=20000):
+        """Measured MUFU ex2.approx.f32 rate of this GPU (thread-instructions per second) and the run time in ms."""
+        rate, ms = C.c_double(), C.c_double()
+        _lib.check(self.lib.lf_mufu_peak(self._ctx, int(iters), C.byref(rate), C.byref(ms)), self.lib)
+        return rate.value, ms.value
 
     def fp64_peak(self, iters=20000):
         """Measured register-only DFMA rate of this GPU (thread-instructions per second) and the run time in ms."""

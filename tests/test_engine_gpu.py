@@ -214,3 +214,36 @@ def test_veff_bit_exact_counts_large():
     want_s = np.bincount(j[ok], weights=ref_phi[ok], minlength=50)[:50]
     np.testing.assert_allclose(sums, want_s, rtol=1e-12)
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# optional FP32 mode of the walker x source loop: 1e-5 relative (BASELINE.json north_star)
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name,kind', [('free_k5_n2000', 'free'), ('free_k3_fixal', 'free'), ('z_k2_n800', 'z')])
+def test_fp32_mode_golden(golden, name, kind):
+    g = golden(name)
+    eng = _engine(g, kind, precision='f32')
+    got = eng.lnprob(g['thetas'])
+    rel = _assert_parity(got, g['lnprob_ref'], rtol=1e-5)
+    assert eng.last_call_info()['fast'] > 0
+    # and it really is a different arithmetic: not bit-identical to the FP64 engine
+    e64 = _engine(g, kind)
+    ref64 = e64.lnprob(g['thetas'])
+    fin = np.isfinite(ref64)
+    assert np.any(got[fin] != ref64[fin])
+    print(name, 'fp32 max rel', rel)
+    eng.close()
+    e64.close()
+
+
+@pytest.mark.parametrize('kind', ['free', 'z'])
+def test_fp32_mode_midsize_against_oracle(kind):
+    cat = synth.make_catalogue(200000, seed=22, evolve=(0.3, -0.2) if kind == 'z' else None)
+    inp = synth.direct_inputs(cat, nknots=2048, size_ln=101 if kind == 'free' else 201, tabulated=(kind != 'free'))
+    th = np.concatenate([synth.draw_thetas(inp, kind, 48, seed=5, mode='near', scale=0.02),
+                         synth.draw_thetas(inp, kind, 16, seed=6, mode='prior')])
+    eng = _engine(inp, kind, precision='f32')
+    got = eng.lnprob(th)
+    rel = _assert_parity(got, lf_oracle.lnprob_batch(inp, kind, th), rtol=1e-5)
+    print(kind, 'fp32 max rel', rel, eng.last_call_info())
+    eng.close()
