@@ -63,7 +63,7 @@ enum {
     P_LNPART0 = 7,  // source-sum part that collapses to sufficient statistics (fast class)
     // z model: quadratic coefficients
     P_AL = 8, P_BL = 9, P_CL = 10, P_AP = 11, P_BP = 12, P_CP = 13,
-    P_FIELD0 = 16,  // + 4*k + {0: aF, 1: cinv, 2: F50 (cgs), 3: ftau}
+    P_FIELD0 = 16,  // + 4*k + {0: aF = -alpha log10 F50, 1: c2 = -log2(e)/ftau, 2: F50 (cgs), 3: ftau}
     P_NSLOTS = P_FIELD0 + 4 * LF_MAX_FIELDS
 };
 
@@ -277,7 +277,7 @@ __global__ void k_prologue(KArgs a) {
                 double lgF = log10(F50);
                 double ftau = F50 * pow(10.0, b);
                 wp[(P_FIELD0 + 4 * k + 0) * WS] = -alpha_c * lgF;
-                wp[(P_FIELD0 + 4 * k + 1) * WS] = -1.0 / ftau;
+                wp[(P_FIELD0 + 4 * k + 1) * WS] = -LOG2E / ftau;
                 wp[(P_FIELD0 + 4 * k + 2) * WS] = F50;
                 wp[(P_FIELD0 + 4 * k + 3) * WS] = ftau;
                 // faintest flux the fast math will see in this field: sources and quadrature points
@@ -399,7 +399,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                     const double aFd = wp[(P_FIELD0 + 4 * k + 0) * WS];           // -alpha*log10(F50)
                     const float af = (float)alpha;
                     const float aFs = (float)(aFd - 17.0 * alpha);                 // -alpha*log10(F50*1e17)
-                    const float c2 = (float)(wp[(P_FIELD0 + 4 * k + 1) * WS] * (1.0e-17 * LOG2E));
+                    const float c2 = (float)(wp[(P_FIELD0 + 4 * k + 1) * WS] * 1.0e-17);
                     const float2* __restrict__ pf = a.src2f + i0;
                     const int cnt = (int)(seg_end - i0);
                     double sum = 0.0;
@@ -423,7 +423,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                     }
                     acc0 = fma(sum, LN2, acc0);
                 } else if (!LITERAL) {
-                    const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], cinv = wp[(P_FIELD0 + 4 * k + 1) * WS];
+                    const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], c2 = wp[(P_FIELD0 + 4 * k + 1) * WS];
                     long long i = i0;
                     if (a.modified) {
                         // 32-bit trip counter; four sources per trip as two independent pairs (two FP64 dependency
@@ -432,8 +432,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                         const int cnt = (int)(seg_end - i);
                         auto pair = [&](const double2& u0, const double2& u1) {
                             double lg0, rd0, lg1, rd1;
-                            fleming_log_parts<true>(u0.x, u0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
-                            fleming_log_parts<true>(u1.x, u1.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg1, rd1);
+                            fleming_log_parts<true>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            fleming_log_parts<true>(u1.x, u1.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg1, rd1);
                             acc0 = fma(lg0, rd0, acc0);
                             acc1 = fma(lg1, rd1, acc1);
                         };
@@ -442,10 +442,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                         // four independent chains per thread, the next four sources prefetched a trip ahead
                         auto quad = [&](const double2& u0, const double2& u1, const double2& u2, const double2& u3) {
                             double lg0, rd0, lg1, rd1, lg2, rd2, lg3, rd3;
-                            fleming_log_parts<true>(u0.x, u0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
-                            fleming_log_parts<true>(u1.x, u1.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg1, rd1);
-                            fleming_log_parts<true>(u2.x, u2.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg2, rd2);
-                            fleming_log_parts<true>(u3.x, u3.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg3, rd3);
+                            fleming_log_parts<true>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            fleming_log_parts<true>(u1.x, u1.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg1, rd1);
+                            fleming_log_parts<true>(u2.x, u2.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg2, rd2);
+                            fleming_log_parts<true>(u3.x, u3.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg3, rd3);
                             acc0 = fma(lg0, rd0, acc0);
                             acc1 = fma(lg1, rd1, acc1);
                             acc0 = fma(lg2, rd2, acc0);
@@ -471,14 +471,14 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                         for (; j < cnt; ++j) {
                             double2 s0 = __ldg(ps + j);
                             double lg0, rd0;
-                            fleming_log_parts<true>(s0.x, s0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            fleming_log_parts<true>(s0.x, s0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
                             acc0 = fma(lg0, rd0, acc0);
                         }
                     } else {
                         for (; i < seg_end; ++i) {
                             double2 s0 = __ldg(&a.src2[i]);
                             double lg0, rd0;
-                            fleming_log_parts<false>(s0.x, s0.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            fleming_log_parts<false>(s0.x, s0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
                             acc0 += lg0;
                         }
                     }
@@ -528,19 +528,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                 }
                 acc0 -= sum;
             } else if (!LITERAL) {
-                // only sum_i 10^(lum_i - L*(z_i)) needs the walker x source loop; the rest is in P_LNPART0
+                // only sum_i 10^(lum_i - L*(z_i)) needs the walker x source loop; the rest is in P_LNPART0.
+                // Base 2 throughout: 2^(log2(10) lum_i - P2(z_i)), 11 FP64 instructions per term
+                const double L2T = 3.32192809488736234787;                              // log2(10)
+                const double a2 = aL * L2T, b2 = bL * L2T, c2 = cL * L2T;
                 long long i = i0;
                 for (; i + 1 < i1; i += 2) {
                     double2 s0 = __ldg(&a.src2[i]), s1 = __ldg(&a.src2[i + 1]);
-                    double d0 = s0.x - fma(fma(aL, s0.y, bL), s0.y, cL);
-                    double d1 = s1.x - fma(fma(aL, s1.y, bL), s1.y, cL);
-                    acc0 -= exp_full(d0 * LN10, s_exp, rep16);
-                    acc1 -= exp_full(d1 * LN10, s_exp, rep16);
+                    double d0 = fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2));
+                    double d1 = fma(L2T, s1.x, -fma(fma(a2, s1.y, b2), s1.y, c2));
+                    acc0 -= exp2_full(d0, s_exp, rep16);
+                    acc1 -= exp2_full(d1, s_exp, rep16);
                 }
                 if (i < i1) {
                     double2 s0 = __ldg(&a.src2[i]);
-                    double d0 = s0.x - fma(fma(aL, s0.y, bL), s0.y, cL);
-                    acc0 -= exp_full(d0 * LN10, s_exp, rep16);
+                    double d0 = fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2));
+                    acc0 -= exp2_full(d0, s_exp, rep16);
                 }
             } else {
                 const double aP = wp[P_AP * WS], bP = wp[P_BP * WS], cP = wp[P_CP * WS], sal = wp[P_SCHAL * WS];
@@ -567,15 +570,15 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                     int k = (int)(q0 / SS);
                     long long seg_end = (k + 1) * SS < q1 ? (k + 1) * SS : q1;
                     if (!LITERAL) {
-                        const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], cinv = wp[(P_FIELD0 + 4 * k + 1) * WS];
+                        const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], c2 = wp[(P_FIELD0 + 4 * k + 1) * WS];
                         // one quadrature point: weight * exp(Schechter exponent + ln completeness)
                         auto point = [&](const QuadPointFree* pt, double& acc) {
                             double2 gf = __ldg(reinterpret_cast<const double2*>(pt));
                             double2 xl = __ldg(reinterpret_cast<const double2*>(pt) + 1);
                             double wt = __ldg(reinterpret_cast<const double2*>(pt) + 2).x;
                             double lg, rd;
-                            if (a.modified) fleming_log_parts<true>(gf.x, gf.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg, rd);
-                            else fleming_log_parts<false>(gf.x, gf.y, alpha, aF, cinv, s_exp, s_log, rep16, rep8, lg, rd);
+                            if (a.modified) fleming_log_parts<true>(gf.x, gf.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg, rd);
+                            else fleming_log_parts<false>(gf.x, gf.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg, rd);
                             double arg = fma(c1, xl.x, c0);
                             arg = fma(-xl.y, tenmL, arg);
                             arg = fma(lg, rd, arg);
@@ -918,7 +921,7 @@ static void fill_tables(Tables& t) {
         long double cm = 1.0L + ((long double)j + 0.5L) / M;          // bin centre of the mantissa
         double invc = ldexp((double)(1.0L / cm), -E);                    // 1 / (cm * 2^E), power-of-two scaling is exact
         t.log_tab[b].x = invc;
-        t.log_tab[b].y = (double)(-logl((long double)invc));             // consistent with the rounded 1/c
+        t.log_tab[b].y = (double)(-logl((long double)invc) + (long double)LOG1P_C0);   // consistent with the rounded 1/c; + fit constant
     }
     t.log_tab[LOG_OCTAVES * M].x = 1.0;  t.log_tab[LOG_OCTAVES * M].y = 0.0;       // argument exactly 1
     t.log_tab[LOG_OCTAVES * M + 1] = t.log_tab[LOG_OCTAVES * M];

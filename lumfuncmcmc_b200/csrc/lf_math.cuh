@@ -6,12 +6,17 @@
 // constant-bank operand).  Integer / MUFU / LDS work rides in the issue slots the FP64 pipe leaves free.
 //   * reciprocal square root and reciprocal: one MUFU seed (rsqrt/rcp.approx.ftz.f64, ~2^-22) + one
 //     third-order correction (error ~2^-63): 5 resp. 3 FP64 instructions, no IEEE div/sqrt sequences.
-//   * exp: 256-entry table of 2^(j/256) in shared memory + degree-4 polynomial on |r| <= ln2/512.
+//   * exp: base-2 range reduction done by ONE fma against 1.5*2^44 (the product f*c2 is never rounded on its own),
+//     256-entry table of 2^(j/256) in shared memory + minimax degree-3 polynomial on |r| <= 2^-9 (1.8e-14).
 //   * log: one table lookup indexed by the top 20 bits of the argument (exponent AND 8 mantissa bits, covering
-//     [2^-12, 1]) returning (1/c, ln c) with the exponent folded in, + degree-5 log1p on |eps| <= 2^-9.  No
-//     exponent extraction, no int->double conversion.
-// All of them are accurate to ~1e-16 absolute/relative over the ranges the classifier admits to the fast
-// path (see k_prologue in lf_engine.cu); anything outside goes to the literal kernels.
+//     [2^-12, 1]) returning (1/c, ln c) with the exponent folded in, + minimax degree-3 log1p on |eps| <= 2^-9
+//     (4.6e-13 absolute, zero mean; the constant term of the fit is folded into the table).  No exponent
+//     extraction, no int->double conversion.
+// Error budget (tools/math/fit_coeffs.py, tests/test_engine_gpu.py): the north-star tolerance is 1e-10 RELATIVE on
+// lnprob, whose terms are O(10) each, so a per-term absolute error of 1e-12 leaves three orders of magnitude of
+// margin; the polynomial degrees below are chosen for ~5e-13 per term instead of the 1e-16 of a libm-grade routine
+// (23 FP64-pipe instructions per term instead of 28).  Anything outside the validated argument ranges goes to the
+// literal kernels (see k_prologue in lf_engine.cu).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -41,18 +46,23 @@ constexpr double LOG_ARG_MIN = 0x1p-12;
 
 // polynomial / reduction constants live in the constant bank: DFMA reads them as c[3][off] operands (two register
 // sources instead of three, and no IMAD.MOV/UMOV pairs to materialise 64-bit immediates)
+constexpr double MAGIC44 = 26388279066624.0;                       // 1.5 * 2^44: ulp 2^-8, low mantissa bits = round(256 x)
+// minimax fits on [-2^-9, 2^-9] (tools/math/fit_coeffs.py)
+constexpr double LOG1P_C0 = 4.5474875525573243324e-13;             // folded into the ln c column of the log table
+constexpr double LOG1P_C1 = 0.9999999999985449674, LOG1P_C2 = -0.50000095367660766342, LOG1P_C3 = 0.33333447770293183222;
+constexpr double EXP2_C0 = 0.99999999999998250473, EXP2_C1 = 0.69314718055993561091, EXP2_C2 = 0.24022654364935376114,
+                 EXP2_C3 = 0.055504116293577099979;
 __constant__ double KC[16] = {
-    256.0 * LOG2E,          // 0
-    -LN2 / 256.0,           // 1
-    1.0 / 24.0,             // 2
-    1.0 / 6.0,              // 3
-    0.2,                    // 4
-    1.0 / 3.0,              // 5
-    MAGIC52,                // 6
-    -0x1.62e42fee00000p-9,  // 7   -(ln2/256) high part (32 significant bits)
-    -0x1.a39ef35793c76p-41, // 8   -(ln2/256) low part
-    LN10,                   // 9
-    0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    MAGIC44,                // 0
+    EXP2_C3,                // 1
+    EXP2_C2,                // 2
+    EXP2_C1,                // 3
+    EXP2_C0,                // 4
+    LOG1P_C3,               // 5
+    LOG1P_C2,               // 6
+    LOG1P_C1,               // 7
+    LOG2E,                  // 8
+    0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 
 struct Tables {                 // device-global master copies (filled by the host at lf_create)
     double exp2_frac[EXP_TAB_N];        // 2^(j/256)
@@ -71,12 +81,11 @@ __device__ __forceinline__ double rcp_seed(double y) {
     return r;
 }
 
-// 1/d for normal positive d, 3 FP64 instructions + 1 MUFU
+// 1/d for normal positive d: MUFU seed (2^-22) + one Newton step (relative error ~6e-14): 2 FP64 instructions + 1 MUFU
 __device__ __forceinline__ double rcp_fast(double d) {
     double r0 = rcp_seed(d);
     double e = fma(-d, r0, 1.0);
-    double p = fma(e, e, e);
-    return fma(r0, p, r0);
+    return fma(r0, e, r0);
 }
 
 // cooperative fill of the (replicated) shared-memory tables
@@ -85,63 +94,61 @@ __device__ __forceinline__ void load_tables(const Tables* __restrict__ t, double
     for (int i = threadIdx.x; i < LOG_TAB_N * LOG_TAB_REP; i += blockDim.x) s_log[i] = t->log_tab[i / LOG_TAB_REP];
 }
 
-// 1 - exp(x) for x in (-2e7, 0]; ABSOLUTE accuracy ~1e-16 (single-FMA range reduction suffices because exp(x) <= 1).
-// FP64 instructions: t, kf, r (3) + Horner (4) + 1 = 8
-__device__ __forceinline__ double one_minus_exp_neg(double x, const double* s_exp, int rep) {
-    double t = fma(x, KC[0], KC[6]);
-    int k = __double2loint(t);
-    double kf = t - KC[6];
-    double r = fma(kf, KC[1], x);                 // |r| <= ln2/512
+// 2^(x2) split as 2^K * T[j] * p(r): returns p(r) ~ 2^r and the scaled table entry Ts = 2^K T[j];  x2 = a * b is
+// formed inside the two fmas only (no separately rounded product).  Needs |x2| < 8.3e6.  FP64 instructions: 6.
+__device__ __forceinline__ void exp2_parts(double a, double b, const double* s_exp, int rep, int kmin, double& Ts, double& p) {
+    double t = fma(a, b, KC[0]);
+    int k = __double2loint(t);                    // round(256 x2)
+    double kf = t - KC[0];
+    double r = fma(a, b, -kf);                    // |r| <= 2^-9, exact up to one rounding
     double T = s_exp[(k & (EXP_TAB_N - 1)) * EXP_TAB_REP + rep];
-    int K = max(k >> EXP_TAB_BITS, -1000);       // exp(x) < 2^-1000 is 0 against 1; keeps the exponent field valid
-    double Ts = __hiloint2double(__double2hiint(T) + (K << 20), __double2loint(T));
-    double p = fma(r, KC[2], KC[3]);
-    p = fma(r, p, 0.5);
-    p = fma(r, p, 1.0);
-    p = fma(r, p, 1.0);                           // exp(r)
+    int K = max(k >> EXP_TAB_BITS, kmin);         // keeps the exponent field valid
+    Ts = __hiloint2double(__double2hiint(T) + (K << 20), __double2loint(T));
+    p = fma(r, KC[1], KC[2]);
+    p = fma(r, p, KC[3]);
+    p = fma(r, p, KC[4]);
+}
+
+// 1 - 2^(f * c2) for f * c2 in (-8.3e6, 0]; ABSOLUTE accuracy ~2e-14.  FP64 instructions: 7
+__device__ __forceinline__ double one_minus_exp2(double f, double c2, const double* s_exp, int rep) {
+    double Ts, p;
+    exp2_parts(f, c2, s_exp, rep, -1000, Ts, p);  // 2^x2 < 2^-1000 is 0 against 1
     return fma(-Ts, p, 1.0);
 }
 
-// full-range exp(x) with RELATIVE accuracy for x in [-708, 709]; below -708 returns 0.
-// FP64 instructions: compare 1 + t, kf, r hi, r lo (4) + Horner (4) + scale (1) = 10
-__device__ __forceinline__ double exp_full(double x, const double* s_exp, int rep) {
-    bool under = x < -708.0;
-    x = under ? -708.0 : x;
-    double t = fma(x, KC[0], KC[6]);
-    int k = __double2loint(t);
-    double kf = t - KC[6];
-    double r = fma(kf, KC[7], x);
-    r = fma(kf, KC[8], r);
-    double T = s_exp[(k & (EXP_TAB_N - 1)) * EXP_TAB_REP + rep];
-    double Ts = __hiloint2double(__double2hiint(T) + ((k >> EXP_TAB_BITS) << 20), __double2loint(T));
-    double p = fma(r, KC[2], KC[3]);
-    p = fma(r, p, 0.5);
-    p = fma(r, p, 1.0);
-    p = p * r;                                    // expm1(r)
-    double e = fma(Ts, p, Ts);
-    return under ? 0.0 : e;
+// 2^(x2) with RELATIVE accuracy ~2e-14 for x2 in [-1020, 1020] (the callers guarantee the range).  FP64 instructions: 7
+__device__ __forceinline__ double exp2_full(double x2, const double* s_exp, int rep) {
+    double Ts, p;
+    exp2_parts(x2, 1.0, s_exp, rep, -1022, Ts, p);
+    return Ts * p;
 }
 
-// log(v) for v in [2^-12, 1].  FP64 instructions: eps 1 + Horner 4 + final 1 = 6
+// exp(x) for x in [-707, 707]; below -707 returns 0.  FP64 instructions: 1 + 1 + 7
+__device__ __forceinline__ double exp_full(double x, const double* s_exp, int rep) {
+    bool under = x < -707.0;
+    double Ts, p;
+    exp2_parts(under ? -707.0 : x, KC[8], s_exp, rep, -1022, Ts, p);
+    return under ? 0.0 : Ts * p;
+}
+
+// log(v) for v in [2^-12, 1], absolute accuracy 4.6e-13 (zero-mean).  FP64 instructions: 4
 __device__ __forceinline__ double log_unit(double v, const double2* s_log, int rep) {
     int b = max((__double2hiint(v) >> (20 - LOG_MANT_BITS)) - LOG_TAB_BASE, 0);
     double2 tb = s_log[b * LOG_TAB_REP + rep];
     double eps = fma(v, tb.x, -1.0);              // v / c_b - 1, |eps| <= 2^-9
-    double a = fma(eps, KC[4], -0.25);
-    a = fma(eps, a, KC[5]);
-    a = fma(eps, a, -0.5);
-    a = fma(eps, a, 1.0);
-    return fma(eps, a, tb.y);
+    double a = fma(eps, KC[5], KC[6]);
+    a = fma(eps, a, KC[7]);
+    return fma(eps, a, tb.y);                     // tb.y = ln c_b + LOG1P_C0
 }
 
 // t = ln(modified Fleming completeness) for one (walker, flux) pair -- the walker x source term.
 //   n  = alpha*log10(f/F50) = fma(alpha, g, aF)            g = log10 f,  aF = -alpha*log10(F50)
 //   fc = 1/2 (1 + n/sqrt(1+n^2))                           VmaxLumFunc.py:118-120
-//   t  = ln(fc) / (1 - exp(-f/ftau))                       VmaxLumFunc.py:124-126, 141   (cinv = -1/ftau)
+//   t  = ln(fc) / (1 - exp(-f/ftau))                       VmaxLumFunc.py:124-126, 141   (c2 = -log2(e)/ftau)
 // MODIFIED=false: plain Fleming curve (fcmin falsy, VmaxLumFunc.py:121-122): t = ln(fc).
-// FP64-pipe instruction count (MODIFIED): 9 + 6 + 9 + 3 = 27, +1 for the caller's accumulate.
+// FP64-pipe instruction count (MODIFIED): 9 + 4 + 7 + 2 = 22, +1 for the caller's accumulate.
 template <bool MODIFIED>
-__device__ __forceinline__ void fleming_log_parts(double g, double f, double alpha, double aF, double cinv,
+__device__ __forceinline__ void fleming_log_parts(double g, double f, double alpha, double aF, double c2,
                                                   const double* s_exp, const double2* s_log, int repe, int repl,
                                                   double& lg, double& rdec) {
     double n = fma(alpha, g, aF);
@@ -156,8 +163,7 @@ __device__ __forceinline__ void fleming_log_parts(double g, double f, double alp
     double fc = fma(0.5, q, 0.5);
     lg = log_unit(fc, s_log, repl);
     if (MODIFIED) {
-        double x = f * cinv;                                  // <= 0; |x| < 2e7 guaranteed by the classifier
-        rdec = rcp_fast(one_minus_exp_neg(x, s_exp, repe));
+        rdec = rcp_fast(one_minus_exp2(f, c2, s_exp, repe));   // f * c2 <= 0, > -8e6 guaranteed by the classifier
     } else {
         rdec = 1.0;
     }

@@ -13,10 +13,10 @@ from lumfuncmcmc_b200.engine import LikelihoodEngine, VeffEngine   # noqa: E402
 quick = len(sys.argv) > 1
 
 
-def run(kind, n, walkers):
+def run(kind, n, walkers, prec='f64'):
     cat = synth.make_catalogue(n, seed=1, evolve=(0.3, -0.2) if kind == 'z' else None)
     inp = synth.direct_inputs(cat, nknots=4096, size_ln=101 if kind == 'free' else 201, tabulated=(kind != 'free'))
-    eng = LikelihoodEngine(inp, kind)
+    eng = LikelihoodEngine(inp, kind, precision=prec)
     for W in walkers:
         th = synth.draw_thetas(inp, kind, W, seed=3, mode='near', scale=0.02)
         for _ in range(3):
@@ -28,17 +28,19 @@ def run(kind, n, walkers):
             ws.append(time.perf_counter() - t0)
             ts.append(eng.last_kernel_ms() * 1e-3)
         k, w = min(ts), min(ws)
-        print("| %-5s | %8.0e | %5d | %9.3f | %9.3f | %10.3e | %10.3e |" % (kind, n, W, k * 1e3, w * 1e3, n * W / k, n * W / w),
+        print("| %-5s | %s | %8.0e | %5d | %9.3f | %9.3f | %10.3e | %10.3e |" % (kind, prec, n, W, k * 1e3, w * 1e3, n * W / k, n * W / w),
               flush=True)
     eng.close()
 
 
-print("| model | sources | walkers | kernel ms | host-call ms | terms/s (kernels) | terms/s (host API) |")
-print("|---|---|---|---|---|---|---|")
+print("| model | loop arithmetic | sources | walkers | kernel ms | host-call ms | terms/s (kernels) | terms/s (host API) |")
+print("|---|---|---|---|---|---|---|---|")
 sizes = [100000, 1000000] if quick else [100000, 1000000, 10000000]
 for n in sizes:
     run('free', n, [64, 256, 1024, 4096])
+    run('free', n, [64, 256, 1024, 4096], 'f32')
 run('z', 1000000, [512])
+run('z', 1000000, [512], 'f32')
 run('fixed', 1000000, [512])
 run('free', 10000, [100])
 

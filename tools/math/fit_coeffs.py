@@ -1,0 +1,41 @@
+"""Near-minimax polynomial coefficients for the trimmed FP64 routines of lf_math.cuh (math v4).
+Remez exchange in 40-digit arithmetic (mpmath) on the scaled variable u = x / h; prints the coefficients and the
+achieved maximum absolute error.    python tools/math/fit_coeffs.py"""
+import mpmath as mp
+
+mp.mp.dps = 40
+
+
+def remez(f, powers, h, iters=12, ngrid=4001):
+    """minimax fit of f(x) ~ sum_k c_k x^p_k on [-h, h] (absolute error); returns (c, max_err)."""
+    m = len(powers)
+    u = [-mp.cos(mp.pi * i / m) for i in range(m + 1)]
+    grid = [mp.mpf(-1) + mp.mpf(2) * i / (ngrid - 1) for i in range(ngrid)]
+    fg = [f(h * g) for g in grid]
+    c = None
+    for _ in range(iters):
+        A = mp.matrix(m + 1, m + 1)
+        b = mp.matrix(m + 1, 1)
+        for i, ui in enumerate(u):
+            for k, p in enumerate(powers):
+                A[i, k] = ui ** p
+            A[i, m] = (-1) ** i
+            b[i] = f(h * ui)
+        sol = mp.lu_solve(A, b)
+        c = [sol[k] for k in range(m)]
+        err = [sum(c[k] * g ** p for k, p in enumerate(powers)) - fg[i] for i, g in enumerate(grid)]
+        ext = [0] + [i for i in range(1, ngrid - 1) if (err[i] - err[i - 1]) * (err[i + 1] - err[i]) <= 0] + [ngrid - 1]
+        ext = sorted(sorted(ext, key=lambda i: -abs(err[i]))[:m + 1])
+        if len(ext) == m + 1:
+            u = [grid[i] for i in ext]
+    emax = max(abs(e) for e in err)
+    return [c[k] / h ** p for k, p in enumerate(powers)], emax
+
+
+if __name__ == '__main__':
+    h = mp.mpf(2) ** -9
+    for name, f in (("log1p(x)", mp.log1p), ("2^x", lambda x: mp.power(2, x))):
+        for deg in (3, 4):
+            c, e = remez(f, list(range(0, deg + 1)), h)
+            print("%s degree %d on |x| <= 2^-9: max abs err %s" % (name, deg, mp.nstr(e, 3)))
+            print("    " + ", ".join(mp.nstr(v, 20) for v in c))
