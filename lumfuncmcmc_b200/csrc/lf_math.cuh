@@ -169,4 +169,148 @@ __device__ __forceinline__ void fleming_log_parts(double g, double f, double alp
     }
 }
 
+// NT independent (walker, source) terms evaluated in lock-step and added to acc[0..NT-1].  The source is written phase
+// by phase so that the NT independent FP64 chains sit next to each other in the instruction stream: on B200 the FP64
+// pipe issues one warp instruction per 2 cycles only while consecutive DFMAs come from the SAME warp (3 cycles when the
+// scheduler has to alternate between warps, tools/microbench/fp64_mix.cu), so a warp must offer >= 4 independent DFMAs
+// at every point of the chain (DFMA latency 8 cycles).
+template <int NT>
+__device__ __forceinline__ void fleming_terms(const double2* u, double alpha, double aF, double c2, const double* s_exp,
+                                              const double2* s_log, int repe, int repl, double* acc) {
+    double n[NT], y[NT], r0[NT], e[NT], q[NT], fc[NT], lg[NT], dec[NT];
+    double t[NT], r[NT], Ts[NT], p[NT];
+    double2 tb[NT];
+    int k[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) n[i] = fma(alpha, u[i].x, aF);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) t[i] = fma(u[i].y, c2, KC[0]);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) y[i] = fma(n[i], n[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) r0[i] = rsqrt_seed(y[i]);
+    // exp branch while the MUFUs are in flight
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        k[i] = __double2loint(t[i]);
+        t[i] = t[i] - KC[0];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        double T = s_exp[(k[i] & (EXP_TAB_N - 1)) * EXP_TAB_REP + repe];
+        int K = max(k[i] >> EXP_TAB_BITS, -1000);
+        Ts[i] = __hiloint2double(__double2hiint(T) + (K << 20), __double2loint(T));
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) r[i] = fma(u[i].y, c2, -t[i]);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], KC[1], KC[2]);
+    // rsqrt correction
+#pragma unroll
+    for (int i = 0; i < NT; ++i) y[i] = y[i] * r0[i];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) e[i] = fma(-y[i], r0[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) n[i] = n[i] * r0[i];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) y[i] = fma(0.375, e[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], KC[3]);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) e[i] = y[i] * e[i];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], KC[4]);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) q[i] = fma(n[i], e[i], n[i]);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) dec[i] = fma(-Ts[i], p[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) fc[i] = fma(0.5, q[i], 0.5);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) r0[i] = rcp_seed(dec[i]);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+        int b = (__double2hiint(fc[i]) >> (20 - LOG_MANT_BITS)) - LOG_TAB_BASE;
+        tb[i] = s_log[b * LOG_TAB_REP + repl];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; ++i) e[i] = fma(-dec[i], r0[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) fc[i] = fma(fc[i], tb[i].x, -1.0);          // eps
+#pragma unroll
+    for (int i = 0; i < NT; ++i) r0[i] = fma(r0[i], e[i], r0[i]);           // 1 / dec
+#pragma unroll
+    for (int i = 0; i < NT; ++i) lg[i] = fma(fc[i], KC[5], KC[6]);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) lg[i] = fma(fc[i], lg[i], KC[7]);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) lg[i] = fma(fc[i], lg[i], tb[i].y);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) acc[i] = fma(lg[i], r0[i], acc[i]);
+}
+
+// ---- libm-grade (~2e-16) routines for the streaming 1/V_eff kernel: its per-source weights are compared at 1e-13 and
+// ---- its shared memory holds histograms, so these use two small UNREPLICATED tables (6 KB): the [1/2, 1) octave of
+// ---- the log table and the 2^(j/256) table, with the exponent handled arithmetically and Taylor polynomials ----
+constexpr int STREAM_LOG_N = 1 << LOG_MANT_BITS;
+constexpr double LN2_HI = 0.693147180369123816490, LN2_LO = 1.90821492927058770002e-10;
+// coefficients in the constant bank (c[3][..] operands: no UMOV pairs to materialise 64-bit immediates)
+__constant__ double KS[16] = {
+    -1.0 / 6.0, 0.2, 1.0 / 3.0,                      // 0-2   log1p
+    LN2_HI, LN2_LO,                                  // 3-4
+    256.0 * LOG2E, MAGIC52, -LN2_HI / 256.0, -LN2_LO / 256.0,   // 5-8   exp range reduction
+    1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0,              // 9-11  expm1
+    0.43429448190325182765,                          // 12    log10(e)
+    0.0, 0.0, 0.0};
+
+__device__ __forceinline__ void load_stream_tables(const Tables* __restrict__ t, double* s_exp, double2* s_logm) {
+    for (int i = threadIdx.x; i < EXP_TAB_N; i += blockDim.x) s_exp[i] = t->exp2_frac[i];
+    for (int i = threadIdx.x; i < STREAM_LOG_N; i += blockDim.x) {
+        double2 e = t->log_tab[(LOG_OCTAVES - 1) * STREAM_LOG_N + i];     // octave [1/2, 1): (1/c, ln c + LOG1P_C0)
+        s_logm[i] = make_double2(e.x, e.y - LOG1P_C0);
+    }
+}
+
+// ln(v) for positive normal v.  ~11 FP64-pipe instructions
+__device__ __forceinline__ double log_stream(double v, const double2* s_logm) {
+    const int hi = __double2hiint(v);
+    const int e = (hi >> 20) - 1022;                                        // v = 2^e m, m in [1/2, 1)
+    const double m = __hiloint2double((hi & 0x000fffff) | 0x3fe00000, __double2loint(v));
+    const double2 tb = s_logm[(hi >> (20 - LOG_MANT_BITS)) & (STREAM_LOG_N - 1)];
+    const double eps = fma(m, tb.x, -1.0);                                  // |eps| <= 2^-9
+    double p = fma(eps, KS[0], KS[1]);
+    p = fma(eps, p, -0.25);
+    p = fma(eps, p, KS[2]);
+    p = fma(eps, p, -0.5);
+    p = fma(eps * eps, p, eps);                                             // log1p(eps)
+    const double ef = (double)e;
+    return fma(ef, KS[3], fma(ef, KS[4], tb.y + p));
+}
+
+// exp(x) for x in [-700, 700] (callers guarantee the range).  ~12 FP64-pipe instructions
+__device__ __forceinline__ double exp_stream(double x, const double* s_exp) {
+    const double t = fma(x, KS[5], KS[6]);
+    const int k = __double2loint(t);
+    const double kf = t - KS[6];
+    double r = fma(kf, KS[7], x);
+    r = fma(kf, KS[8], r);                                                  // |r| <= ln2/512
+    const double T = s_exp[k & (EXP_TAB_N - 1)];
+    const double Ts = __hiloint2double(__double2hiint(T) + ((k >> EXP_TAB_BITS) << 20), __double2loint(T));
+    double p = fma(r, KS[9], KS[10]);
+    p = fma(r, p, KS[11]);
+    p = fma(r, p, 0.5);
+    p = fma(r, p, 1.0);
+    p = p * r;                                                              // expm1(r)
+    return fma(Ts, p, Ts);
+}
+
+// 1/d to ~1e-16 for normal positive d: MUFU seed + two Newton steps
+__device__ __forceinline__ double rcp_stream(double d) {
+    double r = rcp_seed(d);
+    double e = fma(-d, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-d, r, 1.0);
+    return fma(r, e, r);
+}
+
 }  // namespace lfm

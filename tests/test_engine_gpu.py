@@ -189,15 +189,17 @@ def test_veff_weights_and_bit_exact_bin_counts(golden):
     eng.close()
 
 
-def test_veff_bit_exact_counts_large():
-    """1e6 sources, 50 bins: integer counts identical to NumPy's mask counts on the exact linspace edges."""
+@pytest.mark.parametrize('nbins', [50, 700])
+def test_veff_bit_exact_counts_large(nbins):
+    """1e6 sources: integer counts identical to NumPy's mask counts on the exact linspace edges.  50 bins (the
+    reference's default) runs the lane-private histogram kernel, 700 bins the shared-memory-atomics fallback."""
     rng = np.random.default_rng(4)
     n = 1000000
     lum = rng.uniform(40.9, 44.0, n)
     lum[:1000] = lum[1000:2000]                    # ties
     flux = 10 ** rng.uniform(-17.2, -14.5, n)
     fi = np.array([0, n // 3, n // 2, n], dtype=np.int64)
-    edges = np.linspace(lum.min() * 1.001, lum.max(), 51)
+    edges = np.linspace(lum.min() * 1.001, lum.max(), nbins + 1)
     lum[5000:5050] = edges[:50]                    # values exactly on the edges
     from lumfuncmcmc_b200.engine import LikelihoodEngine
     eng = LikelihoodEngine(synth.direct_inputs(synth.make_catalogue(300, seed=1, nfields=3), nknots=64), 'free', device=0)
@@ -211,8 +213,13 @@ def test_veff_bit_exact_counts_large():
     np.testing.assert_allclose(phi, ref_phi, rtol=1e-13)
     j = np.searchsorted(edges, lum, side='right') - 1
     ok = (lum >= edges[0]) & (lum < edges[-1])
-    want_s = np.bincount(j[ok], weights=ref_phi[ok], minlength=50)[:50]
+    want_s = np.bincount(j[ok], weights=ref_phi[ok], minlength=nbins)[:nbins]
     np.testing.assert_allclose(sums, want_s, rtol=1e-12)
+    # a bootstrap replicate on the resident sample: counts exact, sums to 1e-12
+    mult = np.bincount(rng.integers(0, n, n), minlength=n)
+    bc, bs = eng.boot_bin(mult)
+    assert np.array_equal(bc, np.bincount(j[ok], weights=mult[ok], minlength=nbins)[:nbins].astype(np.int64))
+    np.testing.assert_allclose(bs, np.bincount(j[ok], weights=(ref_phi * mult)[ok], minlength=nbins)[:nbins], rtol=1e-12)
     eng.close()
 
 

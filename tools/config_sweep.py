@@ -58,12 +58,12 @@ for _ in range(2):
     wall = time.perf_counter() - t0
 kms = ve.last_kernel_ms()
 want = np.histogram(lum[(lum >= edges[0]) & (lum < edges[-1])], bins=edges)[0]
-print("\nVeff: N=%d nbins=50  kernel %.3f ms (%.3e sources/s, %.1f GB/s of 24 B/source)  host call %.1f ms  counts bit-exact: %s"
-      % (n, kms, n / (kms * 1e-3), 24.0 * n / (kms * 1e-3) / 1e9, wall * 1e3, np.array_equal(counts, want)))
+print("\nVeff: N=%d nbins=50  kernel %.3f ms (%.3e sources/s, %.1f GB/s of 26 B/source: flux, lum in; phi, bin i16 out)  host call %.1f ms  counts bit-exact: %s"
+      % (n, kms, n / (kms * 1e-3), 26.0 * n / (kms * 1e-3) / 1e9, wall * 1e3, np.array_equal(counts, want)))
 mult = np.bincount(rng.integers(0, n, n), minlength=n)
 t0 = time.perf_counter()
 bc, bs = ve.boot_bin(mult)
 wall = time.perf_counter() - t0
 kms = ve.last_kernel_ms()
-print("bootstrap replicate: kernel %.3f ms (%.1f GB/s of 20 B/source)  host call %.1f ms  counts sum %d" % (
-    kms, 20.0 * n / (kms * 1e-3) / 1e9, wall * 1e3, bc.sum()))
+print("bootstrap replicate: kernel %.3f ms (%.1f GB/s of 14 B/source: bin i16 + phi f64 + multiplicity i32)  host call %.1f ms  counts sum %d" % (
+    kms, 14.0 * n / (kms * 1e-3) / 1e9, wall * 1e3, bc.sum()))

@@ -1,0 +1,37 @@
+"""BASELINE.json configs[3]: 1/V_eff weights + binned LF + one bootstrap replicate on N sources (HBM-bound pass).
+    python tools/veff_perf.py [N] [nbins]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lumfuncmcmc_b200.engine import VeffEngine   # noqa: E402
+
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10000000
+nbins = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+rng = np.random.default_rng(4)
+lum = rng.uniform(40.9, 44.0, n)
+flux = 10 ** rng.uniform(-17.2, -14.5, n)
+fi = np.array([0, n // 5, 2 * n // 5, 3 * n // 5, 4 * n // 5, n], dtype=np.int64)
+edges = np.linspace(lum.min() * 1.001, lum.max(), nbins + 1)
+ve = VeffEngine()
+best = 1e9
+for _ in range(4):
+    t0 = time.perf_counter()
+    phi, counts, sums = ve.veff_bin(flux, lum, fi, [2.72, 3.61, 2.55, 3.31, 3.30], 4.56, 0.1, 1.9e6, 3.0e10, edges)
+    wall = time.perf_counter() - t0
+    best = min(best, ve.last_kernel_ms())
+want = np.histogram(lum[(lum >= edges[0]) & (lum < edges[-1])], bins=edges)[0]
+print("Veff: N=%d nbins=%d  kernel %.3f ms (%.3e sources/s, %.1f GB/s of 26 B/source: flux, lum in; phi, bin i16 out)  host call %.1f ms  counts bit-exact: %s"
+      % (n, nbins, best, n / (best * 1e-3), 26.0 * n / (best * 1e-3) / 1e9, wall * 1e3, np.array_equal(counts, want)))
+mult = np.bincount(rng.integers(0, n, n), minlength=n)
+best = 1e9
+for _ in range(4):
+    t0 = time.perf_counter()
+    bc, bs = ve.boot_bin(mult)
+    wall = time.perf_counter() - t0
+    best = min(best, ve.last_kernel_ms())
+print("bootstrap replicate: kernel %.3f ms (%.1f GB/s of 14 B/source: bin i16 + phi f64 + multiplicity i32)  host call %.1f ms  counts sum %d" % (
+    best, 14.0 * n / (best * 1e-3) / 1e9, wall * 1e3, bc.sum()))
