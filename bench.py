@@ -13,7 +13,7 @@ one NCCL all-reduce of W doubles per step.
 value  : terms/s, inputs resident in HBM (theta on the device), CUDA events on the launching stream, max over ranks.
 e2e    : same metric through the public host API (ShardedLikelihood.lnprob: pinned-host theta -> H2D -> kernels
          -> all-reduce -> D2H of W doubles -> sync), host wall clock, max over ranks.
-roofline: the loop is FP64-FMA-pipe bound (no tensor cores, HBM traffic ~0.02 B/term): achieved = terms/s/GPU x 28
+roofline: the loop is FP64-FMA-pipe bound (no tensor cores, HBM traffic ~0.02 B/term): achieved = terms/s/GPU x 23
          FP64-pipe instructions per term (counted in the SASS of k_main<false>) x 2 FLOP, against the register-only
          DFMA rate measured live on the same GPU (lf_fp64_peak) x 2 FLOP.  HBM figures are reported beside it.
 """
@@ -31,7 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FP64_INSTR_PER_TERM = 28          # DFMA/DADD/DMUL per (walker, source) term in k_main<false> (tools/sass_fp64_operands.py)
+FP64_INSTR_PER_TERM = 23          # DFMA/DADD/DMUL per (walker, source) term in k_main<false> (tools/sass_loop_mix.py)
+MUFU_PER_TERM = 4                 # rsqrt, lg2, ex2, rcp per term in the FP32 mode of the loop
 BYTES_PER_SOURCE = 16             # (log10 flux, flux) per source per sweep
 METRIC = "walker x source lnL terms/sec (batched lnprob, free-completeness single-z, FP64)"
 
@@ -45,6 +46,7 @@ def parse():
     ap.add_argument('--nsources', type=float, default=1.0e7, help='sources per GPU')
     ap.add_argument('--walkers', type=int, default=1024)
     ap.add_argument('--kind', default='free', choices=['free', 'fixed', 'z'])
+    ap.add_argument('--precision', default='f64', choices=['f64', 'f32'], help='arithmetic of the walker x source loop')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--prior-draws', action='store_true', help='walkers ~ U(prior) instead of a converged ensemble')
     return ap.parse_args()
@@ -67,7 +69,7 @@ def sample_inputs(inp, n_sample):
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    FIELDS = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
@@ -84,7 +86,9 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Stop sampling; keep the samples whose nvidia-smi timestamp falls inside [t_begin, t_end] (time.time())."""
+        import datetime
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.proc is None:
             return out
@@ -94,20 +98,29 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, pw, reasons = [], [], [], set()
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        rows = []
         for line in open(self.path):
             p = [x.strip() for x in line.split(',')]
-            if len(p) < 7:
+            if len(p) < 8:
                 continue
             try:
-                sm.append(float(p[0])); mx.append(float(p[1])); pw.append(float(p[2]))
+                ts = datetime.datetime.strptime(p[0], '%Y/%m/%d %H:%M:%S.%f').timestamp()
+                rows.append((ts, float(p[1]), float(p[2]), float(p[3]), p[4:8]))
             except ValueError:
                 continue
-            for nm, v in zip(names, p[3:7]):
+        os.unlink(self.path)
+        inside = [r for r in rows if t_begin is not None and t_begin - 0.05 <= r[0] <= t_end + 0.05]
+        window = "timed region"
+        if not inside:                          # region shorter than the sampling period: samples under the same load
+            inside, window = rows[-3:], "last samples before the end of the timed region"
+        sm, mx, pw, reasons = [], [], [], set()
+        for _, a, b, c, flags in inside:
+            sm.append(a); mx.append(b); pw.append(c)
+            for nm, v in zip(names, flags):
                 if v.lower().startswith('active'):
                     reasons.add(nm)
-        os.unlink(self.path)
+        out["window"] = window
         if sm:
             out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), power_w_max=float(max(pw)),
                        reasons=sorted(reasons), samples=len(sm))
@@ -180,9 +193,9 @@ def run_reference(args):
 
 
 def workload_name(args):
-    return ("lnprob throughput: %s-completeness model, %g sources per GPU x %d walkers, FP64 "
+    return ("lnprob throughput: %s-completeness model, %g sources per GPU x %d walkers, %s "
             "(BASELINE.json configs[1]; source-sharded over GPUs as configs[4])" %
-            (args.kind, args.nsources, args.walkers))
+            (args.kind, args.nsources, args.walkers, "FP64" if getattr(args, 'precision', 'f64') == 'f64' else "FP32 loop"))
 
 
 def main():
@@ -208,7 +221,7 @@ def main():
     n = int(args.nsources)
     W = args.walkers
     inp = build_inputs(n, args.kind, seed=1000 + rank)        # this rank's shard
-    like = ShardedLikelihood(inp, args.kind, device=local_rank)
+    like = ShardedLikelihood(inp, args.kind, device=local_rank, precision=args.precision)
     eng = like.engine
     mode = 'prior' if args.prior_draws else 'near'
     thetas = synth.draw_thetas(inp, args.kind, W, seed=7, mode=mode, scale=0.02)     # same on every rank
@@ -223,22 +236,24 @@ def main():
 
     # live FP64-pipe peak of this GPU (roofline denominator; not in MEASURED_PEAKS.json)
     peak_dfma, _ = eng.fp64_peak(100000)
+    peak_mufu, _ = eng.mufu_peak(100000)
 
     # ---- device-resident timing ------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)         # nvidia-smi takes ~0.1 s to start: launched before the warm-up
+    sampler.start()
     for _ in range(max(3, args.warmup)):
         like.lnprob_device(d_th, d_out)
     sync_all()
     launches0 = eng.last_call_info()['launches']
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    t_begin = time.time()
     ev0.record()
     for _ in range(args.steps):
         like.lnprob_device(d_th, d_out)
     ev1.record()
     sync_all()
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_begin, time.time())
     ms_dev = ev0.elapsed_time(ev1)
     info = eng.last_call_info()
     launches = info['launches'] - launches0
@@ -302,13 +317,36 @@ def main():
             hbm_src = 'MEASURED_PEAKS.json'
         except Exception:
             hbm_peak, hbm_src = 6650.0, 'fallback'
-        alg_bytes = n * BYTES_PER_SOURCE + W * like.ndim * 8 + W * 8
-        achieved_tf = per_gpu * FP64_INSTR_PER_TERM * 2 / 1e12
-        peak_tf = peak_dfma * 2 / 1e12
+        f32 = args.precision == 'f32'
+        bytes_per_source = 8 if f32 else BYTES_PER_SOURCE
+        alg_bytes = n * bytes_per_source + W * like.ndim * 8 + W * 8
+        if f32:
+            roof = {"bound": "mufu", "achieved": per_gpu * MUFU_PER_TERM / 1e12, "peak": peak_mufu / 1e12, "unit": "T MUFU instr/s",
+                    "note": "FP32 mode of k_main<false> is SFU bound: achieved = terms/s/GPU x %d MUFU instr/term (rsqrt, lg2, ex2, "
+                            "rcp); peak = ex2.approx.f32 rate measured live on this GPU (lf_mufu_peak)" % MUFU_PER_TERM}
+        else:
+            roof = {"bound": "fp64", "achieved": per_gpu * FP64_INSTR_PER_TERM * 2 / 1e12, "peak": peak_dfma * 2 / 1e12, "unit": "TFLOP/s",
+                    "note": "FP64-FMA-pipe bound kernel k_main<false> (no tensor cores; HBM traffic ~0.02 B/term): achieved = terms/s/GPU "
+                            "x %d FP64-pipe instr/term (counted in SASS, tools/sass_loop_mix.py) x 2 FLOP; peak = register-only DFMA "
+                            "rate measured live on this GPU (lf_fp64_peak: %.3e DFMA/s) x 2 FLOP" % (FP64_INSTR_PER_TERM, peak_dfma)}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        # DRAM bytes of one k_main launch from the committed ncu --set full capture of this workload (profiles/), if any
+        roof["traffic"] = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'k_main_traffic.json')))
+            key = "%s_%s_%d_%d" % (args.kind, args.precision, n, W)
+            if key in tr:
+                roof["traffic"] = tr[key]["dram_bytes_per_launch"]
+                roof["traffic_source"] = tr[key]["source"]
+        except Exception:
+            pass
+        roof["hbm"] = {"achieved": alg_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": alg_bytes / step_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                       "algorithmic_bytes_per_step": alg_bytes}
         line = {
-            "metric": METRIC, "value": value, "unit": "terms/s", "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if not f32 else METRIC.replace("FP64", "FP32 loop"), "value": value, "unit": "terms/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": workload_name(args), "kind": args.kind, "sources_per_gpu": n, "walkers": W,
                        "ndim": like.ndim, "nfields": eng.nfields, "size_ln": eng.size_ln,
                        "walker_draws": mode, "walker_classes_last_step": info,
@@ -324,14 +362,7 @@ def main():
                                            "lnprob calls per step through the public host API" % (W, args.nsources, world),
                                "steps_timed": n_samp_steps, "small": small},
             "clocks": clocks,
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": None,
-                         "note": "FP64-FMA-pipe bound kernel k_main<false>: achieved = terms/s/GPU x %d FP64-pipe "
-                                 "instr/term x 2 FLOP; peak = register-only DFMA rate measured live on this GPU "
-                                 "(lf_fp64_peak: %.3e DFMA/s) x 2 FLOP" % (FP64_INSTR_PER_TERM, peak_dfma),
-                         "hbm": {"achieved": alg_bytes / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": alg_bytes / step_s / 1e9 / hbm_peak, "peak_source": hbm_src,
-                                 "algorithmic_bytes_per_step": alg_bytes}},
+            "roofline": roof,
         }
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_serial(inp, args.kind, thetas)

@@ -111,9 +111,12 @@ struct KArgs {
     double* wp;
     double* colA;                      // Z: per (column, walker) ln-amplitude  [K? no: S][Wcap]
     double* colB;                      // Z: per (column, walker) 10^-L*(z_col)
-    int* cls_count;                    // [0..2] walkers per class, [3] / [4] work-item counters of k_main<fast/literal>
+    int* cls_count;                    // [0..2] walkers per class, [3] / [4] work-item counters of k_main<fast/literal>,
+                                       // [5] / [6] walkers per class in the quadrature lists
     int* list_fast;
     int* list_lit;
+    int* list_fastq;                   // walkers of each class whose quadrature THIS rank integrates (w % nshare == share)
+    int* list_litq;
     double* partial;                   // [rows][Wcap]
     int n_src_slabs, n_quad_slabs;
     int share, nshare;
@@ -307,6 +310,10 @@ __global__ void k_prologue(KArgs a) {
     if (a.force_literal) cls = CLS_LIT;
     int pos = atomicAdd(&a.cls_count[cls], 1);
     (cls == CLS_FAST ? a.list_fast : a.list_lit)[pos] = (int)w;
+    if (a.nshare <= 1 || (w % a.nshare) == a.share) {          // a function of w only: every rank agrees on who integrates w
+        int posq = atomicAdd(&a.cls_count[cls == CLS_FAST ? 5 : 6], 1);
+        (cls == CLS_FAST ? a.list_fastq : a.list_litq)[posq] = (int)w;
+    }
 }
 
 // Z model: per (column i, walker) constants of the quadrature integrand
@@ -343,7 +350,10 @@ __global__ void k_zcolumns(KArgs a) {
 #endif
 #define WARPS_PER_BLOCK LF_WARPS_PER_BLOCK
 #define BLOCK_THREADS (32 * WARPS_PER_BLOCK)
-static const size_t SMEM_TABLE_BYTES = sizeof(double2) * LOG_TAB_N * LOG_TAB_REP + sizeof(double) * EXP_TAB_N * EXP_TAB_REP;
+// per-warp staging buffer of the quadrature loop: QSTAGE points of 48 B, filled with coalesced loads
+#define QSTAGE 64
+static const size_t SMEM_STAGE_BYTES = (size_t)WARPS_PER_BLOCK * QSTAGE * 3 * sizeof(double2);
+static const size_t SMEM_TABLE_BYTES = sizeof(double2) * LOG_TAB_N * LOG_TAB_REP + sizeof(double) * EXP_TAB_N * EXP_TAB_REP + SMEM_STAGE_BYTES;
 
 __device__ __forceinline__ int field_of(const KArgs& a, long long i) {
     int k = 0;
@@ -356,12 +366,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
     extern __shared__ __align__(16) unsigned char smem_tables[];       // fast kernels only (SMEM_TABLE_BYTES)
     double2* s_log = reinterpret_cast<double2*>(smem_tables);
     double* s_exp = reinterpret_cast<double*>(s_log + LOG_TAB_N * LOG_TAB_REP);
+    double2* s_stage = reinterpret_cast<double2*>(s_exp + EXP_TAB_N * EXP_TAB_REP) + (threadIdx.x >> 5) * (QSTAGE * 3);
     const int cls = LITERAL ? CLS_LIT : CLS_FAST;
-    const int count = a.cls_count[cls];
-    const int n_wg = (count + 31) >> 5;
+    const int count_src = a.cls_count[cls], count_quad = a.cls_count[LITERAL ? 6 : 5];
+    const int n_wg = (count_src + 31) >> 5, n_wgq = (count_quad + 31) >> 5;
     if (n_wg == 0) return;
-    const int rows = a.n_src_slabs + a.n_quad_slabs;
-    const long long n_items = (long long)n_wg * rows;
+    const long long n_src_items = (long long)n_wg * a.n_src_slabs;
+    const long long n_items = n_src_items + (long long)n_wgq * a.n_quad_slabs;
     if (!LITERAL) {
         load_tables(a.tables, s_exp, s_log);
         __syncthreads();
@@ -372,15 +383,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
     const int lane = threadIdx.x & 31;
     const int rep16 = lane & (EXP_TAB_REP - 1), rep8 = lane & (LOG_TAB_REP - 1);   // table replica of this lane
     const long long WS = a.Wcap;
-    const int* list = LITERAL ? a.list_lit : a.list_fast;
     int* counter = a.cls_count + (LITERAL ? 4 : 3);
   for (;;) {
     long long item = 0;
     if (lane == 0) item = atomicAdd(counter, 1);
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item >= n_items) break;
-    const int wg = (int)(item % n_wg);
-    const int row = (int)(item / n_wg);
+    // source items first (all walkers of the class), then quadrature items (the walkers this rank integrates)
+    const bool is_src = item < n_src_items;
+    const long long it = is_src ? item : item - n_src_items;
+    const int groups = is_src ? n_wg : n_wgq;
+    const int wg = (int)(it % groups);
+    const int row = (int)(it / groups) + (is_src ? 0 : a.n_src_slabs);
+    const int count = is_src ? count_src : count_quad;
+    const int* list = is_src ? (LITERAL ? a.list_lit : a.list_fast) : (LITERAL ? a.list_litq : a.list_fastq);
     const int slot = wg * 32 + lane;
     const bool active = slot < count;
     const long long w = list[active ? slot : count - 1];       // inactive lanes shadow a valid walker
@@ -546,9 +562,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
         }
     } else {
         // ---------------- quadrature slab: contributes the integral (k_finish subtracts it) ----------------
-        if (a.nshare > 1 && (w % a.nshare) != a.share) {
-            // another rank integrates this walker
-        } else {
+        {
             const int qrow = row - a.n_src_slabs;
             long long q0 = (a.NQ * qrow) / a.n_quad_slabs, q1 = (a.NQ * (qrow + 1)) / a.n_quad_slabs;
             const long long SS = (long long)a.S * a.S;
@@ -562,10 +576,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                     if (!LITERAL) {
                         const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], c2 = wp[(P_FIELD0 + 4 * k + 1) * WS];
                         // one quadrature point: weight * exp(Schechter exponent + ln completeness)
-                        auto point = [&](const QuadPointFree* pt, double& acc) {
-                            double2 gf = __ldg(reinterpret_cast<const double2*>(pt));
-                            double2 xl = __ldg(reinterpret_cast<const double2*>(pt) + 1);
-                            double wt = __ldg(reinterpret_cast<const double2*>(pt) + 2).x;
+                        auto point = [&](const double2* pt, double& acc) {
+                            double2 gf = pt[0], xl = pt[1];
+                            double wt = pt[2].x;
                             double lg, rd;
                             if (a.modified) fleming_log_parts<true>(gf.x, gf.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg, rd);
                             else fleming_log_parts<false>(gf.x, gf.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg, rd);
@@ -574,12 +587,37 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                             arg = fma(lg, rd, arg);
                             acc = fma(wt, exp_full(arg, s_exp, rep16), acc);
                         };
-                        long long q = q0;
-                        for (; q + 1 < seg_end; q += 2) {        // two independent chains per thread
-                            point(&a.qpf[q], acc0);
-                            point(&a.qpf[q + 1], acc1);
+                        // the warp stages QSTAGE points at a time in shared memory with coalesced 16-byte loads (all of
+                        // them in flight at once), then every lane reads the points back as broadcasts
+                        for (long long q = q0; q < seg_end; q += QSTAGE) {
+                            const int cnt = (int)(seg_end - q < QSTAGE ? seg_end - q : QSTAGE);
+                            const double2* __restrict__ src = reinterpret_cast<const double2*>(a.qpf + q);
+                            __syncwarp();
+                            for (int t = lane; t < cnt * 3; t += 32) s_stage[t] = __ldg(src + t);
+                            __syncwarp();
+                            int j = 0;
+                            if (a.modified) {
+                                constexpr int NT = 4;
+                                for (; j + NT <= cnt; j += NT) {
+                                    double2 u[NT];
+                                    double arg[NT], wt[NT];
+#pragma unroll
+                                    for (int t = 0; t < NT; ++t) {
+                                        u[t] = s_stage[(j + t) * 3];
+                                        double2 xl = s_stage[(j + t) * 3 + 1];
+                                        wt[t] = s_stage[(j + t) * 3 + 2].x;
+                                        arg[t] = fma(-xl.y, tenmL, fma(c1, xl.x, c0));
+                                    }
+                                    fleming_terms<NT>(u, alpha, aF, c2, s_exp, s_log, rep16, rep8, arg);   // arg += ln completeness
+#pragma unroll
+                                    for (int t = 0; t < NT; t += 2) {
+                                        acc0 = fma(wt[t], exp_full(arg[t], s_exp, rep16), acc0);
+                                        acc1 = fma(wt[t + 1], exp_full(arg[t + 1], s_exp, rep16), acc1);
+                                    }
+                                }
+                            }
+                            for (; j < cnt; ++j) point(s_stage + j * 3, acc0);
                         }
-                        if (q < seg_end) point(&a.qpf[q], acc0);
                     } else {
                         const double F50 = wp[(P_FIELD0 + 4 * k + 2) * WS], ftau = wp[(P_FIELD0 + 4 * k + 3) * WS];
                         for (long long q = q0; q < seg_end; ++q) {                    // lumfuncmcmc.py:375-376
@@ -1043,7 +1081,7 @@ struct lf_ctx {
     // per-call scratch (grown on demand)
     long long Wcap = 0; int rows_cap = 0;
     double* d_wp = nullptr; double* d_colA = nullptr; double* d_colB = nullptr; double* d_partial = nullptr;
-    int* d_cls = nullptr; int* d_list_fast = nullptr; int* d_list_lit = nullptr;
+    int* d_cls = nullptr; int* d_list_fast = nullptr; int* d_list_lit = nullptr; int* d_list_fastq = nullptr; int* d_list_litq = nullptr;
     double* d_thetas = nullptr; double* d_out = nullptr;
     double* h_thetas = nullptr; double* h_out = nullptr;           // pinned staging
     long long launches = 0; double last_ms = 0.0;
@@ -1151,7 +1189,7 @@ extern "C" void lf_destroy(lf_ctx* c) {
     dfree(c->d_lum); dfree(c->d_flux); dfree(c->d_z); dfree(c->d_om); dfree(c->d_Lsrc); dfree(c->d_src2); dfree(c->d_src2f);
     dfree(c->d_qpf); dfree(c->d_qp); dfree(c->d_zarr); dfree(c->d_tables);
     dfree(c->d_wp); dfree(c->d_colA); dfree(c->d_colB); dfree(c->d_partial);
-    dfree(c->d_cls); dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_thetas); dfree(c->d_out);
+    dfree(c->d_cls); dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_list_fastq); dfree(c->d_list_litq); dfree(c->d_thetas); dfree(c->d_out);
     dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
     dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
     if (c->h_thetas) cudaFreeHost(c->h_thetas);
@@ -1381,7 +1419,7 @@ static int ensure_scratch(lf_ctx* c, long long W, int rows) {
         long long cap = std::max<long long>(64, W);
         cap = (cap + 31) / 32 * 32;
         dfree(c->d_wp); dfree(c->d_colA); dfree(c->d_colB); dfree(c->d_partial);
-        dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_thetas); dfree(c->d_out);
+        dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_list_fastq); dfree(c->d_list_litq); dfree(c->d_thetas); dfree(c->d_out);
         if (c->h_thetas) { cudaFreeHost(c->h_thetas); c->h_thetas = nullptr; }
         if (c->h_out) { cudaFreeHost(c->h_out); c->h_out = nullptr; }
         CK(cudaMalloc(&c->d_wp, sizeof(double) * P_NSLOTS * cap));
@@ -1391,6 +1429,8 @@ static int ensure_scratch(lf_ctx* c, long long W, int rows) {
         }
         CK(cudaMalloc(&c->d_list_fast, sizeof(int) * cap));
         CK(cudaMalloc(&c->d_list_lit, sizeof(int) * cap));
+        CK(cudaMalloc(&c->d_list_fastq, sizeof(int) * cap));
+        CK(cudaMalloc(&c->d_list_litq, sizeof(int) * cap));
         CK(cudaMalloc(&c->d_thetas, sizeof(double) * c->ndim * cap));
         CK(cudaMalloc(&c->d_out, sizeof(double) * cap));
         CK(cudaMallocHost(&c->h_thetas, sizeof(double) * c->ndim * cap));
@@ -1436,6 +1476,7 @@ static int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, doubl
     a.thetas = d_thetas; a.out = d_out; a.W = W; a.Wcap = c->Wcap;
     a.wp = c->d_wp; a.colA = c->d_colA; a.colB = c->d_colB;
     a.cls_count = c->d_cls; a.list_fast = c->d_list_fast; a.list_lit = c->d_list_lit;
+    a.list_fastq = c->d_list_fastq; a.list_litq = c->d_list_litq;
     a.partial = c->d_partial; a.n_src_slabs = n_src; a.n_quad_slabs = n_quad;
     CK(cudaMemsetAsync(c->d_cls, 0, 8 * sizeof(int), st));
     const int T = 128;
