@@ -131,6 +131,23 @@ int lf_fp64_peak(lf_ctx* ctx, int32_t iters, double* dfma_per_s, double* ms);
 /* Same for the MUFU (SFU) pipe: sustained ex2.approx.f32 thread-instructions / s (roofline of LF_PREC_F32). */
 int lf_mufu_peak(lf_ctx* ctx, int32_t iters, double* mufu_per_s, double* ms);
 
+/* Device-resident affine-invariant ensemble sampler: replaces emcee.EnsembleSampler(...).run_mcmc(pos, nsteps)
+ * (lumfuncmcmc.py:489-491, lumfuncmcmc_z.py:444-446) for a context on one GPU.  Goodman & Weare stretch move with
+ * scale `a` (emcee's default 2), fixed split of the ensemble into walkers [0, W/2) and [W/2, W) as in emcee 2.x,
+ * Philox4x32-10 counter RNG keyed by `seed` (counter = walker, step, half), proposals / log-posterior / accept all on
+ * the device, one CUDA graph per ensemble update replayed nsteps times.  W must be even.
+ *   pos0[W][ndim]            initial positions (host)
+ *   chain[nsteps][W][ndim]   positions after every update (host, may be NULL)
+ *   lnprob[nsteps][W]        log-posterior of those positions (host, may be NULL)
+ *   naccepted[W]             accepted proposals per walker (host, may be NULL)
+ *   step0                    index of the first update (continuing a run: pass the number of updates already done)
+ * Returns the final positions in pos_out[W][ndim] and lnprob_out[W] (host, may be NULL). */
+int lf_sampler_run(lf_ctx* ctx, const double* pos0, int64_t W, int64_t nsteps, uint64_t seed, double a, int64_t step0,
+                   double* chain, double* lnprob, int64_t* naccepted, double* pos_out, double* lnprob_out);
+
+/* Device time (ms) of the nsteps graph replays of the last lf_sampler_run call. */
+int lf_sampler_last_ms(lf_ctx* ctx, double* ms);
+
 /* Device time (ms, CUDA events on the engine's stream) of the kernels of the last lf_lnprob_batch call. */
 int lf_last_kernel_ms(lf_ctx* ctx, double* ms);
 

@@ -230,6 +230,24 @@ class LikelihoodEngine(_VeffOps):
                                                    C.c_void_p(d_out.data_ptr()), C.c_void_p(st.cuda_stream)), self.lib)
         return d_out
 
+    def sampler_run(self, pos0, nsteps, seed, a=2.0, step0=0, store_chain=True):
+        """Device-resident stretch-move run (see include/lf_engine.h, lf_sampler_run).  Returns a dict with
+        chain (nsteps, W, ndim), lnprob (nsteps, W), naccepted (W,), pos (W, ndim), lp (W,), device_ms."""
+        pos0 = np.ascontiguousarray(pos0, dtype=np.float64)
+        W, nd = pos0.shape
+        if nd != self.ndim:
+            raise ValueError("positions have %d parameters, this model takes %d" % (nd, self.ndim))
+        nsteps = int(nsteps)
+        chain = np.empty((nsteps, W, nd), dtype=np.float64) if store_chain else None
+        lnp = np.empty((nsteps, W), dtype=np.float64) if store_chain else None
+        nacc = np.zeros(W, dtype=np.int64)
+        pos, lp = np.empty((W, nd), dtype=np.float64), np.empty(W, dtype=np.float64)
+        _lib.check(self.lib.lf_sampler_run(self._ctx, _ptr(pos0), W, nsteps, C.c_uint64(int(seed) & (2 ** 64 - 1)), float(a),
+                                           int(step0), _ptr(chain), _ptr(lnp), _ptr(nacc), _ptr(pos), _ptr(lp)), self.lib)
+        ms = C.c_double()
+        _lib.check(self.lib.lf_sampler_last_ms(self._ctx, C.byref(ms)), self.lib)
+        return dict(chain=chain, lnprob=lnp, naccepted=nacc, pos=pos, lp=lp, device_ms=ms.value)
+
     def last_call_info(self):
         counts = (C.c_int64 * 3)()
         launches = C.c_int64()

@@ -6,6 +6,7 @@ outputs -- per-source luminosities, the D_L / dV/dz interpolants, the bicubic Om
 ARE the engine's inputs, and drop-in parity is defined on them.
 """
 import logging
+import os
 import time
 
 import numpy as np
@@ -168,15 +169,28 @@ class LFBase:
         self._engines = {}
 
     # ------------------------------------------------------------------ sampling
+    def _device_sampler_engine(self, func):
+        """Engine whose parameter rows ARE the sampled vector for ``func`` (None: host sampler only)."""
+        return None
+
     def _run_sampler(self, func):
         """emcee-style ensemble run handing the GPU a whole half-ensemble per call (reference lumfuncmcmc.py:479-513)."""
-        from .sampler import EnsembleSampler
+        from .sampler import DeviceEnsembleSampler, EnsembleSampler
         self.log.info('Fitting Schechter model to true luminosity function using emcee')
         pos = self.get_init_walker_values()
         ndim = pos.shape[1]
         start = time.time()
-        sampler = EnsembleSampler(self.nwalkers, ndim, func, vectorize=True)
-        sampler.run_mcmc(pos, self.nsteps, rstate0=np.random.get_state())
+        # sampler_backend = 'device' (attribute or LF_SAMPLER=device): the whole run stays on the GPU whenever the sampled
+        # parameter vector is the engine's own row layout; otherwise (and by default) the host sampler drives the engine
+        backend = getattr(self, 'sampler_backend', None) or os.environ.get('LF_SAMPLER', 'host')
+        eng = self._device_sampler_engine(func) if backend == 'device' else None
+        if eng is not None and eng.ndim == ndim:
+            sampler = DeviceEnsembleSampler(self.nwalkers, ndim, eng)
+            sampler.run_mcmc(pos, self.nsteps, rstate0=np.random.get_state())
+            self.set_parameters_from_list(sampler.chain[-1, -1, :])
+        else:
+            sampler = EnsembleSampler(self.nwalkers, ndim, func, vectorize=True)
+            sampler.run_mcmc(pos, self.nsteps, rstate0=np.random.get_state())
         elapsed = time.time() - start
         self.log.info("Total time taken: %0.2f s" % elapsed)
         self.log.info("Time taken per step per walker: %0.2f ms" % (elapsed / (self.nsteps) * 1000. / self.nwalkers))

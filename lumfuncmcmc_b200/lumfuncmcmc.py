@@ -201,6 +201,12 @@ class LumFuncMCMC(LFBase):
         self.nfreeparams = len(vals)
         return vals
 
+    def _device_sampler_engine(self, func):
+        # user rows equal engine rows only when every parameter of the free-completeness model is sampled
+        if not self.fix_comp and not self.fix_sch_al and func == self.lnprob:
+            return self._engine('free')
+        return None
+
     def fit_model(self):
         """Run the ensemble sampler on ``lnprob`` (or ``lnprob_fix_comp``) and keep the post-burn-in samples with
         their ln-probabilities in ``self.samples`` (reference lumfuncmcmc.py:479-513)."""

@@ -163,6 +163,9 @@ class LumFuncMCMCz(LFBase):
         self.nfreeparams = len(vals)
         return vals
 
+    def _device_sampler_engine(self, func):
+        return self._z_engine()
+
     def fit_model(self):
         self._run_sampler(self.lnprob)
 

@@ -107,6 +107,85 @@ class EnsembleSampler:
         return self.get_autocorr_time()
 
 
+class DeviceEnsembleSampler(EnsembleSampler):
+    """Same interface, but the whole run lives on the GPU (``LikelihoodEngine.sampler_run``): proposals from a
+    Philox4x32-10 counter stream, log-posterior from the engine, accept/reject and the chain all on the device, one
+    CUDA graph per ensemble update.  The split of the ensemble is the fixed first-half / second-half split of
+    emcee 2.x.  ``rstate0`` only seeds the counter stream (its first state word); chains are reproducible for a given
+    seed and equal, sample for sample, to :func:`philox_stretch_reference` driven by the same log-posterior."""
+
+    def __init__(self, nwalkers, ndim, engine, a=2.0, seed=None):
+        super().__init__(nwalkers, ndim, engine.lnprob, a=a, vectorize=True, randomize_split=False)
+        self.engine = engine
+        self.seed = seed
+        self.device_ms = 0.0
+
+    def run_mcmc(self, pos0, nsteps, rstate0=None, lnprob0=None, progress=False, seed=None):
+        if seed is None:
+            seed = self.seed
+        if seed is None:
+            if rstate0 is not None:
+                seed = int(np.asarray(rstate0[1], dtype=np.uint64)[0]) | (int(np.asarray(rstate0[1], dtype=np.uint64)[1]) << 32)
+            else:
+                seed = int(self._random.randint(0, 2 ** 31 - 1))
+        self.seed = seed
+        pos0 = np.array(pos0, dtype=np.float64, copy=True)
+        if pos0.shape != (self.nwalkers, self.ndim):
+            raise ValueError("initial positions must have shape (nwalkers, ndim)")
+        out = self.engine.sampler_run(pos0, nsteps, seed, a=self.a, step0=self.iterations)
+        self._chain = np.concatenate([self._chain, out['chain']])
+        self._lnprob = np.concatenate([self._lnprob, out['lnprob']])
+        self.naccepted += out['naccepted']
+        self.iterations += int(nsteps)
+        self.ncalls += 2 * int(nsteps) + 2
+        self.device_ms += out['device_ms']
+        return out['pos'], out['lp'], rstate0
+
+
+# ---- host replay of the device sampler's random stream (test infrastructure and documentation of the algorithm) ----
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Philox4x32-10 on uint32 NumPy arrays (Salmon et al. 2011); returns four uint32 arrays."""
+    M0, M1, W0, W1 = np.uint64(0xD2511F53), np.uint64(0xCD9E8D57), 0x9E3779B9, 0xBB67AE85
+    c0, c1, c2, c3 = (np.asarray(c, dtype=np.uint64) for c in (c0, c1, c2, c3))
+    k0, k1 = int(k0), int(k1)
+    mask = np.uint64(0xFFFFFFFF)
+    for _ in range(10):
+        p0, p1 = M0 * c0, M1 * c2
+        hi0, lo0, hi1, lo1 = p0 >> np.uint64(32), p0 & mask, p1 >> np.uint64(32), p1 & mask
+        c0, c1, c2, c3 = hi1 ^ c1 ^ np.uint64(k0), lo1, hi0 ^ c3 ^ np.uint64(k1), lo0
+        k0, k1 = (k0 + W0) & 0xFFFFFFFF, (k1 + W1) & 0xFFFFFFFF
+    return tuple(c.astype(np.uint32) for c in (c0, c1, c2, c3))
+
+
+def philox_stretch_reference(log_prob_fn, pos0, nsteps, seed, a=2.0, step0=0):
+    """The device sampler's algorithm, operation for operation, on the host: returns (chain, lnprob, naccepted)."""
+    pos = np.array(pos0, dtype=np.float64, copy=True)
+    W, ndim = pos.shape
+    half = W // 2
+    lp = np.asarray(log_prob_fn(pos), dtype=np.float64).copy()
+    chain, lnp, nacc = np.empty((nsteps, W, ndim)), np.empty((nsteps, W)), np.zeros(W, dtype=np.int64)
+    k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
+    for t in range(nsteps):
+        step = step0 + t
+        for h in (0, 1):
+            me = h * half + np.arange(half)
+            r = philox4x32_10(me, np.full(half, step & 0xFFFFFFFF), np.full(half, step >> 32), np.full(half, h), k0, k1)
+            u1 = (r[0].astype(np.float64) + 0.5) * 2.3283064365386963e-10
+            u3 = (r[2].astype(np.float64) + 0.5) * 2.3283064365386963e-10
+            tt = (a - 1.0) * u1 + 1.0
+            z = (tt * tt) / a
+            partner = (1 - h) * half + ((r[1].astype(np.uint64) * np.uint64(half)) >> np.uint64(32)).astype(np.int64)
+            prop = pos[partner] - (pos[partner] - pos[me]) * z[:, None]
+            new_lp = np.asarray(log_prob_fn(prop), dtype=np.float64)
+            with np.errstate(invalid='ignore'):
+                acc = np.log(u3) < (ndim - 1.0) * np.log(z) + new_lp - lp[me]
+            pos[me[acc]] = prop[acc]
+            lp[me[acc]] = new_lp[acc]
+            nacc[me[acc]] += 1
+        chain[t], lnp[t] = pos, lp
+    return chain, lnp, nacc
+
+
 def _autocorr_1d(x):
     n = 1 << int(np.ceil(np.log2(max(len(x), 2))))
     f = np.fft.fft(x - np.mean(x), n=2 * n)

@@ -155,3 +155,50 @@ def test_driver_end_to_end_writes_the_reference_outputs(tmp_path, monkeypatch, e
     assert np.array_equal(m2.samples, m.samples) and not hasattr(m2, 'chain')
     m.close()
     m2.close()
+
+
+@pytest.mark.parametrize('kind', ['free', 'z'])
+def test_device_sampler_chain_equals_host_replay(kind):
+    """The device-resident sampler (Philox stream, CUDA graph per update) produces, sample for sample, the chain of
+    its host restatement driven by the same engine's lnprob; stored ln-probabilities are the engine's values at the
+    stored positions and agree with the oracle to 1e-10."""
+    from lumfuncmcmc_b200 import synth
+    from lumfuncmcmc_b200.engine import LikelihoodEngine
+    from lumfuncmcmc_b200.sampler import DeviceEnsembleSampler, philox_stretch_reference
+    cat = synth.make_catalogue(3000, seed=31, nfields=3, evolve=(0.3, -0.2) if kind == 'z' else None)
+    inp = synth.direct_inputs(cat, nknots=512, size_ln=101 if kind == 'free' else 201, tabulated=(kind != 'free'))
+    eng = LikelihoodEngine(inp, kind, device=0)
+    W, nsteps, seed = 48, 25, 0x1234567890abcdef
+    p0 = np.concatenate([synth.draw_thetas(inp, kind, W - 6, seed=2, mode='near', scale=0.01),
+                         synth.draw_thetas(inp, kind, 6, seed=3, mode='prior')])         # a few walkers start at -inf
+    smp = DeviceEnsembleSampler(W, eng.ndim, eng, seed=seed)
+    pos, lp, _ = smp.run_mcmc(p0, nsteps)
+    chain, lnp, nacc = philox_stretch_reference(eng.lnprob, p0, nsteps, seed)
+    assert np.array_equal(smp.chain, np.swapaxes(chain, 0, 1))
+    assert np.array_equal(smp.lnprobability, lnp.T)
+    assert np.array_equal(smp.naccepted, nacc) and nacc.sum() > 0
+    assert np.array_equal(pos, chain[-1]) and np.array_equal(lp, lnp[-1])
+    # continuing the run continues the counter stream
+    pos2, lp2, _ = smp.run_mcmc(pos, 5)
+    chain2, lnp2, _ = philox_stretch_reference(eng.lnprob, chain[-1], 5, seed, step0=nsteps)
+    assert np.array_equal(pos2, chain2[-1]) and smp.chain.shape == (W, nsteps + 5, eng.ndim)
+    # the stored ln-probabilities are the oracle's values at the stored positions
+    ref = lf_oracle.lnprob_batch(inp, kind, chain[-1])
+    _check(lnp[-1], ref)
+    assert smp.device_ms > 0.0
+    eng.close()
+
+
+def test_fit_model_on_the_device_sampler():
+    m = _build('free', n=2000, nfields=5, seed=11)
+    m.nwalkers, m.nsteps = 40, 30
+    m.sampler_backend = 'device'
+    np.random.seed(4)
+    m.fit_model()
+    from lumfuncmcmc_b200.sampler import DeviceEnsembleSampler
+    assert isinstance(m.sampler, DeviceEnsembleSampler)
+    assert m.chain.shape == (40, 30, 9) and m.samples.shape[1] == 10
+    # every stored sample carries the engine's own lnprob of that position
+    last = m.chain[:, -1, :]
+    assert np.allclose(m.sampler.lnprobability[:, -1], m.lnprob(last), rtol=1e-12, atol=0, equal_nan=True)
+    m.close()

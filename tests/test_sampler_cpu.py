@@ -65,3 +65,30 @@ def test_integrated_time_of_ar1_process():
         x[t] = rho * x[t - 1] + rng.standard_normal((4, 1))
     tau = integrated_time(x)[0]
     assert abs(tau - (1 + rho) / (1 - rho)) < 4.0          # 19 for rho = 0.9
+
+
+def test_philox4x32_10_known_answers():
+    """Random123 known-answer vectors for Philox4x32-10 (the counter RNG of the device-resident sampler)."""
+    from lumfuncmcmc_b200.sampler import philox4x32_10
+    r = philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(x[0]) for x in r] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = 0xffffffff
+    r = philox4x32_10([f], [f], [f], [f], f, f)
+    assert [int(x[0]) for x in r] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    r = philox4x32_10([0x243f6a88], [0x85a308d3], [0x13198a2e], [0x03707344], 0xa4093822, 0x299f31d0)
+    assert [int(x[0]) for x in r] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_stretch_reference_samples_a_gaussian():
+    """The host restatement of the device sampler's algorithm is a valid sampler (fixed split, counter stream)."""
+    from lumfuncmcmc_b200.sampler import philox_stretch_reference
+    mu, sig = np.array([1.0, -2.0]), np.array([0.5, 2.0])
+    rs = np.random.RandomState(2)
+    chain, lnp, nacc = philox_stretch_reference(_gauss(mu, sig), mu + 0.1 * rs.randn(40, 2), 1500, seed=12345)
+    flat = chain[300:].reshape(-1, 2)
+    assert np.all(np.abs(flat.mean(axis=0) - mu) < 0.15 * sig)
+    assert np.all(np.abs(flat.std(axis=0) / sig - 1.0) < 0.1)
+    assert 0.3 < nacc.mean() / 1500 < 0.9
+    # continuing a run (step0) reproduces the one-shot chain
+    c1, l1, _ = philox_stretch_reference(_gauss(mu, sig), chain[9], 5, seed=12345, step0=10)
+    assert np.array_equal(c1, chain[10:15])
