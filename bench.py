@@ -296,8 +296,19 @@ def main():
         t0 = time.perf_counter()
         smp_s.run_mcmc(smp_s.chain[:, -1, :], 200)
         dt_s = time.perf_counter() - t0
-        small = {"workload": "BASELINE.json configs[0] size: 1e4 sources x 100 walkers, 1 GPU", "steps_per_s": 200 / dt_s,
-                 "lnprob_calls_per_s": 400 / dt_s, "acceptance": float(np.mean(smp_s.acceptance_fraction))}
+        # the same run with the device-resident sampler (proposals, lnprob, accept and chain on the GPU, one CUDA graph
+        # per ensemble update); wall clock includes the upload of the start positions and the download of the chain
+        from lumfuncmcmc_b200.sampler import DeviceEnsembleSampler
+        dev_s = DeviceEnsembleSampler(100, eng_s.ndim, eng_s, seed=17)
+        dev_s.run_mcmc(th_s, 50)
+        t0 = time.perf_counter()
+        dev_s.run_mcmc(dev_s.chain[:, -1, :], 2000)
+        dt_d = time.perf_counter() - t0
+        small = {"workload": "BASELINE.json configs[0] size: 1e4 sources x 100 walkers, 1 GPU",
+                 "steps_per_s": 2000 / dt_d, "sampler": "device-resident (lf_sampler_run), 2000 updates, wall clock incl. chain D2H",
+                 "device_ms_per_step": dev_s.device_ms / 2050, "acceptance": float(np.mean(dev_s.acceptance_fraction)),
+                 "host_sampler": {"steps_per_s": 200 / dt_s, "lnprob_calls_per_s": 400 / dt_s,
+                                  "acceptance": float(np.mean(smp_s.acceptance_fraction))}}
         eng_s.close()
 
     t = torch.tensor([ms_dev, t_e2e * 1e3, t_steps * 1e3], dtype=torch.float64, device='cuda')

@@ -187,16 +187,25 @@ __device__ __forceinline__ float fleming_log2_f32(float gs, float fs, float alph
 #define N_MIN_SAFE (-28.0)      /* fc >= 3.2e-4 > 2^-12, the lower end of the log table */
 #define X_MIN_SAFE (1.0e-4)
 
+// Thread (x, y) = (walker lane, field): the per-field work (a dozen libdevice pow/log/exp calls each) runs in parallel
+// and thread y == 0 combines the fields in index order, so the sums are the same as a sequential loop over fields.
+#define PRO_WALKERS 32
 __global__ void k_prologue(KArgs a) {
-    long long w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (w >= a.W) return;
-    const double* th = a.thetas + w * a.ndim;
-    double* wp = a.wp + w;
+    __shared__ double s_part[LF_MAX_FIELDS][PRO_WALKERS], s_lb[LF_MAX_FIELDS][PRO_WALKERS];
+    __shared__ int s_rok[LF_MAX_FIELDS][PRO_WALKERS];
+    const int wl = threadIdx.x, k = threadIdx.y;
+    const long long w = blockIdx.x * (long long)PRO_WALKERS + wl;
+    const bool live = w < a.W;
+    const double* th = a.thetas + (live ? w : 0) * a.ndim;
+    double* wp = a.wp + (live ? w : 0);
     const long long WS = a.Wcap;
     const double NINF = neg_inf();
-    int cls = CLS_FAST;
     bool ok = a.fixed_prior_ok != 0;
     const bool gate = a.prior_gate != 0;      // lnlike() (no prior) vs lnprob()
+    bool rejected = false;
+    double part = 0.0, lb = 1.0e300;          // this field's share of the sufficient-statistics sum, and of the lower bound
+    int rok = 1;
+    const FieldStats& s = a.fs[k];
 
     if (a.model == LF_MODEL_Z) {
         double L1 = th[0], L2 = th[1], L3 = th[2], p1 = th[3], p2 = th[4], p3 = th[5];
@@ -205,23 +214,21 @@ __global__ void k_prologue(KArgs a) {
         if (!a.fix_sch_al) ok = ok && in_box(sal, a.sch_al_lims);
         ok = ok && in_box_strict(L1, a.Lstar_lims) && in_box_strict(L2, a.Lstar_lims) && in_box_strict(L3, a.Lstar_lims);
         ok = ok && in_box_strict(p1, a.phistar_lims) && in_box_strict(p2, a.phistar_lims) && in_box_strict(p3, a.phistar_lims);
-        if (gate && !ok) { a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return; }
+        rejected = gate && !ok;
         double aL, bL, cL, aP, bP, cP;
         quad_coef(L1, L2, L3, a.z1, a.z2, a.z3, aL, bL, cL);
         quad_coef(p1, p2, p3, a.z1, a.z2, a.z3, aP, bP, cP);
         double c1 = (sal + 1.0) * LN10;
-        wp[P_AL * WS] = aL; wp[P_BL * WS] = bL; wp[P_CL * WS] = cL;
-        wp[P_AP * WS] = aP; wp[P_BP * WS] = bP; wp[P_CP * WS] = cP;
-        wp[P_C1 * WS] = c1; wp[P_SCHAL * WS] = sal;
-        // sufficient-statistics part of the source sum and a conservative lower bound of every term
-        double lnpart0 = 0.0, lb = 1.0e300;
-        for (int k = 0; k < a.K; ++k) {
-            const FieldStats& s = a.fs[k];
-            if (s.n == 0.0) continue;
+        if (k == 0 && live && !rejected) {
+            wp[P_AL * WS] = aL; wp[P_BL * WS] = bL; wp[P_CL * WS] = cL;
+            wp[P_AP * WS] = aP; wp[P_BP * WS] = bP; wp[P_CP * WS] = cP;
+            wp[P_C1 * WS] = c1; wp[P_SCHAL * WS] = sal;
+        }
+        if (s.n != 0.0) {
             // sum_i [ ln ln10 + ln10 phi*(z_i) + c1 (lum_i - L*(z_i)) + ln Om_i ]
             double sphi = aP * s.sum_z2 + bP * s.sum_z + cP * s.n;
             double sL = aL * s.sum_z2 + bL * s.sum_z + cL * s.n;
-            lnpart0 += s.n * LNLN10 + LN10 * sphi + c1 * (s.sum_lum - sL) + s.sum_lnom;
+            part = s.n * LNLN10 + LN10 * sphi + c1 * (s.sum_lum - sL) + s.sum_lnom;
             // ranges of the quadratics over [z_min, z_max]
             double Llo = fmin(fma(fma(aL, s.z_min, bL), s.z_min, cL), fma(fma(aL, s.z_max, bL), s.z_max, cL));
             double Lhi = fmax(fma(fma(aL, s.z_min, bL), s.z_min, cL), fma(fma(aL, s.z_max, bL), s.z_max, cL));
@@ -230,15 +237,10 @@ __global__ void k_prologue(KArgs a) {
             if (aP != 0.0) { double zv = -bP / (2.0 * aP); if (zv > s.z_min && zv < s.z_max) { double v = fma(fma(aP, zv, bP), zv, cP); Plo = fmin(Plo, v); } }
             double dlo = s.lum_min - Lhi, dhi = s.lum_max - Llo;
             double emax = pow(10.0, dhi);
-            double tlo = LNLN10 + LN10 * Plo + fmin(c1 * dlo, c1 * dhi) - emax + s.lnom_min;
-            lb = fmin(lb, tlo);
+            lb = LNLN10 + LN10 * Plo + fmin(c1 * dlo, c1 * dhi) - emax + s.lnom_min;
             if (!(emax < 690.0)) lb = -1.0e300;
             if (!(dlo > -40.0)) lb = -1.0e300;
         }
-        wp[P_LNPART0 * WS] = lnpart0;
-        if (!(lb > LB_SAFE)) cls = CLS_LIT;
-        // per-column constants for the quadrature: column i <-> zarr_i
-        // (filled by k_zcolumns after classification; needs c1, coefficients only)
     } else {
         const int K = a.K;
         double Lstar = th[0], phistar = th[1];
@@ -251,63 +253,69 @@ __global__ void k_prologue(KArgs a) {
         if (!a.fix_sch_al) ok = ok && in_box(sal, a.sch_al_lims);
         double alpha_c = 0.0;
         if (a.model == LF_MODEL_FREE) {
-            for (int k = 0; k < K; ++k) ok = ok && in_box(th[p + k], a.Flim_lims);
+            for (int kk = 0; kk < K; ++kk) ok = ok && in_box(th[p + kk], a.Flim_lims);
             alpha_c = th[p + K];
             ok = ok && in_box(alpha_c, a.alpha_lims);
         }
-        if (gate && !ok) { a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return; }
+        rejected = gate && !ok;
         // certain underflow: exp(-10^(lum_max - L*)) == 0 makes Phi == 0 for the brightest source
-        if (exp(-pow(10.0, a.lum_max_all - Lstar)) == 0.0 && a.N > 0) {
-            a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return;
-        }
+        if (!rejected && a.N > 0 && exp(-pow(10.0, a.lum_max_all - Lstar)) == 0.0) rejected = true;
         double tenmL = pow(10.0, -Lstar);
         double c1 = (sal + 1.0) * LN10;
         double c0 = LNLN10 + phistar * LN10 - Lstar * c1;
-        wp[P_TENML * WS] = tenmL; wp[P_C0 * WS] = c0; wp[P_C1 * WS] = c1;
-        wp[P_LSTAR * WS] = Lstar; wp[P_PHISTAR * WS] = phistar; wp[P_SCHAL * WS] = sal;
-        wp[P_ALPHA * WS] = alpha_c;
-        double lnpart0 = 0.0, lb = 1.0e300;
-        bool range_ok = true;
-        double b = 0.0;
-        if (a.model == LF_MODEL_FREE) {
-            b = -1.0 * sqrt(a.fcA2 * pow(alpha_c, -2.0));   // inverse_fleming, VmaxLumFunc.py:164-165
-            range_ok = alpha_c > 0.0;
+        if (k == 0 && live && !rejected) {
+            wp[P_TENML * WS] = tenmL; wp[P_C0 * WS] = c0; wp[P_C1 * WS] = c1;
+            wp[P_LSTAR * WS] = Lstar; wp[P_PHISTAR * WS] = phistar; wp[P_SCHAL * WS] = sal;
+            wp[P_ALPHA * WS] = alpha_c;
         }
-        for (int k = 0; k < K; ++k) {
-            const FieldStats& s = a.fs[k];
-            double tmin = 0.0, lnom = 0.0;
-            if (a.model == LF_MODEL_FREE) {
-                double F50 = 1.0e-17 * th[p + k];
-                double lgF = log10(F50);
-                double ftau = F50 * pow(10.0, b);
+        double tmin = 0.0, lnom = 0.0;
+        if (a.model == LF_MODEL_FREE) {
+            double b = -1.0 * sqrt(a.fcA2 * pow(alpha_c, -2.0));   // inverse_fleming, VmaxLumFunc.py:164-165
+            if (!(alpha_c > 0.0)) rok = 0;
+            double F50 = 1.0e-17 * th[p + k];
+            double lgF = log10(F50);
+            double ftau = F50 * pow(10.0, b);
+            if (live && !rejected) {
                 wp[(P_FIELD0 + 4 * k + 0) * WS] = -alpha_c * lgF;
                 wp[(P_FIELD0 + 4 * k + 1) * WS] = -LOG2E / ftau;
                 wp[(P_FIELD0 + 4 * k + 2) * WS] = F50;
                 wp[(P_FIELD0 + 4 * k + 3) * WS] = ftau;
-                // faintest flux the fast math will see in this field: sources and quadrature points
-                double gmin = fmin(s.n > 0.0 ? s.g_min : 1.0e300, s.grid_g_min);
-                double fmn = fmin(s.n > 0.0 ? s.f_min : 1.0e300, s.grid_f_min);
-                if (!(alpha_c * (gmin - lgF) > (a.precision == LF_PREC_F32 ? -12.0 : N_MIN_SAFE))) range_ok = false;
-                if (a.modified && !(fmn / ftau > X_MIN_SAFE)) range_ok = false;
-                if (a.modified && !(a.fcap / ftau < 5.0e6)) range_ok = false;      // exp range reduction stays in int32
-                if (s.n > 0.0) tmin = log(fleming_literal(s.f_min, F50, alpha_c, ftau, a.modified != 0));
-                lnom = s.ln_om0;
             }
-            if (s.n == 0.0) continue;
+            // faintest flux the fast math will see in this field: sources and quadrature points
+            double gmin = fmin(s.n > 0.0 ? s.g_min : 1.0e300, s.grid_g_min);
+            double fmn = fmin(s.n > 0.0 ? s.f_min : 1.0e300, s.grid_f_min);
+            if (!(alpha_c * (gmin - lgF) > (a.precision == LF_PREC_F32 ? -12.0 : N_MIN_SAFE))) rok = 0;
+            if (a.modified && !(fmn / ftau > X_MIN_SAFE)) rok = 0;
+            if (a.modified && !(a.fcap / ftau < 5.0e6)) rok = 0;      // exp range reduction stays in int32
+            if (s.n > 0.0) tmin = log(fleming_literal(s.f_min, F50, alpha_c, ftau, a.modified != 0));
+            lnom = s.ln_om0;
+        }
+        if (s.n != 0.0) {
             // Schechter exponent S(l) = c0 + c1 l - 10^(l - L*) is concave in l: minimum at an end of the range
             double s_lo = fmin(c0 + c1 * s.lum_min - pow(10.0, s.lum_min - Lstar),
                                c0 + c1 * s.lum_max - pow(10.0, s.lum_max - Lstar));
             if (a.model == LF_MODEL_FREE) {
-                lb = fmin(lb, s_lo + lnom + tmin);
-                lnpart0 += s.n * (c0 + lnom) + c1 * s.sum_lum - tenmL * s.sum_L;
+                lb = s_lo + lnom + tmin;
+                part = s.n * (c0 + lnom) + c1 * s.sum_lum - tenmL * s.sum_L;
             } else {
-                lb = fmin(lb, s_lo + s.lnom_min);
-                lnpart0 += s.n * c0 + c1 * s.sum_lum - tenmL * s.sum_L + s.sum_lnom;
+                lb = s_lo + s.lnom_min;
+                part = s.n * c0 + c1 * s.sum_lum - tenmL * s.sum_L + s.sum_lnom;
             }
         }
-        wp[P_LNPART0 * WS] = lnpart0;
-        if (!range_ok || !(lb > LB_SAFE)) cls = CLS_LIT;
     }
+    s_part[k][wl] = part; s_lb[k][wl] = lb; s_rok[k][wl] = rok;
+    __syncthreads();
+    if (k != 0 || !live) return;
+    if (rejected) { a.out[w] = NINF; atomicAdd(&a.cls_count[CLS_NONE], 1); return; }
+    double lnpart0 = 0.0, lbm = 1.0e300;
+    bool range_ok = true;
+    for (int kk = 0; kk < a.K; ++kk) {
+        if (a.fs[kk].n != 0.0) { lnpart0 += s_part[kk][wl]; lbm = fmin(lbm, s_lb[kk][wl]); }
+        range_ok = range_ok && s_rok[kk][wl] != 0;
+    }
+    wp[P_LNPART0 * WS] = lnpart0;
+    int cls = CLS_FAST;
+    if (!range_ok || !(lbm > LB_SAFE)) cls = CLS_LIT;
     if (a.force_literal) cls = CLS_LIT;
     int pos = atomicAdd(&a.cls_count[cls], 1);
     (cls == CLS_FAST ? a.list_fast : a.list_lit)[pos] = (int)w;
@@ -1480,8 +1488,7 @@ static int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, doubl
     a.list_fastq = c->d_list_fastq; a.list_litq = c->d_list_litq;
     a.partial = c->d_partial; a.n_src_slabs = n_src; a.n_quad_slabs = n_quad;
     CK(cudaMemsetAsync(c->d_cls, 0, 8 * sizeof(int), st));
-    const int T = 128;
-    k_prologue<<<(unsigned)((W + T - 1) / T), T, 0, st>>>(a);
+    k_prologue<<<(unsigned)((W + PRO_WALKERS - 1) / PRO_WALKERS), dim3(PRO_WALKERS, c->cfg.nfields), 0, st>>>(a);
     c->launches++;
     if (c->cfg.model == LF_MODEL_Z) {
         long long tot = (long long)c->cfg.size_ln * W;
