@@ -254,3 +254,39 @@ def test_fp32_mode_midsize_against_oracle(kind):
     rel = _assert_parity(got, lf_oracle.lnprob_batch(inp, kind, th), rtol=1e-5)
     print(kind, 'fp32 max rel', rel, eng.last_call_info())
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json full size (1e7 sources): oracle on a few walkers + size-independent properties on the ensemble
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_catalogue_properties_and_oracle_spot_check():
+    n = 10_000_000
+    cat = synth.make_catalogue(n, seed=77)
+    inp = synth.direct_inputs(cat, nknots=4096, size_ln=101)
+    th = np.concatenate([synth.draw_thetas(inp, 'free', 60, seed=5, mode='near', scale=0.02),
+                         synth.draw_thetas(inp, 'free', 4, seed=6, mode='prior')])
+    eng = _engine(inp, 'free')
+    whole = eng.lnprob(th)
+    assert eng.last_call_info()['fast'] >= 60
+    # (1) the reference algorithm on three walkers (3e7 terms of NumPy work)
+    ref = lf_oracle.lnprob_batch(inp, 'free', th[[0, 31, 59]])
+    _assert_parity(whole[[0, 31, 59]], ref)
+    eng.close()
+    # (2) additivity over three unequal source shards, each integrating a third of the walkers
+    parts = []
+    for r, (a, b) in enumerate([(0.0, 0.21), (0.21, 0.64), (0.64, 1.0)]):
+        e = _engine(_shard(inp, a, b), 'free', quadrature_share=(r, 3))
+        parts.append(e.lnprob(th))
+        e.close()
+    with np.errstate(invalid='ignore'):
+        total = parts[0] + parts[1] + parts[2]
+    _assert_parity(total, whole, rtol=1e-12)
+    # (3) permutation of the sources inside every field leaves the result unchanged (sums reorder: 1e-13)
+    rng = np.random.default_rng(9)
+    fi = inp['field_ind']
+    perm = np.concatenate([fi[k] + rng.permutation(fi[k + 1] - fi[k]) for k in range(len(fi) - 1)])
+    p = dict(inp)
+    p['lum'], p['z'] = inp['lum'][perm], inp['z'][perm]
+    e = _engine(p, 'free')
+    _assert_parity(e.lnprob(th), whole, rtol=1e-13)
+    e.close()
