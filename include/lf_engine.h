@@ -131,6 +131,27 @@ int lf_fp64_peak(lf_ctx* ctx, int32_t iters, double* dfma_per_s, double* ms);
 /* Same for the MUFU (SFU) pipe: sustained ex2.approx.f32 thread-instructions / s (roofline of LF_PREC_F32). */
 int lf_mufu_peak(lf_ctx* ctx, int32_t iters, double* mufu_per_s, double* ms);
 
+/* ---- set-up tables on the GPU (the step before the path; reference lumfuncmcmc.py:180-202, VmaxLumFunc.py:14-17) ----
+ * Context-free: they take a device ordinal and host buffers.
+ *
+ * FLRW distances of LambdaCDM(H0, Om0, Ode0, radiation Or0, curvature Ok0 = 1 - Om0 - Ode0 - Or0) for n redshifts:
+ * luminosity distance [Mpc] and differential comoving volume [Mpc^3 / sr]; either output may be NULL.  Same arithmetic
+ * as lumfuncmcmc_b200/cosmology.py (cumulative 8-point Gauss-Legendre panels of width `panel` + one 8-point closure per
+ * redshift), operation for operation, so the two agree to the last ulp of sin/sinh.  cum[ncum] is the host's
+ * cumulative panel integral of dz/E (cum[p] = int_0^{p*panel}). */
+typedef struct lf_cosmology {
+    double H0, Om0, Ode0, Or0, Ok0, panel;
+    double gl_x[8], gl_w[8];     /* Gauss-Legendre nodes / weights on [-1, 1], as numpy.polynomial.legendre.leggauss(8) */
+} lf_cosmology;
+int lf_cosmo_distances(int32_t device, const lf_cosmology* cosmo, const double* cum, int64_t ncum, int64_t n,
+                       const double* z, double* DL_Mpc, double* dVdz);
+
+/* y[i] = numpy.interp(x[i], xk, yk) for increasing knots xk[nk], BIT-IDENTICAL to NumPy's arithmetic
+ * (slope * (x - xk[j]) + yk[j] with the slope formed per call, exact-knot and last-knot special cases); this is what
+ * scipy.interpolate.interp1d(kind='linear') evaluates (lumfuncmcmc.py:196-197).  x outside [xk[0], xk[nk-1]] is an
+ * error (interp1d raises). */
+int lf_interp_linear(int32_t device, int64_t nk, const double* xk, const double* yk, int64_t n, const double* x, double* y);
+
 /* Device-resident affine-invariant ensemble sampler: replaces emcee.EnsembleSampler(...).run_mcmc(pos, nsteps)
  * (lumfuncmcmc.py:489-491, lumfuncmcmc_z.py:444-446) for a context on one GPU.  Goodman & Weare stretch move with
  * scale `a` (emcee's default 2), fixed split of the ensemble into walkers [0, W/2) and [W/2, W) as in emcee 2.x,
@@ -150,6 +171,9 @@ int lf_sampler_last_ms(lf_ctx* ctx, double* ms);
 
 /* Device time (ms, CUDA events on the engine's stream) of the kernels of the last lf_lnprob_batch call. */
 int lf_last_kernel_ms(lf_ctx* ctx, double* ms);
+
+/* Number of CUDA devices visible to the library (0 when there is none or the driver is missing). */
+int lf_device_count(void);
 
 const char* lf_last_error(void);
 const char* lf_version(void);

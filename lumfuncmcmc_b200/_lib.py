@@ -17,7 +17,13 @@ LIB_PATH = os.environ.get('LF_ENGINE_LIB', os.path.join(_HERE, 'csrc', 'liblfeng
 #: every symbol include/lf_engine.h declares (checked by tests/test_abi.py)
 EXPORTS = ['lf_ndim', 'lf_create', 'lf_destroy', 'lf_set_sources', 'lf_set_grid', 'lf_set_quadrature_share', 'lf_set_prior_gate',
            'lf_lnprob_batch', 'lf_lnprob_batch_device', 'lf_last_call_info', 'lf_veff_bin', 'lf_bin_weights', 'lf_boot_bin',
-           'lf_fp64_peak', 'lf_mufu_peak', 'lf_last_kernel_ms', 'lf_sampler_run', 'lf_sampler_last_ms', 'lf_last_error', 'lf_version']
+           'lf_fp64_peak', 'lf_mufu_peak', 'lf_last_kernel_ms', 'lf_sampler_run', 'lf_sampler_last_ms', 'lf_cosmo_distances', 'lf_interp_linear', 'lf_device_count', 'lf_last_error', 'lf_version']
+
+
+class LFCosmology(C.Structure):
+    """Mirror of ``lf_cosmology`` (include/lf_engine.h)."""
+    _fields_ = [(n, C.c_double) for n in ('H0', 'Om0', 'Ode0', 'Or0', 'Ok0', 'panel')] + \
+               [('gl_x', C.c_double * 8), ('gl_w', C.c_double * 8)]
 
 
 class LFConfig(C.Structure):
@@ -67,6 +73,8 @@ def load():
     lib.lf_last_kernel_ms.argtypes = [vp, dp]
     lib.lf_sampler_run.argtypes = [vp, vp, i64, i64, C.c_uint64, C.c_double, i64, vp, vp, vp, vp, vp]
     lib.lf_sampler_last_ms.argtypes = [vp, dp]
+    lib.lf_cosmo_distances.argtypes = [C.c_int32, vp, vp, i64, i64, vp, vp, vp]
+    lib.lf_interp_linear.argtypes = [C.c_int32, i64, vp, vp, i64, vp, vp]
     _lib = lib
     return lib
 

@@ -12,7 +12,6 @@ lumfuncmcmc.py:180-235) and then evaluates ``lnprob`` for a whole walker ensembl
 import ctypes as C
 
 import numpy as np
-from scipy.interpolate import interp1d
 
 from . import _lib
 
@@ -35,8 +34,10 @@ def source_flux(inp):
     zint, DLarr = np.asarray(inp['zint']), np.asarray(inp['DLarr'])
     if z.size and (z.min() < zint[0] or z.max() > zint[-1]):
         raise ValueError("source redshift outside the D_L interpolation table")
-    # the same SciPy linear interpolant object the reference builds (lumfuncmcmc.py:196), evaluated once
-    DL = interp1d(zint, DLarr)(z)
+    # the linear interpolant the reference builds (lumfuncmcmc.py:196: interp1d -> numpy.interp), evaluated once; for a
+    # large catalogue on the GPU, bit-identical (lf_interp_linear)
+    from .setup_gpu import LinearTable
+    DL = LinearTable(zint, DLarr)(z)
     L = 10 ** np.asarray(inp['lum'], dtype=np.float64)
     return L / (4.0 * np.pi * (3.086e24 * DL) ** 2)
 

@@ -11,10 +11,11 @@ import time
 
 import numpy as np
 from scipy.integrate import quad
-from scipy.interpolate import RectBivariateSpline, interp1d
+from scipy.interpolate import RectBivariateSpline
 
 from . import VmaxLumFunc as V
 from .cosmology import cosmo as _cosmo
+from .setup_gpu import GPU_MIN_POINTS, LinearTable, cosmo_distances, gpu_count
 
 MPC_CM = 3.086e24          # the reference's Mpc -> cm constant (lumfuncmcmc.py:70)
 
@@ -62,17 +63,24 @@ class LFBase:
         """D_L and dV/dz/dOmega linear interpolants on N knots over [0.95 zmin, 1.05 zmax], exact D_L per source,
         and the per-field minimum-luminosity curves (reference lumfuncmcmc.py:180-202)."""
         zint = np.linspace(0.95 * self.zmin, 1.05 * self.zmax, len(self.z))
-        self.DL = _cosmo.luminosity_distance(self.z)
-        DLarr = _cosmo.luminosity_distance(zint)
-        dVdzarr = _cosmo.differential_comoving_volume(zint)
-        self.DLf, self.dVdzf = interp1d(zint, DLarr), interp1d(zint, dVdzarr)
+        dev = getattr(self, 'device', 0)
+        if len(self.z) >= GPU_MIN_POINTS and gpu_count() > 0:
+            # the three O(N) cosmology passes on the GPU (same arithmetic as cosmology.py, SURVEY.md 8 f-2)
+            self.DL = cosmo_distances(_cosmo, self.z, device=dev, want_dv=False)[0]
+            DLarr, dVdzarr = cosmo_distances(_cosmo, zint, device=dev)
+        else:
+            self.DL = _cosmo.luminosity_distance(self.z)
+            DLarr = _cosmo.luminosity_distance(zint)
+            dVdzarr = _cosmo.differential_comoving_volume(zint)
+        # interp1d(kind='linear') evaluates numpy.interp; LinearTable does the same (on the GPU for per-source arrays)
+        self.DLf, self.dVdzf = LinearTable(zint, DLarr, dev), LinearTable(zint, dVdzarr, dev)
         self.minlumf = []
         for k in range(self.nfields):
             if self.min_comp_frac <= 0.001:
                 minlum = np.zeros_like(DLarr)
             else:
                 minlum = np.log10(4.0 * np.pi * (DLarr * MPC_CM) ** 2 * roots[k])
-            self.minlumf.append(interp1d(zint, minlum))
+            self.minlumf.append(LinearTable(zint, minlum, dev))
 
     def _fluxes_and_luminosities(self):
         """flux <-> log-luminosity with first-order error propagation (reference lumfuncmcmc.py:165-173, 251-270)."""

@@ -1,0 +1,37 @@
+"""Set-up (constructor + engine creation) wall clock at N sources, device path vs host path.   python tools/setup_time.py [N]"""
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from lumfuncmcmc_b200 import configLF, setup_gpu, synth        # noqa: E402
+import lumfuncmcmc_b200.lfbase as lfbase                       # noqa: E402
+from lumfuncmcmc_b200.lumfuncmcmc import LumFuncMCMC           # noqa: E402
+
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 10000000
+cat = synth.make_catalogue(n, seed=3, nfields=5)
+
+
+def build():
+    t0 = time.perf_counter()
+    m = LumFuncMCMC(cat['z'], flux=cat['flux'], flux_e=cat['flux_e'], Flim=list(cat['Flim']), alpha=cat['alpha'],
+                    Omega_0=list(cat['Omega_0']), Flim_lims=configLF.Flim_lims, alpha_lims=configLF.alpha_lims,
+                    sch_al=configLF.sch_al, Lstar=configLF.Lstar, phistar=configLF.phistar, fcmin=cat['fcmin'],
+                    min_comp_frac=0.0, field_names=cat['field_names'], field_ind=cat['field_ind'])
+    t1 = time.perf_counter()
+    th = np.array([42.5, -2.0, -1.49] + list(cat['Flim']) + [cat['alpha']])
+    v = m.lnprob(th)                                           # creates the engine (uploads, derived arrays, statistics)
+    t2 = time.perf_counter()
+    m.close()
+    return t1 - t0, t2 - t1, v
+
+
+c, e, v = build()
+print("N=%d  device set-up path: constructor %.2f s, engine creation + first lnprob %.2f s, lnprob %.6f" % (n, c, e, v))
+lfbase.gpu_count = lambda: 0
+setup_gpu.gpu_count = lambda: 0
+c, e, v2 = build()
+print("N=%d  host set-up path:   constructor %.2f s, engine creation + first lnprob %.2f s, lnprob %.6f  (rel diff %.1e)"
+      % (n, c, e, v2, abs(v - v2) / abs(v2)))
