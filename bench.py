@@ -47,6 +47,8 @@ def parse():
     ap.add_argument('--walkers', type=int, default=1024)
     ap.add_argument('--kind', default='free', choices=['free', 'fixed', 'z'])
     ap.add_argument('--precision', default='f64', choices=['f64', 'f32'], help='arithmetic of the walker x source loop')
+    ap.add_argument('--exchange', default='nccl', choices=['nccl', 'p2p'],
+                    help="multi-GPU sum of the per-walker partials: NCCL all-reduce or the engine's peer-memory kernel")
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--prior-draws', action='store_true', help='walkers ~ U(prior) instead of a converged ensemble')
     return ap.parse_args()
@@ -221,7 +223,8 @@ def main():
     n = int(args.nsources)
     W = args.walkers
     inp = build_inputs(n, args.kind, seed=1000 + rank)        # this rank's shard
-    like = ShardedLikelihood(inp, args.kind, device=local_rank, precision=args.precision)
+    like = ShardedLikelihood(inp, args.kind, device=local_rank, precision=args.precision, exchange=args.exchange,
+                             wcap=max(4096, W))
     eng = like.engine
     mode = 'prior' if args.prior_draws else 'near'
     thetas = synth.draw_thetas(inp, args.kind, W, seed=7, mode=mode, scale=0.02)     # same on every rank
@@ -363,7 +366,8 @@ def main():
                        "walker_draws": mode, "walker_classes_last_step": info,
                        "l2": "source arrays (%.0f MB per GPU) exceed the 126 MB L2; no flush needed" % (n * 16 / 1e6)
                        if n * 16 > 126e6 else "inputs fit in L2 (resident by design: re-swept by every walker group)",
-                       "parallelism": "sources sharded x%d, walkers replicated, NCCL all-reduce of %d B/step" % (world, W * 8)},
+                       "parallelism": "sources sharded x%d, walkers replicated, %s of %d B/step" % (
+                           world, "NCCL all-reduce" if like.exchange == "nccl" else "peer-memory all-reduce kernel (P2P stores over NVLink)", W * 8)},
             "e2e": {"value": e2e_value, "unit": "terms/s", "h2d_bytes_per_step": W * like.ndim * 8,
                     "d2h_bytes_per_step": W * 8, "ms_per_step": ms_e2e / args.steps,
                     "timing": "host wall clock around ShardedLikelihood.lnprob (pinned theta H2D, kernels, all-reduce, D2H, sync), max over ranks"},

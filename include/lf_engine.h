@@ -131,6 +131,21 @@ int lf_fp64_peak(lf_ctx* ctx, int32_t iters, double* dfma_per_s, double* ms);
 /* Same for the MUFU (SFU) pipe: sustained ex2.approx.f32 thread-instructions / s (roofline of LF_PREC_F32). */
 int lf_mufu_peak(lf_ctx* ctx, int32_t iters, double* mufu_per_s, double* ms);
 
+/* ---- multi-GPU exchange over peer memory (one process per GPU on one NVLink/NVSwitch node) ----
+ * The only exchange of the path is the sum over ranks of the W per-walker partial log-posteriors (lumfuncmcmc.py:370 is a
+ * plain sum over sources, so source shards add up).  Instead of an NCCL call it can run as one kernel of this library:
+ * every rank stores its vector into a slot of every peer's receive buffer (P2P stores), raises a flag, waits for the
+ * peers' flags and adds the slots in rank order -- the result is identical on all ranks and independent of timing, the
+ * kernel is capturable in a CUDA graph, and no host round trip or second library sits between k_finish and the sampler.
+ *   lf_peer_buffer_create   allocate this rank's receive buffer for vectors of up to wcap doubles; returns its CUDA IPC handle
+ *   lf_peer_buffer_connect  open the world handles (row r = rank r's handle, own row ignored)
+ *   lf_allreduce_device     in-place SUM over ranks of d_vec[W] on `stream` (asynchronous)
+ *   lf_peer_status          0, or non-zero if a wait for a peer timed out (~4 s) since the last call */
+int lf_peer_buffer_create(lf_ctx* ctx, int32_t rank, int32_t world, int64_t wcap, unsigned char handle_out[64]);
+int lf_peer_buffer_connect(lf_ctx* ctx, const unsigned char* handles);
+int lf_allreduce_device(lf_ctx* ctx, double* d_vec, int64_t W, void* stream);
+int lf_peer_status(lf_ctx* ctx, int32_t* timed_out);
+
 /* ---- set-up tables on the GPU (the step before the path; reference lumfuncmcmc.py:180-202, VmaxLumFunc.py:14-17) ----
  * Context-free: they take a device ordinal and host buffers.
  *

@@ -1,4 +1,4 @@
-"""Source-sharded likelihood across GPUs: one process per GPU, one all-reduce of W doubles per call.
+"""Source-sharded likelihood across GPUs: one process per GPU, one exchange of W doubles per call.
 
 ``lnprob`` is a plain sum over independent sources (reference lumfuncmcmc.py:370, :388; lumfuncmcmc_z.py:371),
 so rank r holds its own shard of sources, evaluates the shard's per-walker partial log-likelihood and the
@@ -6,6 +6,11 @@ quadrature term of the walkers ``w % world == r``, and a single ``all_reduce(SUM
 every rank the full log-posterior (-inf propagates through the sum).  The message is W*8 bytes (8 KiB at
 W = 1024): latency-bound on NVLink/NVSwitch, so NCCL's small-message path is the right tool and there is no
 bandwidth-bound exchange to fuse into the compute kernel.
+
+``exchange='p2p'`` replaces the NCCL call by the engine's own peer-memory kernel (``lf_allreduce_device``): every rank
+stores its W partials into a slot of every peer's buffer over NVLink, raises a flag, waits for the peers' flags and
+adds the slots in rank order -- identical bits on every rank, no second library between ``k_finish`` and the caller,
+capturable in a CUDA graph.  ``torch.distributed`` is then used only once, to hand round the CUDA IPC handles.
 
 With ``torch.distributed`` not initialised (or world size 1) this degrades to the single-GPU engine.
 The host-side logic (sharding, share assignment, reduction semantics) is exercised on CPU with the gloo
@@ -49,7 +54,7 @@ class ShardedLikelihood:
 
     ``inp`` is THIS rank's shard (already split, e.g. by :func:`shard_inputs`)."""
 
-    def __init__(self, inp, kind, device=None, group=None, precision='f64'):
+    def __init__(self, inp, kind, device=None, group=None, precision='f64', exchange='nccl', wcap=4096):
         import torch
         import torch.distributed as dist
         from .engine import LikelihoodEngine
@@ -62,6 +67,16 @@ class ShardedLikelihood:
                                        precision=precision)
         self.ndim = self.engine.ndim
         self._cap = 0
+        if exchange not in ('nccl', 'p2p'):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        self.exchange = exchange if self.world > 1 else 'nccl'
+        self.wcap = int(wcap)
+        if self.exchange == 'p2p':
+            handle = self.engine.peer_buffer_create(self.rank, self.world, self.wcap)
+            handles = [None] * self.world
+            dist.all_gather_object(handles, handle, group=group)
+            self.engine.peer_buffer_connect(handles)
+            dist.barrier(group=group)
 
     def _ensure(self, W):
         if W <= self._cap:
@@ -77,6 +92,10 @@ class ShardedLikelihood:
     def lnprob_device(self, d_thetas, d_out=None):
         """Device-resident call on torch's current stream: kernels + all-reduce, asynchronous."""
         d_out = self.engine.lnprob_device(d_thetas, d_out)
+        if self.exchange == 'p2p':
+            if d_out.shape[0] > self.wcap:
+                raise ValueError("more walkers (%d) than the peer buffers hold (wcap=%d)" % (d_out.shape[0], self.wcap))
+            return self.engine.allreduce_device(d_out)
         return reduce_partials(d_out, self.group)
 
     def lnprob(self, thetas):
@@ -90,7 +109,19 @@ class ShardedLikelihood:
             out = self.lnprob_device(self._d_th[:W], self._d_out[:W])
             self._h_out[:W].copy_(out, non_blocking=True)
             t.cuda.current_stream().synchronize()
+        if self.exchange == 'p2p' and self.engine.peer_timed_out():
+            raise RuntimeError("peer-memory all-reduce timed out waiting for another rank")
         return self._h_out[:W].numpy().copy()
+
+    def sampler_run(self, pos0, nsteps, seed, a=2.0, step0=0):
+        """Device-resident ensemble run over all ranks (every rank gets the same chain).  Needs ``exchange='p2p'`` when
+        there is more than one rank: the sum over ranks runs inside the captured CUDA graph of each update."""
+        if self.world > 1 and self.exchange != 'p2p':
+            raise RuntimeError("the device-resident sampler over several GPUs needs exchange='p2p'")
+        out = self.engine.sampler_run(pos0, nsteps, seed, a=a, step0=step0)
+        if self.exchange == 'p2p' and self.engine.peer_timed_out():
+            raise RuntimeError("peer-memory all-reduce timed out waiting for another rank")
+        return out
 
     def close(self):
         self.engine.close()

@@ -249,6 +249,32 @@ class LikelihoodEngine(_VeffOps):
         _lib.check(self.lib.lf_sampler_last_ms(self._ctx, C.byref(ms)), self.lib)
         return dict(chain=chain, lnprob=lnp, naccepted=nacc, pos=pos, lp=lp, device_ms=ms.value)
 
+    # ---- peer-memory exchange (multi-GPU without NCCL on the data path) ----
+    def peer_buffer_create(self, rank, world, wcap):
+        """Allocate this rank's receive buffer; returns its 64-byte CUDA IPC handle (bytes)."""
+        h = (C.c_ubyte * 64)()
+        _lib.check(self.lib.lf_peer_buffer_create(self._ctx, int(rank), int(world), int(wcap), h), self.lib)
+        return bytes(h)
+
+    def peer_buffer_connect(self, handles):
+        """``handles``: list of the world ranks' IPC handles, in rank order."""
+        blob = b''.join(handles)
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        _lib.check(self.lib.lf_peer_buffer_connect(self._ctx, buf), self.lib)
+
+    def allreduce_device(self, d_vec, stream=None):
+        """In-place SUM over ranks of a CUDA float64 vector, one kernel over peer memory (asynchronous)."""
+        import torch
+        st = torch.cuda.current_stream(d_vec.device) if stream is None else stream
+        _lib.check(self.lib.lf_allreduce_device(self._ctx, C.c_void_p(d_vec.data_ptr()), d_vec.shape[0],
+                                                C.c_void_p(st.cuda_stream)), self.lib)
+        return d_vec
+
+    def peer_timed_out(self):
+        v = C.c_int32()
+        _lib.check(self.lib.lf_peer_status(self._ctx, C.byref(v)), self.lib)
+        return bool(v.value)
+
     def last_call_info(self):
         counts = (C.c_int64 * 3)()
         launches = C.c_int64()

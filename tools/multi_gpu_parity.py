@@ -24,6 +24,30 @@ for kind in ('free', 'fixed', 'z'):
     th = np.concatenate([synth.draw_thetas(inp, kind, 96, seed=5), synth.draw_thetas(inp, kind, 32, seed=6, mode='prior')])
     like = ShardedLikelihood(shard_inputs(inp, rank, world), kind, device=local)
     got = like.lnprob(th)
+    # the same exchange as one kernel over peer memory instead of NCCL: identical on every rank, equal to the NCCL sum
+    p2p = ShardedLikelihood(shard_inputs(inp, rank, world), kind, device=local, exchange='p2p', wcap=256)
+    for _ in range(3):                                     # repeated calls exercise both parities of the buffers
+        got_p = p2p.lnprob(th)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, got_p.tobytes())
+    same_everywhere = all(g == gathered[0] for g in gathered)
+    with np.errstate(invalid='ignore'):
+        fin_p = np.isfinite(got)
+        rel_p = np.max(np.abs(got_p[fin_p] - got[fin_p]) / np.abs(got[fin_p])) if fin_p.any() else 0.0
+    p2p_ok = same_everywhere and np.array_equal(np.isneginf(got_p), np.isneginf(got)) and rel_p < 1e-13
+    # device-resident sampler across the ranks (CUDA graph per update, peer-memory exchange inside the graph): every
+    # rank ends with the same chain, equal to the host replay of the Philox stream driven by the sharded lnprob
+    chain_ok = True
+    if kind != 'fixed':
+        from lumfuncmcmc_b200.sampler import philox_stretch_reference
+        p0 = synth.draw_thetas(inp, kind, 64, seed=8, mode='near', scale=0.01)
+        run = p2p.engine.sampler_run(p0, 12, seed=99)
+        ref_chain, ref_lnp, _ = philox_stretch_reference(p2p.lnprob, p0, 12, 99)
+        g2 = [None] * world
+        dist.all_gather_object(g2, run['chain'].tobytes())
+        chain_ok = all(g == g2[0] for g in g2) and np.array_equal(run['chain'], ref_chain) and np.array_equal(run['lnprob'], ref_lnp)
+    p2p_ok = p2p_ok and chain_ok
+    p2p.close()
     if rank == 0:
         from oracle import lf_oracle
         single = LikelihoodEngine(inp, kind, device=local)
@@ -34,8 +58,10 @@ for kind in ('free', 'fixed', 'z'):
         ref = lf_oracle.lnprob_batch(inp, kind, th[:12])
         f2 = np.isfinite(ref)
         rel_o = np.max(np.abs(got[:12][f2] - ref[f2]) / np.abs(ref[f2]))
-        print("%s: world=%d  -inf sets equal=%s  max rel vs single GPU %.2e  vs oracle %.2e" % (kind, world, same_inf, rel, rel_o))
-        ok = ok and same_inf and rel < 1e-12 and rel_o < 1e-10
+        print("%s: world=%d  -inf sets equal=%s  max rel vs single GPU %.2e  vs oracle %.2e   peer-memory exchange: identical on "
+              "all ranks=%s, max rel vs NCCL %.2e, multi-GPU device sampler chain == host replay on all ranks: %s"
+              % (kind, world, same_inf, rel, rel_o, same_everywhere, rel_p, chain_ok))
+        ok = ok and same_inf and rel < 1e-12 and rel_o < 1e-10 and p2p_ok
         single.close()
     like.close()
     dist.barrier()
