@@ -365,8 +365,16 @@ __global__ void k_zcolumns(KArgs a) {
 #define BLOCK_THREADS (32 * WARPS_PER_BLOCK)
 // per-warp staging buffer of the quadrature loop: QSTAGE points of 48 B, filled with coalesced loads
 #define QSTAGE 64
-static const size_t SMEM_STAGE_BYTES = (size_t)WARPS_PER_BLOCK * QSTAGE * 3 * sizeof(double2);
-static const size_t SMEM_TABLE_BYTES = sizeof(double2) * LOG_TAB_N * LOG_TAB_REP + sizeof(double) * EXP_TAB_N * EXP_TAB_REP + SMEM_STAGE_BYTES;
+// Per-model launch shape of the fast kernels.  FREE: 12 warps (up to 168 registers), shared memory = log table + exp table +
+// staging.  Z / FIXED: lighter loops (<= 128 registers) -> 16 warps; no log table, the small replicated exp table + staging.
+__host__ __device__ constexpr int main_warps(int model) { return model == LF_MODEL_FREE ? WARPS_PER_BLOCK : 16; }
+__host__ __device__ constexpr size_t main_table_bytes(int model) {
+    return model == LF_MODEL_FREE ? sizeof(double2) * LOG_TAB_N * LOG_TAB_REP + sizeof(double) * EXP_SMEM_DOUBLES
+                                  : sizeof(double) * EXP_TAB_N * EXP_TAB_REP;
+}
+__host__ __device__ constexpr size_t main_smem_bytes(int model) {
+    return main_table_bytes(model) + (size_t)main_warps(model) * QSTAGE * 3 * sizeof(double2);
+}
 
 __device__ __forceinline__ int field_of(const KArgs& a, long long i) {
     int k = 0;
@@ -374,12 +382,13 @@ __device__ __forceinline__ int field_of(const KArgs& a, long long i) {
     return k;
 }
 
-template <bool LITERAL>
-__global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_tables[];       // fast kernels only (SMEM_TABLE_BYTES)
-    double2* s_log = reinterpret_cast<double2*>(smem_tables);
-    double* s_exp = reinterpret_cast<double*>(s_log + LOG_TAB_N * LOG_TAB_REP);
-    double2* s_stage = reinterpret_cast<double2*>(s_exp + EXP_TAB_N * EXP_TAB_REP) + (threadIdx.x >> 5) * (QSTAGE * 3);
+// One instantiation per (class, model): each model's loop gets its own register allocation and instruction schedule.
+template <bool LITERAL, int MODEL>
+__global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_tables[];       // fast kernels only (main_smem_bytes(MODEL))
+    double2* s_log = reinterpret_cast<double2*>(smem_tables);          // FREE: log table; Z / FIXED: the replicated exp table
+    double* s_exp = reinterpret_cast<double*>(s_log + LOG_TAB_N * LOG_TAB_REP);     // FREE only
+    double2* s_stage = reinterpret_cast<double2*>(smem_tables + main_table_bytes(MODEL)) + (threadIdx.x >> 5) * (QSTAGE * 3);
     const int cls = LITERAL ? CLS_LIT : CLS_FAST;
     const int count_src = a.cls_count[cls], count_quad = a.cls_count[LITERAL ? 6 : 5];
     const int n_wg = (count_src + 31) >> 5, n_wgq = (count_quad + 31) >> 5;
@@ -387,7 +396,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
     const long long n_src_items = (long long)n_wg * a.n_src_slabs;
     const long long n_items = n_src_items + (long long)n_wgq * a.n_quad_slabs;
     if (!LITERAL) {
-        load_tables(a.tables, s_exp, s_log);
+        // FREE: log table + (big) exp table; Z / FIXED: no log table, the small replicated exp table takes its place
+        if (MODEL == LF_MODEL_FREE) load_tables(a.tables, s_exp, s_log);
+        else load_exp_replicated(a.tables, reinterpret_cast<double*>(s_log));
         __syncthreads();
     }
     // persistent warps: every warp pulls (walker group, slab) items from a global counter until none are left.
@@ -395,6 +406,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
     // item owns its own partial[] row, so the result does not depend on which warp ran it.
     const int lane = threadIdx.x & 31;
     const int rep16 = lane & (EXP_TAB_REP - 1), rep8 = lane & (LOG_TAB_REP - 1);   // table replica of this lane
+    const double* s_exp_rep = reinterpret_cast<const double*>(s_log);               // Z / FIXED models only
     const long long WS = a.Wcap;
     int* counter = a.cls_count + (LITERAL ? 4 : 3);
   for (;;) {
@@ -419,7 +431,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
     if (row < a.n_src_slabs) {
         // ---------------- source slab ----------------
         long long i0 = (a.N * row) / a.n_src_slabs, i1 = (a.N * (row + 1)) / a.n_src_slabs;
-        if (a.model == LF_MODEL_FREE) {
+        if (MODEL == LF_MODEL_FREE) {
             const double alpha = wp[P_ALPHA * WS];
             int k = field_of(a, i0);
             while (i0 < i1) {
@@ -515,7 +527,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                 i0 = seg_end;
                 ++k;
             }
-        } else if (a.model == LF_MODEL_FIXED) {
+        } else if (MODEL == LF_MODEL_FIXED) {
             // fast class: the whole source sum is in P_LNPART0 (sufficient statistics); literal class sums terms
             if (LITERAL) {
                 const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
@@ -551,19 +563,30 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                 // Base 2 throughout: 2^(log2(10) lum_i - P2(z_i)), 11 FP64 instructions per term
                 const double L2T = 3.32192809488736234787;                              // log2(10)
                 const double a2 = aL * L2T, b2 = bL * L2T, c2 = cL * L2T;
-                long long i = i0;
-                for (; i + 1 < i1; i += 2) {
-                    double2 s0 = __ldg(&a.src2[i]), s1 = __ldg(&a.src2[i + 1]);
-                    double d0 = fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2));
-                    double d1 = fma(L2T, s1.x, -fma(fma(a2, s1.y, b2), s1.y, c2));
-                    acc0 -= exp2_full(d0, s_exp, rep16);
-                    acc1 -= exp2_full(d1, s_exp, rep16);
+                // four sources in lock-step (four independent FP64 chains per thread), the next four prefetched
+                const double2* __restrict__ ps = a.src2 + i0;
+                const int cnt = (int)(i1 - i0);
+                double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+                double2 A0, A1, A2, A3;
+                int j = 0;
+                if (cnt >= 4) { A0 = __ldg(ps); A1 = __ldg(ps + 1); A2 = __ldg(ps + 2); A3 = __ldg(ps + 3); }
+                for (; j + 4 <= cnt; j += 4) {
+                    const double2 s0 = A0, s1 = A1, s2 = A2, s3 = A3;
+                    if (j + 8 <= cnt) { A0 = __ldg(ps + j + 4); A1 = __ldg(ps + j + 5); A2 = __ldg(ps + j + 6); A3 = __ldg(ps + j + 7); }
+                    const double d0 = fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2));
+                    const double d1 = fma(L2T, s1.x, -fma(fma(a2, s1.y, b2), s1.y, c2));
+                    const double d2 = fma(L2T, s2.x, -fma(fma(a2, s2.y, b2), s2.y, c2));
+                    const double d3 = fma(L2T, s3.x, -fma(fma(a2, s3.y, b2), s3.y, c2));
+                    e0 += exp2_full<false>(d0, s_exp_rep, rep16);
+                    e1 += exp2_full<false>(d1, s_exp_rep, rep16);
+                    e2 += exp2_full<false>(d2, s_exp_rep, rep16);
+                    e3 += exp2_full<false>(d3, s_exp_rep, rep16);
                 }
-                if (i < i1) {
-                    double2 s0 = __ldg(&a.src2[i]);
-                    double d0 = fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2));
-                    acc0 -= exp2_full(d0, s_exp, rep16);
+                for (; j < cnt; ++j) {
+                    const double2 s0 = __ldg(ps + j);
+                    e0 += exp2_full<false>(fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2)), s_exp_rep, rep16);
                 }
+                acc0 -= (e0 + e1) + (e2 + e3);
             } else {
                 const double aP = wp[P_AP * WS], bP = wp[P_BP * WS], cP = wp[P_CP * WS], sal = wp[P_SCHAL * WS];
                 for (long long i = i0; i < i1; ++i) {                                 // lumfuncmcmc_z.py:371
@@ -579,7 +602,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
             const int qrow = row - a.n_src_slabs;
             long long q0 = (a.NQ * qrow) / a.n_quad_slabs, q1 = (a.NQ * (qrow + 1)) / a.n_quad_slabs;
             const long long SS = (long long)a.S * a.S;
-            if (a.model == LF_MODEL_FREE) {
+            if (MODEL == LF_MODEL_FREE) {
                 const double alpha = wp[P_ALPHA * WS];
                 const double c0 = wp[P_C0 * WS], c1 = wp[P_C1 * WS], tenmL = wp[P_TENML * WS];
                 const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
@@ -598,7 +621,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                             double arg = fma(c1, xl.x, c0);
                             arg = fma(-xl.y, tenmL, arg);
                             arg = fma(lg, rd, arg);
-                            acc = fma(wt, exp_full(arg, s_exp, rep16), acc);
+                            acc = fma(wt, exp_full<EXP_BIG>(arg, s_exp, rep16), acc);
                         };
                         // the warp stages QSTAGE points at a time in shared memory with coalesced 16-byte loads (all of
                         // them in flight at once), then every lane reads the points back as broadcasts
@@ -624,8 +647,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                                     fleming_terms<NT>(u, alpha, aF, c2, s_exp, s_log, rep16, rep8, arg);   // arg += ln completeness
 #pragma unroll
                                     for (int t = 0; t < NT; t += 2) {
-                                        acc0 = fma(wt[t], exp_full(arg[t], s_exp, rep16), acc0);
-                                        acc1 = fma(wt[t + 1], exp_full(arg[t + 1], s_exp, rep16), acc1);
+                                        acc0 = fma(wt[t], exp_full<EXP_BIG>(arg[t], s_exp, rep16), acc0);
+                                        acc1 = fma(wt[t + 1], exp_full<EXP_BIG>(arg[t + 1], s_exp, rep16), acc1);
                                     }
                                 }
                             }
@@ -642,49 +665,69 @@ __global__ void __launch_bounds__(BLOCK_THREADS, LF_MIN_BLOCKS) k_main(KArgs a) 
                     }
                     q0 = seg_end;
                 }
-            } else if (a.model == LF_MODEL_FIXED) {
-                const double c0 = wp[P_C0 * WS], c1 = wp[P_C1 * WS], tenmL = wp[P_TENML * WS];
-                const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
-                for (long long q = q0; q < q1; ++q) {
-                    const QuadPoint* pt = &a.qp[q];
-                    if (!LITERAL) {
-                        double2 xl = __ldg(reinterpret_cast<const double2*>(pt));
-                        double wt = __ldg(reinterpret_cast<const double2*>(pt) + 1).x;
-                        double arg = fma(c1, xl.x, c0);
-                        arg = fma(-xl.y, tenmL, arg);
-                        acc0 = fma(wt, exp_full(arg, s_exp, rep16), acc0);
-                    } else {                                                          // lumfuncmcmc.py:391
-                        acc0 = fma(__ldg(&pt->wt), schechter_literal(__ldg(&pt->x), sal, Lstar, phistar), acc0);
-                    }
-                }
             } else {
-                // Z: points are stored column-major: q = (k*S + i)*S + j  (column i <-> zarr_i)
-                const double c1 = wp[P_C1 * WS], sal = wp[P_SCHAL * WS];
-                const double aL = wp[P_AL * WS], bL = wp[P_BL * WS], cL = wp[P_CL * WS];
-                const double aP = wp[P_AP * WS], bP = wp[P_BP * WS], cP = wp[P_CP * WS];
-                while (q0 < q1) {
-                    long long col = q0 / a.S;                    // global column index k*S + i
-                    int i = (int)(col % a.S);
-                    long long seg_end = (col + 1) * a.S < q1 ? (col + 1) * a.S : q1;
-                    if (!LITERAL) {
-                        const double cA = a.colA[(long long)i * WS + w], cB = a.colB[(long long)i * WS + w];
-                        for (long long q = q0; q < seg_end; ++q) {
-                            const QuadPoint* pt = &a.qp[q];
-                            double2 xl = __ldg(reinterpret_cast<const double2*>(pt));
-                            double wt = __ldg(reinterpret_cast<const double2*>(pt) + 1).x;
-                            double arg = fma(c1, xl.x, cA);
-                            arg = fma(-xl.y, cB, arg);
-                            acc0 = fma(wt, exp_full(arg, s_exp, rep16), acc0);
+                // FIXED / Z fast path: sum_q wt_q exp(c1 x_q - Lx_q cB + cA) over [qa, qb); the warp stages QSTAGE points
+                // (32 B each) in shared memory with coalesced loads and evaluates them four at a time
+                const double c1 = wp[P_C1 * WS];
+                auto quad_segment = [&](long long qa, long long qb, double cA, double cB) {
+                    for (long long q = qa; q < qb; q += QSTAGE) {
+                        const int cnt = (int)(qb - q < QSTAGE ? qb - q : QSTAGE);
+                        const double2* __restrict__ src = reinterpret_cast<const double2*>(a.qp + q);
+                        __syncwarp();
+                        for (int t = lane; t < cnt * 2; t += 32) s_stage[t] = __ldg(src + t);
+                        __syncwarp();
+                        int j = 0;
+                        for (; j + 4 <= cnt; j += 4) {
+                            double arg[4], wt[4];
+#pragma unroll
+                            for (int t = 0; t < 4; ++t) {
+                                const double2 xl = s_stage[(j + t) * 2];
+                                wt[t] = s_stage[(j + t) * 2 + 1].x;
+                                arg[t] = fma(-xl.y, cB, fma(c1, xl.x, cA));
+                            }
+#pragma unroll
+                            for (int t = 0; t < 4; t += 2) {
+                                acc0 = fma(wt[t], exp_full<false>(arg[t], s_exp_rep, rep16), acc0);
+                                acc1 = fma(wt[t + 1], exp_full<false>(arg[t + 1], s_exp_rep, rep16), acc1);
+                            }
                         }
-                    } else {
-                        double z = __ldg(&a.zarr[i]);
-                        double ps = aP * z * z + bP * z + cP, Ls = aL * z * z + bL * z + cL;
-                        for (long long q = q0; q < seg_end; ++q) {                    // lumfuncmcmc_z.py:374
-                            const QuadPoint* pt = &a.qp[q];
-                            acc0 = fma(__ldg(&pt->wt), schechter_literal(__ldg(&pt->x), sal, Ls, ps), acc0);
+                        for (; j < cnt; ++j) {
+                            const double2 xl = s_stage[j * 2];
+                            acc0 = fma(s_stage[j * 2 + 1].x, exp_full<false>(fma(-xl.y, cB, fma(c1, xl.x, cA)), s_exp_rep, rep16), acc0);
                         }
                     }
-                    q0 = seg_end;
+                };
+                if (MODEL == LF_MODEL_FIXED) {
+                    if (!LITERAL) {
+                        quad_segment(q0, q1, wp[P_C0 * WS], wp[P_TENML * WS]);
+                    } else {
+                        const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
+                        for (long long q = q0; q < q1; ++q) {                         // lumfuncmcmc.py:391
+                            const QuadPoint* pt = &a.qp[q];
+                            acc0 = fma(__ldg(&pt->wt), schechter_literal(__ldg(&pt->x), sal, Lstar, phistar), acc0);
+                        }
+                    }
+                } else {
+                    // Z: points are stored column-major: q = (k*S + i)*S + j  (column i <-> zarr_i)
+                    const double sal = wp[P_SCHAL * WS];
+                    const double aL = wp[P_AL * WS], bL = wp[P_BL * WS], cL = wp[P_CL * WS];
+                    const double aP = wp[P_AP * WS], bP = wp[P_BP * WS], cP = wp[P_CP * WS];
+                    while (q0 < q1) {
+                        long long col = q0 / a.S;                    // global column index k*S + i
+                        int i = (int)(col % a.S);
+                        long long seg_end = (col + 1) * a.S < q1 ? (col + 1) * a.S : q1;
+                        if (!LITERAL) {
+                            quad_segment(q0, seg_end, a.colA[(long long)i * WS + w], a.colB[(long long)i * WS + w]);
+                        } else {
+                            double z = __ldg(&a.zarr[i]);
+                            double ps = aP * z * z + bP * z + cP, Ls = aL * z * z + bL * z + cL;
+                            for (long long q = q0; q < seg_end; ++q) {                // lumfuncmcmc_z.py:374
+                                const QuadPoint* pt = &a.qp[q];
+                                acc0 = fma(__ldg(&pt->wt), schechter_literal(__ldg(&pt->x), sal, Ls, ps), acc0);
+                            }
+                        }
+                        q0 = seg_end;
+                    }
                 }
             }
         }
@@ -1133,6 +1176,8 @@ extern "C" int lf_ndim(const lf_ctx* ctx) { return ctx ? ctx->ndim : -1; }
 
 static void fill_tables(Tables& t) {
     for (int j = 0; j < EXP_TAB_N; ++j) t.exp2_frac[j] = (double)exp2l((long double)j / EXP_TAB_N);
+    for (int i = 0; i < EXPB_N; ++i) t.exp2_big[i] = (double)exp2l((long double)(EXPB_KMIN + i) / EXP_TAB_N);
+    t.exp2_big[EXPB_N] = 1.0;
     const int M = 1 << LOG_MANT_BITS;
     for (int b = 0; b < LOG_OCTAVES * M; ++b) {
         int E = -LOG_OCTAVES + b / M, j = b % M;
@@ -1170,7 +1215,9 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     CK(cudaMalloc(&c->d_tables, sizeof(Tables)));
     CK(cudaMemcpy(c->d_tables, &t, sizeof(Tables), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&c->d_cls, 8 * sizeof(int)));
-    CK(cudaFuncSetAttribute(k_main<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TABLE_BYTES));
+    CK(cudaFuncSetAttribute(k_main<false, LF_MODEL_FREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem_bytes(LF_MODEL_FREE)));
+    CK(cudaFuncSetAttribute(k_main<false, LF_MODEL_FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem_bytes(LF_MODEL_FIXED)));
+    CK(cudaFuncSetAttribute(k_main<false, LF_MODEL_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem_bytes(LF_MODEL_Z)));
     {
         const int atom_smem = (int)(sizeof(double) * (VEFF_MAX_BINS + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * VEFF_MAX_BINS);
         CK(cudaFuncSetAttribute(k_veff<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, atom_smem));
@@ -1180,8 +1227,16 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     CK(cudaFuncSetAttribute(k_veff_priv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
     CK(cudaFuncSetAttribute(k_veff_priv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
     CK(cudaFuncSetAttribute(k_veff_priv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_fast, k_main<false>, BLOCK_THREADS, SMEM_TABLE_BYTES));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lit, k_main<true>, BLOCK_THREADS, 0));
+    if (cfg->model == LF_MODEL_FREE) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_fast, k_main<false, LF_MODEL_FREE>, 32 * main_warps(LF_MODEL_FREE), main_smem_bytes(LF_MODEL_FREE)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lit, k_main<true, LF_MODEL_FREE>, 32 * main_warps(LF_MODEL_FREE), 0));
+    } else if (cfg->model == LF_MODEL_FIXED) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_fast, k_main<false, LF_MODEL_FIXED>, 32 * main_warps(LF_MODEL_FIXED), main_smem_bytes(LF_MODEL_FIXED)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lit, k_main<true, LF_MODEL_FIXED>, 32 * main_warps(LF_MODEL_FIXED), 0));
+    } else {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_fast, k_main<false, LF_MODEL_Z>, 32 * main_warps(LF_MODEL_Z), main_smem_bytes(LF_MODEL_Z)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lit, k_main<true, LF_MODEL_Z>, 32 * main_warps(LF_MODEL_Z), 0));
+    }
     if (c->occ_fast < 1) c->occ_fast = 1;
     if (c->occ_lit < 1) c->occ_lit = 1;
     memset(&c->ka, 0, sizeof(KArgs));
@@ -1482,7 +1537,7 @@ static int ensure_scratch(lf_ctx* c, long long W, int rows) {
 // choose slab counts so that one class fills the machine with a few waves of warp items
 static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
     const long long n_wg = (W + 31) / 32;
-    const long long target_items = (long long)c->sm_count * 16 * 24;   // ~24 items per resident warp
+    const long long target_items = (long long)c->sm_count * 16 * 24;   // ~24-32 items per resident warp
     long long rows = std::min<long long>(4096, std::max<long long>(1, target_items / n_wg));
     const int model = c->cfg.model;
     // relative cost of a quadrature point vs a source term
@@ -1521,11 +1576,20 @@ static int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, doubl
     }
     const long long n_wg = (W + 31) / 32;
     const long long items = n_wg * (n_src + n_quad);
-    const long long need = (items + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK;      // never more blocks than items
+    const int wpb = main_warps(c->cfg.model);
+    const long long need = (items + wpb - 1) / wpb;      // never more blocks than items
     const unsigned bf = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_fast);
     const unsigned bl = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_lit);
-    k_main<false><<<bf, BLOCK_THREADS, SMEM_TABLE_BYTES, st>>>(a);
-    k_main<true><<<bl, BLOCK_THREADS, 0, st>>>(a);
+    if (c->cfg.model == LF_MODEL_FREE) {
+        k_main<false, LF_MODEL_FREE><<<bf, 32 * main_warps(LF_MODEL_FREE), main_smem_bytes(LF_MODEL_FREE), st>>>(a);
+        k_main<true, LF_MODEL_FREE><<<bl, 32 * main_warps(LF_MODEL_FREE), 0, st>>>(a);
+    } else if (c->cfg.model == LF_MODEL_FIXED) {
+        k_main<false, LF_MODEL_FIXED><<<bf, 32 * main_warps(LF_MODEL_FIXED), main_smem_bytes(LF_MODEL_FIXED), st>>>(a);
+        k_main<true, LF_MODEL_FIXED><<<bl, 32 * main_warps(LF_MODEL_FIXED), 0, st>>>(a);
+    } else {
+        k_main<false, LF_MODEL_Z><<<bf, 32 * main_warps(LF_MODEL_Z), main_smem_bytes(LF_MODEL_Z), st>>>(a);
+        k_main<true, LF_MODEL_Z><<<bl, 32 * main_warps(LF_MODEL_Z), 0, st>>>(a);
+    }
     k_finish<<<(unsigned)((W + 31) / 32), 32 * FIN_GROUPS, 0, st>>>(a);
     c->launches += 3;
     CK(cudaGetLastError());

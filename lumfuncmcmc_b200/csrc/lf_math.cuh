@@ -38,7 +38,18 @@ constexpr double MPC_CM_REF = 3.086e24;                             // the refer
 #ifndef LF_LOG_REP
 #define LF_LOG_REP 2
 #endif
-constexpr int EXP_TAB_BITS = 8, EXP_TAB_N = 1 << EXP_TAB_BITS, EXP_TAB_REP = LF_EXP_REP;   // 256*16*8 B = 32 KB, replicated x16: a half-warp never bank-conflicts
+#ifndef LF_EXP_BIG
+#define LF_EXP_BIG 1
+#endif
+constexpr int EXP_TAB_BITS = 8, EXP_TAB_N = 1 << EXP_TAB_BITS, EXP_TAB_REP = LF_EXP_REP;   // small table: 256*16*8 B = 32 KB, replicated x16 (a half-warp never bank-conflicts)
+// LF_EXP_BIG: one unreplicated table of 2^(k/256) for k = EXPB_KMIN .. 0 (80 KB): the decay factor 2^(x2), x2 <= 0, is a
+// single look-up with the integer k clamped at -40*256 (2^-40 = 9e-13 against 1, times |ln fc| < 0.01 for a source that
+// bright) -- no index masking, no exponent arithmetic; the full-range exp of the FREE model's quadrature uses its top
+// 256 entries.  The Z / FIXED models have no log table and keep the small replicated table in its place (their hot
+// loop is the full-range exp, where bank conflicts of an unreplicated table cost 20 %).
+constexpr int EXPB_KMIN = -40 * (1 << EXP_TAB_BITS), EXPB_N = -EXPB_KMIN + 1;
+constexpr int EXP_SMEM_DOUBLES = LF_EXP_BIG ? ((EXPB_N + 1) & ~1) : EXP_TAB_N * EXP_TAB_REP;
+constexpr bool EXP_BIG = LF_EXP_BIG != 0;
 constexpr int LOG_OCTAVES = 12, LOG_MANT_BITS = 8;
 constexpr int LOG_TAB_N = LOG_OCTAVES * (1 << LOG_MANT_BITS) + 1, LOG_TAB_REP = LF_LOG_REP;  // 3073*2*16 B = 96 KB, two replicas (even / odd lanes)
 constexpr int LOG_TAB_BASE = (1023 - LOG_OCTAVES) << LOG_MANT_BITS;                        // index of 2^-12 in (hi >> 12)
@@ -66,6 +77,7 @@ __constant__ double KC[16] = {
 
 struct Tables {                 // device-global master copies (filled by the host at lf_create)
     double exp2_frac[EXP_TAB_N];        // 2^(j/256)
+    double exp2_big[EXPB_N + 1];        // 2^(k/256), k = EXPB_KMIN .. 0
     double2 log_tab[LOG_TAB_N + 1];     // bin b <-> argument bits (hi >> 12) == LOG_TAB_BASE + b:
                                         //   (1/c_b, ln c_b), c_b = bin centre incl. its power of two; last: (1, 0)
 };
@@ -89,20 +101,35 @@ __device__ __forceinline__ double rcp_fast(double d) {
 }
 
 // cooperative fill of the (replicated) shared-memory tables
+// models without a log table: only the small replicated exp table
+__device__ __forceinline__ void load_exp_replicated(const Tables* __restrict__ t, double* s_exp_rep) {
+    for (int i = threadIdx.x; i < EXP_TAB_N * EXP_TAB_REP; i += blockDim.x) s_exp_rep[i] = t->exp2_frac[i / EXP_TAB_REP];
+}
 __device__ __forceinline__ void load_tables(const Tables* __restrict__ t, double* s_exp, double2* s_log) {
+#if LF_EXP_BIG
+    for (int i = threadIdx.x; i < EXPB_N; i += blockDim.x) s_exp[i] = t->exp2_big[i];
+#else
     for (int i = threadIdx.x; i < EXP_TAB_N * EXP_TAB_REP; i += blockDim.x) s_exp[i] = t->exp2_frac[i / EXP_TAB_REP];
+#endif
     for (int i = threadIdx.x; i < LOG_TAB_N * LOG_TAB_REP; i += blockDim.x) s_log[i] = t->log_tab[i / LOG_TAB_REP];
 }
 
 // 2^(x2) split as 2^K * T[j] * p(r): returns p(r) ~ 2^r and the scaled table entry Ts = 2^K T[j];  x2 = a * b is
 // formed inside the two fmas only (no separately rounded product).  Needs |x2| < 8.3e6.  FP64 instructions: 6.
+template <bool BIG>
 __device__ __forceinline__ void exp2_parts(double a, double b, const double* s_exp, int rep, int kmin, double& Ts, double& p) {
     double t = fma(a, b, KC[0]);
     int k = __double2loint(t);                    // round(256 x2)
     double kf = t - KC[0];
     double r = fma(a, b, -kf);                    // |r| <= 2^-9, exact up to one rounding
-    double T = s_exp[(k & (EXP_TAB_N - 1)) * EXP_TAB_REP + rep];
+    double T;
     int K = max(k >> EXP_TAB_BITS, kmin);         // keeps the exponent field valid
+    if (BIG) {
+        T = s_exp[(k & (EXP_TAB_N - 1)) + (EXPB_N - 1 - EXP_TAB_N)];         // 2^((j - 256)/256), j = k mod 256
+        K += 1;
+    } else {
+        T = s_exp[(k & (EXP_TAB_N - 1)) * EXP_TAB_REP + rep];
+    }
     Ts = __hiloint2double(__double2hiint(T) + (K << 20), __double2loint(T));
     p = fma(r, KC[1], KC[2]);
     p = fma(r, p, KC[3]);
@@ -112,22 +139,35 @@ __device__ __forceinline__ void exp2_parts(double a, double b, const double* s_e
 // 1 - 2^(f * c2) for f * c2 in (-8.3e6, 0]; ABSOLUTE accuracy ~2e-14.  FP64 instructions: 7
 __device__ __forceinline__ double one_minus_exp2(double f, double c2, const double* s_exp, int rep) {
     double Ts, p;
-    exp2_parts(f, c2, s_exp, rep, -1000, Ts, p);  // 2^x2 < 2^-1000 is 0 against 1
+#if LF_EXP_BIG
+    double t = fma(f, c2, KC[0]);
+    int k = max(__double2loint(t), EXPB_KMIN);    // round(256 x2), clamped: 2^-40 is 0 against 1 at the budget of this routine
+    double kf = t - KC[0];
+    double r = fma(f, c2, -kf);
+    Ts = s_exp[k - EXPB_KMIN];
+    p = fma(r, KC[1], KC[2]);
+    p = fma(r, p, KC[3]);
+    p = fma(r, p, KC[4]);
+#else
+    exp2_parts<false>(f, c2, s_exp, rep, -1000, Ts, p);  // 2^x2 < 2^-1000 is 0 against 1
+#endif
     return fma(-Ts, p, 1.0);
 }
 
 // 2^(x2) with RELATIVE accuracy ~2e-14 for x2 in [-1020, 1020] (the callers guarantee the range).  FP64 instructions: 7
+template <bool BIG>
 __device__ __forceinline__ double exp2_full(double x2, const double* s_exp, int rep) {
     double Ts, p;
-    exp2_parts(x2, 1.0, s_exp, rep, -1022, Ts, p);
+    exp2_parts<BIG>(x2, 1.0, s_exp, rep, -1022, Ts, p);
     return Ts * p;
 }
 
 // exp(x) for x in [-707, 707]; below -707 returns 0.  FP64 instructions: 1 + 1 + 7
+template <bool BIG>
 __device__ __forceinline__ double exp_full(double x, const double* s_exp, int rep) {
     bool under = x < -707.0;
     double Ts, p;
-    exp2_parts(under ? -707.0 : x, KC[8], s_exp, rep, -1022, Ts, p);
+    exp2_parts<BIG>(under ? -707.0 : x, KC[8], s_exp, rep, -1022, Ts, p);
     return under ? 0.0 : Ts * p;
 }
 
@@ -197,9 +237,13 @@ __device__ __forceinline__ void fleming_terms(const double2* u, double alpha, do
     }
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
+#if LF_EXP_BIG
+        Ts[i] = s_exp[max(k[i], EXPB_KMIN) - EXPB_KMIN];
+#else
         double T = s_exp[(k[i] & (EXP_TAB_N - 1)) * EXP_TAB_REP + repe];
         int K = max(k[i] >> EXP_TAB_BITS, -1000);
         Ts[i] = __hiloint2double(__double2hiint(T) + (K << 20), __double2loint(T));
+#endif
     }
 #pragma unroll
     for (int i = 0; i < NT; ++i) r[i] = fma(u[i].y, c2, -t[i]);
@@ -230,8 +274,11 @@ __device__ __forceinline__ void fleming_terms(const double2* u, double alpha, do
     for (int i = 0; i < NT; ++i) r0[i] = rcp_seed(dec[i]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-        int b = (__double2hiint(fc[i]) >> (20 - LOG_MANT_BITS)) - LOG_TAB_BASE;
-        tb[i] = s_log[b * LOG_TAB_REP + repl];
+        // byte offset of table row b = (hi >> 12) - LOG_TAB_BASE: ((hi >> 12) * 32) = (hi >> 7) & ~31, the base folds into
+        // the load's immediate, the replica offset is OR-ed in (LOP3 co-issues with the FP64 pipe, IMAD does not)
+        static_assert(LOG_TAB_REP == 2 && LOG_MANT_BITS == 8, "index arithmetic below assumes 32-byte rows");
+        const unsigned off = ((unsigned)(__double2hiint(fc[i]) >> 7) & ~31u) | (unsigned)(repl << 4);
+        tb[i] = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(s_log) + off - (LOG_TAB_BASE << 5));
     }
 #pragma unroll
     for (int i = 0; i < NT; ++i) e[i] = fma(-dec[i], r0[i], 1.0);
