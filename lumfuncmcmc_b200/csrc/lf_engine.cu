@@ -99,6 +99,8 @@ struct KArgs {
     double fcap;                       // cap of the flux copy used in the decay argument (see k_derive_free)
     // resident arrays
     const double2* src2;               // FREE: (log10 flux, flux)   Z: (lum, z)
+    const double2* csrc;               // compressed catalogue, two entries per pseudo-source: (xi = log10 f, min(10^xi, fcap)), (weight, -); or NULL
+    long long M; long long cfield_ind[LF_MAX_FIELDS + 1];
     const float2* src2f;               // LF_PREC_F32 copy: FREE (log10 f + 17, f * 1e17)   Z: (lum - 42, z - z2)
     int precision;                     // LF_PREC_F64 | LF_PREC_F32 (arithmetic of the walker x source loop only)
     const double* lum;
@@ -431,7 +433,42 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
     if (row < a.n_src_slabs) {
         // ---------------- source slab ----------------
         long long i0 = (a.N * row) / a.n_src_slabs, i1 = (a.N * (row + 1)) / a.n_src_slabs;
-        if (MODEL == LF_MODEL_FREE) {
+        if (MODEL == LF_MODEL_FREE && !LITERAL && a.csrc != nullptr) {
+            // compressed catalogue: sum_m w_m t(xi_m) over this slab of pseudo-sources (see lumfuncmcmc_b200/compress.py)
+            const double alpha = wp[P_ALPHA * WS];
+            long long m0 = (a.M * row) / a.n_src_slabs, m1 = (a.M * (row + 1)) / a.n_src_slabs;
+            int k = 0;
+            while (k + 1 < a.K && m0 >= a.cfield_ind[k + 1]) ++k;
+            while (m0 < m1) {
+                const long long seg_end = a.cfield_ind[k + 1] < m1 ? a.cfield_ind[k + 1] : m1;
+                const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], c2 = wp[(P_FIELD0 + 4 * k + 1) * WS];
+                long long m = m0;
+                for (; m + 1 < seg_end; m += 2) {
+                    const double2 u0 = __ldg(&a.csrc[2 * m]), u1 = __ldg(&a.csrc[2 * m + 2]);
+                    const double w0 = __ldg(&a.csrc[2 * m + 1]).x, w1 = __ldg(&a.csrc[2 * m + 3]).x;
+                    double lg0, rd0, lg1, rd1;
+                    if (a.modified) {
+                        fleming_log_parts<true>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                        fleming_log_parts<true>(u1.x, u1.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg1, rd1);
+                    } else {
+                        fleming_log_parts<false>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                        fleming_log_parts<false>(u1.x, u1.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg1, rd1);
+                    }
+                    acc0 = fma(w0 * lg0, rd0, acc0);
+                    acc1 = fma(w1 * lg1, rd1, acc1);
+                }
+                if (m < seg_end) {
+                    const double2 u0 = __ldg(&a.csrc[2 * m]);
+                    const double w0 = __ldg(&a.csrc[2 * m + 1]).x;
+                    double lg0, rd0;
+                    if (a.modified) fleming_log_parts<true>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                    else fleming_log_parts<false>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                    acc0 = fma(w0 * lg0, rd0, acc0);
+                }
+                m0 = seg_end;
+                ++k;
+            }
+        } else if (MODEL == LF_MODEL_FREE) {
             const double alpha = wp[P_ALPHA * WS];
             int k = field_of(a, i0);
             while (i0 < i1) {
@@ -1143,7 +1180,7 @@ struct lf_ctx {
     // resident
     long long N = 0, NQ = 0;
     double* d_lum = nullptr; double* d_flux = nullptr; double* d_z = nullptr; double* d_om = nullptr;
-    double* d_Lsrc = nullptr; double2* d_src2 = nullptr; float2* d_src2f = nullptr;
+    double* d_Lsrc = nullptr; double2* d_src2 = nullptr; float2* d_src2f = nullptr; double2* d_csrc = nullptr;
     QuadPointFree* d_qpf = nullptr; QuadPoint* d_qp = nullptr; double* d_zarr = nullptr;
     Tables* d_tables = nullptr;
     bool have_sources = false, have_grid = false;
@@ -1262,6 +1299,16 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     return 0;
 }
 
+struct DevBufs {                       // frees whatever was allocated when it goes out of scope
+    std::vector<void*> p;
+    ~DevBufs() { for (void* q : p) cudaFree(q); }
+    template <typename T> cudaError_t alloc(T** out, size_t bytes) {
+        cudaError_t e = cudaMalloc(out, bytes ? bytes : 8);
+        if (e == cudaSuccess) p.push_back(*out);
+        return e;
+    }
+};
+
 template <typename T>
 static void dfree(T*& p) {
     if (p) cudaFree(p);
@@ -1271,7 +1318,7 @@ static void dfree(T*& p) {
 extern "C" void lf_destroy(lf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    dfree(c->d_lum); dfree(c->d_flux); dfree(c->d_z); dfree(c->d_om); dfree(c->d_Lsrc); dfree(c->d_src2); dfree(c->d_src2f);
+    dfree(c->d_lum); dfree(c->d_flux); dfree(c->d_z); dfree(c->d_om); dfree(c->d_Lsrc); dfree(c->d_src2); dfree(c->d_src2f); dfree(c->d_csrc);
     dfree(c->d_qpf); dfree(c->d_qp); dfree(c->d_zarr); dfree(c->d_tables);
     dfree(c->d_wp); dfree(c->d_colA); dfree(c->d_colB); dfree(c->d_partial);
     dfree(c->d_cls); dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_list_fastq); dfree(c->d_list_litq); dfree(c->d_thetas); dfree(c->d_out);
@@ -1325,6 +1372,7 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
     c->N = n;
     KArgs& a = c->ka;
     a.N = n;
+    dfree(c->d_csrc); a.csrc = nullptr; a.M = 0;              // a new catalogue invalidates its compressed form
     for (int k = 0; k <= K; ++k) a.field_ind[k] = field_ind[k];
     for (int k = 0; k < K; ++k) {
         FieldStats& s = a.fs[k];
@@ -1488,6 +1536,50 @@ extern "C" int lf_set_grid(lf_ctx* c, const double* logL, const double* zarr, co
     return 0;
 }
 
+__global__ void k_derive_compressed(long long m, const double* __restrict__ xi, const double* __restrict__ w, double fcap,
+                                    double2* __restrict__ out) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const double g = xi[i];
+    out[2 * i] = make_double2(g, fmin(pow(10.0, g), fcap));
+    out[2 * i + 1] = make_double2(w[i], 0.0);
+}
+
+extern "C" int lf_set_compressed_sources(lf_ctx* c, int64_t M, const double* xi, const double* w, const int64_t* cfield_ind) {
+    if (!c) return fail("lf_set_compressed_sources: null context");
+    if (c->cfg.model != LF_MODEL_FREE) return fail("lf_set_compressed_sources: only the free-completeness model has a compressed form");
+    if (c->cfg.precision != LF_PREC_F64) return fail("lf_set_compressed_sources: FP64 only");
+    if (!c->have_sources) return fail("lf_set_compressed_sources: call lf_set_sources first");
+    CK(cudaSetDevice(c->device));
+    dfree(c->d_csrc);
+    c->ka.csrc = nullptr; c->ka.M = 0;
+    if (M == 0) return 0;
+    if (M < 0 || !xi || !w || !cfield_ind) return fail("lf_set_compressed_sources: bad arguments");
+    const int K = c->cfg.nfields;
+    if (cfield_ind[0] != 0 || cfield_ind[K] != M) return fail("lf_set_compressed_sources: cfield_ind must run from 0 to M");
+    for (int k = 0; k < K; ++k) {
+        if (cfield_ind[k + 1] < cfield_ind[k]) return fail("lf_set_compressed_sources: cfield_ind must be non-decreasing");
+        if ((cfield_ind[k + 1] > cfield_ind[k]) != (c->ka.fs[k].n > 0.0)) return fail("lf_set_compressed_sources: a field has sources but no pseudo-sources (or the reverse)");
+    }
+    // every node must lie inside the range of fluxes the classification bounds were computed for
+    for (int k = 0; k < K; ++k)
+        for (int64_t m = cfield_ind[k]; m < cfield_ind[k + 1]; ++m)
+            if (!(xi[m] >= c->ka.fs[k].g_min - 1.0e-9) || !(xi[m] == xi[m])) return fail("lf_set_compressed_sources: a node lies below the field's faintest source");
+    double *d_xi = nullptr, *d_w = nullptr;
+    DevBufs tmp;
+    CK(tmp.alloc(&d_xi, sizeof(double) * M));
+    CK(tmp.alloc(&d_w, sizeof(double) * M));
+    CK(cudaMalloc(&c->d_csrc, sizeof(double2) * 2 * (size_t)M));
+    CK(cudaMemcpy(d_xi, xi, sizeof(double) * M, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(d_w, w, sizeof(double) * M, cudaMemcpyHostToDevice));
+    k_derive_compressed<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(M, d_xi, d_w, c->ka.fcap, c->d_csrc);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    c->ka.csrc = c->d_csrc; c->ka.M = M;
+    for (int k = 0; k <= K; ++k) c->ka.cfield_ind[k] = cfield_ind[k];
+    return 0;
+}
+
 extern "C" int lf_set_prior_gate(lf_ctx* c, int32_t enabled) {
     if (!c) return fail("lf_set_prior_gate: null context");
     c->ka.prior_gate = enabled ? 1 : 0;
@@ -1543,12 +1635,13 @@ static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
     // relative cost of a quadrature point vs a source term
     double src_cost = model == LF_MODEL_FREE ? 1.0 : (model == LF_MODEL_Z ? 0.5 : 0.0);
     double quad_cost = model == LF_MODEL_FREE ? 1.5 : 0.6;
-    double wsrc = src_cost * (double)c->N, wq = quad_cost * (double)c->NQ;
+    const long long n_eff = (c->d_csrc && model == LF_MODEL_FREE) ? c->ka.M : c->N;      // pseudo-sources when compressed
+    double wsrc = src_cost * (double)n_eff, wq = quad_cost * (double)c->NQ;
     double tot = wsrc + wq;
     if (tot <= 0.0) { n_src = 1; n_quad = 1; return; }
     long long rs = (long long)llround((double)rows * wsrc / tot), rq = rows - rs;
     const long long min_per = 64;       // at least this many sources / points per work item
-    rs = std::max<long long>(1, std::min<long long>(rs, std::max<long long>(1, c->N / min_per)));
+    rs = std::max<long long>(1, std::min<long long>(rs, std::max<long long>(1, n_eff / min_per)));
     rq = std::max<long long>(1, std::min<long long>(rq, std::max<long long>(1, c->NQ / min_per)));
     n_src = (int)rs;
     n_quad = (int)rq;
@@ -1877,15 +1970,6 @@ __global__ void k_interp(long long nk, const double* __restrict__ xk, const doub
     y[i] = r;
 }
 
-struct DevBufs {                       // frees whatever was allocated when it goes out of scope
-    std::vector<void*> p;
-    ~DevBufs() { for (void* q : p) cudaFree(q); }
-    template <typename T> cudaError_t alloc(T** out, size_t bytes) {
-        cudaError_t e = cudaMalloc(out, bytes ? bytes : 8);
-        if (e == cudaSuccess) p.push_back(*out);
-        return e;
-    }
-};
 
 extern "C" int lf_cosmo_distances(int32_t device, const lf_cosmology* cosmo, const double* cum, int64_t ncum, int64_t n,
                                   const double* z, double* DL_Mpc, double* dVdz) {

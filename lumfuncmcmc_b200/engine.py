@@ -116,7 +116,7 @@ class VeffEngine(_VeffOps):
 class LikelihoodEngine(_VeffOps):
     """One engine context on one GPU holding one shard of sources."""
 
-    def __init__(self, inp, kind, device=0, force_literal=False, quadrature_share=(0, 1), precision='f64'):
+    def __init__(self, inp, kind, device=0, force_literal=False, quadrature_share=(0, 1), precision='f64', compress=False):
         if precision not in ('f64', 'f32'):
             raise ValueError("precision must be 'f64' or 'f32'")
         self.precision = precision
@@ -176,6 +176,7 @@ class LikelihoodEngine(_VeffOps):
                 zz = _f64(inp['z'])
         _lib.check(self.lib.lf_set_sources(self._ctx, self.nsources, _ptr(lum), _ptr(flux), _ptr(zz), _ptr(om),
                                            _ptr(fi), _ptr(om0i)), self.lib)
+        self._flux_host = flux                      # kept for compress_catalogue (free model)
         # ---- quadrature grid -----------------------------------------------------------------
         logL = _f64(inp['logL'])
         if logL.shape != (K, S, S):
@@ -192,6 +193,24 @@ class LikelihoodEngine(_VeffOps):
             _lib.check(self.lib.lf_set_grid(self._ctx, _ptr(logL), _ptr(zarr), None, None, _ptr(ip), None), self.lib)
         if tuple(quadrature_share) != (0, 1):
             self.set_quadrature_share(*quadrature_share)
+        self.npseudo = 0
+        if compress:
+            if kind != 'free' or precision != 'f64':
+                raise ValueError("compress=True applies to the free-completeness model in FP64")
+            self.compress_catalogue(flux, fi, alpha_max=float(cfg.alpha_lims[1]), **(compress if isinstance(compress, dict) else {}))
+
+    def compress_catalogue(self, flux, field_ind, alpha_max, nodes=12, bin_dex=None):
+        """Switch the fast kernels' source sum to the weighted pseudo-source form (see :mod:`.compress`)."""
+        from .compress import compress_sources
+        xi, w, cfi = compress_sources(np.log10(flux), field_ind, alpha_max, nodes=nodes, bin_dex=bin_dex)
+        xi, w = _f64(xi), _f64(w)
+        _lib.check(self.lib.lf_set_compressed_sources(self._ctx, xi.shape[0], _ptr(xi), _ptr(w), _ptr(cfi)), self.lib)
+        self.npseudo = int(xi.shape[0])
+        return self.npseudo
+
+    def uncompress_catalogue(self):
+        _lib.check(self.lib.lf_set_compressed_sources(self._ctx, 0, None, None, None), self.lib)
+        self.npseudo = 0
 
     # ------------------------------------------------------------------------------------------
     def set_quadrature_share(self, share, nshare):

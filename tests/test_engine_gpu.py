@@ -290,3 +290,35 @@ def test_full_size_catalogue_properties_and_oracle_spot_check():
     e = _engine(p, 'free')
     _assert_parity(e.lnprob(th), whole, rtol=1e-13)
     e.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# compressed catalogue (opt-in): weighted pseudo-sources instead of the walker x source loop
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('name', ['free_k5_n2000', 'free_k3_fixal', 'free_k2_mcf50'])
+def test_compressed_catalogue_golden(golden, name):
+    g = golden(name)
+    eng = _engine(g, 'free', compress=True)
+    assert 0 < eng.npseudo
+    got = eng.lnprob(g['thetas'])
+    _assert_parity(got, g['lnprob_ref'])
+    eng.uncompress_catalogue()
+    _assert_parity(got, eng.lnprob(g['thetas']), rtol=1e-12)
+    eng.close()
+
+
+def test_compressed_catalogue_midsize_against_brute_force_and_oracle():
+    """N = 2e5 -> a few thousand pseudo-sources; walkers near the truth and over the whole prior box (alpha_c up to 7)."""
+    cat = synth.make_catalogue(200000, seed=23)
+    inp = synth.direct_inputs(cat, nknots=2048, size_ln=101)
+    th = np.concatenate([synth.draw_thetas(inp, 'free', 64, seed=5, mode='near', scale=0.02),
+                         synth.draw_thetas(inp, 'free', 64, seed=6, mode='prior')])
+    th[64:72, -1] = 7.0                                          # the prior's steepest completeness curve
+    brute, comp = _engine(inp, 'free'), _engine(inp, 'free', compress=True)
+    assert comp.npseudo < 20000
+    a, b = brute.lnprob(th), comp.lnprob(th)
+    rel = _assert_parity(b, a, rtol=1e-12)
+    _assert_parity(b[:16], lf_oracle.lnprob_batch(inp, 'free', th[:16]))
+    print('compressed: %d pseudo-sources for %d sources, max rel diff vs brute force %.2e' % (comp.npseudo, 200000, rel))
+    brute.close()
+    comp.close()
