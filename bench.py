@@ -309,7 +309,7 @@ def main():
         dt_d = time.perf_counter() - t0
         small = {"workload": "BASELINE.json configs[0] size: 1e4 sources x 100 walkers, 1 GPU",
                  "steps_per_s": 2000 / dt_d, "sampler": "device-resident (lf_sampler_run), 2000 updates, wall clock incl. chain D2H",
-                 "device_ms_per_step": dev_s.device_ms / 2050, "acceptance": float(np.mean(dev_s.acceptance_fraction)),
+                 "device_ms_per_step": dev_s.device_ms / 2050, "steps_per_s_device_time": 2050.0e3 / dev_s.device_ms, "acceptance": float(np.mean(dev_s.acceptance_fraction)),
                  "host_sampler": {"steps_per_s": 200 / dt_s, "lnprob_calls_per_s": 400 / dt_s,
                                   "acceptance": float(np.mean(smp_s.acceptance_fraction))}}
         eng_s.close()

@@ -487,12 +487,18 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
                         float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
                         int j = j0;
                         if (a.modified) {
-                            for (; j + 4 <= j1; j += 4) {
-                                float2 u0 = __ldg(pf + j), u1 = __ldg(pf + j + 1), u2 = __ldg(pf + j + 2), u3 = __ldg(pf + j + 3);
-                                f0 += fleming_log2_f32<true>(u0.x, u0.y, af, aFs, c2);
-                                f1 += fleming_log2_f32<true>(u1.x, u1.y, af, aFs, c2);
-                                f2 += fleming_log2_f32<true>(u2.x, u2.y, af, aFs, c2);
-                                f3 += fleming_log2_f32<true>(u3.x, u3.y, af, aFs, c2);
+#ifndef LF_F32_ILP
+#define LF_F32_ILP 16
+#endif
+                            for (; j + LF_F32_ILP <= j1; j += LF_F32_ILP) {
+                                float2 u[LF_F32_ILP];
+                                float tt[LF_F32_ILP];
+#pragma unroll
+                                for (int t = 0; t < LF_F32_ILP; ++t) u[t] = __ldg(pf + j + t);
+#pragma unroll
+                                for (int t = 0; t < LF_F32_ILP; ++t) tt[t] = fleming_log2_f32<true>(u[t].x, u[t].y, af, aFs, c2);
+#pragma unroll
+                                for (int t = 0; t < LF_F32_ILP; t += 4) { f0 += tt[t]; f1 += tt[t + 1]; f2 += tt[t + 2]; f3 += tt[t + 3]; }
                             }
                             for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += fleming_log2_f32<true>(u0.x, u0.y, af, aFs, c2); }
                         } else {
@@ -586,12 +592,17 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
                     const long long j1 = j0 + 64 < cnt ? j0 + 64 : cnt;
                     float f0 = 0.f, f1 = 0.f;
                     long long j = j0;
-                    for (; j + 2 <= j1; j += 2) {
-                        float2 u0 = __ldg(pf + j), u1 = __ldg(pf + j + 1);
-                        f0 += mufu_ex2((u0.x - fmaf(fmaf(q2, u0.y, q1), u0.y, q0)) * L2T);
-                        f1 += mufu_ex2((u1.x - fmaf(fmaf(q2, u1.y, q1), u1.y, q0)) * L2T);
+                    for (; j + 8 <= j1; j += 8) {                   // eight independent MUFU chains per thread
+                        float2 u[8];
+                        float e[8];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) u[t] = __ldg(pf + j + t);
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) e[t] = mufu_ex2((u[t].x - fmaf(fmaf(q2, u[t].y, q1), u[t].y, q0)) * L2T);
+#pragma unroll
+                        for (int t = 0; t < 8; t += 2) { f0 += e[t]; f1 += e[t + 1]; }
                     }
-                    if (j < j1) { float2 u0 = __ldg(pf + j); f0 += mufu_ex2((u0.x - fmaf(fmaf(q2, u0.y, q1), u0.y, q0)) * L2T); }
+                    for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += mufu_ex2((u0.x - fmaf(fmaf(q2, u0.y, q1), u0.y, q0)) * L2T); }
                     sum += (double)(f0 + f1);
                 }
                 acc0 -= sum;
