@@ -322,3 +322,27 @@ def test_compressed_catalogue_midsize_against_brute_force_and_oracle():
     print('compressed: %d pseudo-sources for %d sources, max rel diff vs brute force %.2e' % (comp.npseudo, 200000, rel))
     brute.close()
     comp.close()
+
+
+def test_peer_memory_allreduce_degenerates_to_identity_on_one_rank(golden):
+    """world = 1: the peer-memory exchange kernel (stores, flag, wait, rank-ordered sum) returns the vector unchanged,
+    for both buffer parities and for lengths that are not a multiple of the 256-walker chunk.  The multi-rank case is
+    exercised by tools/multi_gpu_parity.py under torchrun (profiles/r01_multi_gpu_parity_2gpu_p2p.log)."""
+    import torch
+    g = golden('free_k3_fixal')
+    eng = _engine(g, 'free')
+    handle = eng.peer_buffer_create(0, 1, 1000)
+    assert len(handle) == 64
+    eng.peer_buffer_connect([handle])
+    for n in (1, 255, 256, 257, 1000):
+        v = torch.arange(n, dtype=torch.float64, device='cuda') * 0.5 - 3.0
+        v[0] = float('-inf')
+        want = v.clone()
+        for _ in range(3):
+            eng.allreduce_device(v)
+        torch.cuda.synchronize()
+        assert torch.equal(v, want)
+    assert not eng.peer_timed_out()
+    with pytest.raises(Exception):
+        eng.allreduce_device(torch.zeros(5000, dtype=torch.float64, device='cuda'))
+    eng.close()
