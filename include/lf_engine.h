@@ -133,6 +133,12 @@ int lf_bin_weights(lf_ctx* ctx, int64_t n, const double* lum, const double* phi,
  * sumphi[j] = sum_i mult[i] * phi_i over bin j; counts[j] = sum_i mult[i]. */
 int lf_boot_bin(lf_ctx* ctx, const int32_t* mult, int64_t* counts, double* sumphi);
 
+/* The same with the resampling done on the device: replicate `replicate` draws n indices from a Philox4x32-10 stream
+ * keyed by `seed` (counter = draw index, replicate), accumulates the multiplicities with integer atomics and bins them.
+ * Statistically equivalent to VmaxLumFunc.py:352-359, not NumPy's MT19937 stream (use lf_boot_bin with host-drawn
+ * multiplicities for that).  Integer counts do not depend on the order of the atomics, so a replicate is reproducible. */
+int lf_boot_bin_device(lf_ctx* ctx, uint64_t seed, int64_t replicate, int64_t* counts, double* sumphi);
+
 /* Register-only FP64 FMA micro-benchmark on the context's device: sustained DFMA thread-instructions / s. */
 int lf_fp64_peak(lf_ctx* ctx, int32_t iters, double* dfma_per_s, double* ms);
 

@@ -97,7 +97,7 @@ def veff_weights_gpu(flux, lum, field_ind, Flim, alpha, fcmin, sum_omega, vol_in
 
 
 def getBootErrLog(L, phi, minz, maxz, nboot=100, nbin=25, Fmin=1.0e-20, Larr=None, correct_low=False, device=0,
-                  engine=None, return_counts=False):
+                  engine=None, return_counts=False, rng='host', seed=None):
     """Binned luminosity function dn/dlogL with bootstrap variances (reference VmaxLumFunc.py:304-364).
 
     Bin edges ``linspace(min(L)*1.001, max(L), nbin+1)`` unless ``Larr`` is given; bins are half-open
@@ -105,6 +105,10 @@ def getBootErrLog(L, phi, minz, maxz, nboot=100, nbin=25, Fmin=1.0e-20, Larr=Non
     reference does (:353), so a seeded run resamples the same sources.  The index draw happens on the host (it is
     the reference's RNG); the gather + binning of every replicate is one GPU pass over per-source multiplicities.
     ``correct_low`` (partial-bin correction, never enabled by the MCMC classes) is not supported.
+
+    ``rng='device'`` (additive option) resamples on the GPU instead: a Philox stream keyed by ``seed`` (default: one draw
+    from NumPy's global stream) generates every replicate's indices and multiplicities on the device -- statistically
+    equivalent variances, 100 replicates of 1e7 sources in a fraction of a second instead of half a minute of host RNG.
     """
     if correct_low:
         raise NotImplementedError("correct_low=True is outside the supported path (the MCMC classes never pass it)")
@@ -122,9 +126,16 @@ def getBootErrLog(L, phi, minz, maxz, nboot=100, nbin=25, Fmin=1.0e-20, Larr=Non
     lfbinorig = np.where(counts > 0, sums / dL, 0.0)
     lfbin = np.zeros((nboot, nb))
     n = len(phi)
+    if rng not in ('host', 'device'):
+        raise ValueError("rng must be 'host' or 'device'")
+    if rng == 'device' and seed is None:
+        seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
     for k in range(nboot):
-        boot = np.random.randint(n, size=n)
-        bc, bs = eng.boot_bin(np.bincount(boot, minlength=n))
+        if rng == 'device':
+            bc, bs = eng.boot_bin_device(seed, k)
+        else:
+            boot = np.random.randint(n, size=n)
+            bc, bs = eng.boot_bin(np.bincount(boot, minlength=n))
         lfbin[k] = np.where(bc > 0, bs / dL, 0.0)
     binavg = np.average(lfbin, axis=0)
     var = 1. / (nboot - 1) * np.sum((lfbin - binavg) ** 2, axis=0)

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get('LF_ENGINE_LIB', os.path.join(_HERE, 'csrc', 'liblfeng
 
 #: every symbol include/lf_engine.h declares (checked by tests/test_abi.py)
 EXPORTS = ['lf_ndim', 'lf_create', 'lf_destroy', 'lf_set_sources', 'lf_set_grid', 'lf_set_quadrature_share', 'lf_set_prior_gate', 'lf_set_compressed_sources',
-           'lf_lnprob_batch', 'lf_lnprob_batch_device', 'lf_last_call_info', 'lf_veff_bin', 'lf_bin_weights', 'lf_boot_bin',
+           'lf_lnprob_batch', 'lf_lnprob_batch_device', 'lf_last_call_info', 'lf_veff_bin', 'lf_bin_weights', 'lf_boot_bin', 'lf_boot_bin_device',
            'lf_fp64_peak', 'lf_mufu_peak', 'lf_last_kernel_ms', 'lf_sampler_run', 'lf_sampler_last_ms', 'lf_cosmo_distances', 'lf_interp_linear', 'lf_device_count', 'lf_peer_buffer_create', 'lf_peer_buffer_connect',
            'lf_allreduce_device', 'lf_peer_status', 'lf_last_error', 'lf_version']
 
@@ -69,6 +69,7 @@ def load():
                                 vp, vp, vp, C.c_int32, vp, vp, vp]
     lib.lf_bin_weights.argtypes = [vp, i64, vp, vp, vp, C.c_int32, vp, vp]
     lib.lf_boot_bin.argtypes = [vp, vp, vp, vp]
+    lib.lf_boot_bin_device.argtypes = [vp, C.c_uint64, i64, vp, vp]
     lib.lf_fp64_peak.argtypes = [vp, C.c_int32, dp, dp]
     lib.lf_mufu_peak.argtypes = [vp, C.c_int32, dp, dp]
     lib.lf_last_kernel_ms.argtypes = [vp, dp]

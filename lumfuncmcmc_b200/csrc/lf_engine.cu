@@ -2104,6 +2104,16 @@ __global__ void k_stretch_accept(SamplerArgs s, int h) {
 }
 __global__ void k_step_advance(long long* step) { *step += 1; }
 
+__global__ void k_boot_draw(long long n, uint32_t k0, uint32_t k1, uint32_t rep_lo, uint32_t rep_hi, int* __restrict__ mult) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // Philox call q yields draws 4q .. 4q+3
+    if (4 * q >= n) return;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), rep_lo, rep_hi, k0, k1, r);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (4 * q + t < n) atomicAdd(&mult[(long long)(((unsigned long long)r[t] * (unsigned long long)n) >> 32)], 1);
+}
+
 extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t nsteps, uint64_t seed, double a, int64_t step0,
                               double* chain, double* lnprob, int64_t* naccepted, double* pos_out, double* lnprob_out) {
     if (!c || !pos0) return fail("lf_sampler_run: null argument");
@@ -2353,6 +2363,39 @@ extern "C" int lf_bin_weights(lf_ctx* c, int64_t n, const double* lum, const dou
     CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (cudaEventQuery(c->ev1) == cudaSuccess) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
+    return 0;
+}
+
+// multiplicities of one bootstrap replicate: n uniform draws with replacement, 4 per Philox call
+__global__ void k_boot_draw(long long n, uint32_t k0, uint32_t k1, uint32_t rep_lo, uint32_t rep_hi, int* __restrict__ mult);
+
+extern "C" int lf_boot_bin_device(lf_ctx* c, uint64_t seed, int64_t replicate, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_boot_bin_device: null context");
+    if (!c->v_phi || c->vN <= 0) return fail("lf_boot_bin_device: call lf_veff_bin or lf_bin_weights first");
+    if (!counts || !sumphi) return fail("lf_boot_bin_device: bad arguments");
+    if (c->vN >= (1LL << 32)) return fail("lf_boot_bin_device: more than 2^32 sources");
+    CK(cudaSetDevice(c->device));
+    if (!c->v_mult) CK(cudaMalloc(&c->v_mult, sizeof(int) * (size_t)c->vN));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(c->v_mult, 0, sizeof(int) * (size_t)c->vN, c->stream));
+    const long long calls = (c->vN + 3) / 4;
+    k_boot_draw<<<(unsigned)((calls + 255) / 256), 256, 0, c->stream>>>(c->vN, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                                      (uint32_t)replicate, (uint32_t)((uint64_t)replicate >> 32), c->v_mult);
+    VeffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
+    a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult; a.bin = c->v_bin;
+    const int nbins = c->v_nbins, blocks = c->v_blocks;
+    const VeffPlan plan = veff_plan(c, c->vN, nbins);
+    veff_launch<1>(plan, a, c->stream);
+    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
     return 0;
 }
 

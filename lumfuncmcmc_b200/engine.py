@@ -71,6 +71,14 @@ class _VeffOps:
         _lib.check(self.lib.lf_boot_bin(self._ctx, _ptr(mult), _ptr(counts), _ptr(sums)), self.lib)
         return counts, sums
 
+    def boot_bin_device(self, seed, replicate):
+        """One bootstrap replicate resampled ON the device (Philox stream keyed by ``seed``; counter = draw, replicate)."""
+        nb = self._nbins_resident()
+        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
+        _lib.check(self.lib.lf_boot_bin_device(self._ctx, C.c_uint64(int(seed) & (2 ** 64 - 1)), int(replicate),
+                                               _ptr(counts), _ptr(sums)), self.lib)
+        return counts, sums
+
     def _nbins_resident(self):
         return getattr(self, '_veff_nbins', 0)
 

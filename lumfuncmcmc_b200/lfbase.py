@@ -268,7 +268,7 @@ class LFBase:
                                                sum_Omega, vol_int, edges, vol_per_source=vol, valid=valid)
         self.Lavg, self.lfbinorig, self.var, self.bincounts = V.getBootErrLog(
             self.lum, self.phifunc, self.zmin, self.zmax, self.nboot, self.nbins, Fmin=1.0e-17 * np.max(self.Flim),
-            engine=eng, return_counts=True)
+            engine=eng, return_counts=True, rng=getattr(self, 'boot_rng', None) or os.environ.get('LF_BOOT_RNG', 'host'))
 
     def _veff_engine(self):
         if self._engines:

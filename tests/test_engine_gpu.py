@@ -346,3 +346,39 @@ def test_peer_memory_allreduce_degenerates_to_identity_on_one_rank(golden):
     with pytest.raises(Exception):
         eng.allreduce_device(torch.zeros(5000, dtype=torch.float64, device='cuda'))
     eng.close()
+
+
+def test_device_resampled_bootstrap_equals_host_replay_of_the_philox_stream():
+    """rng='device': every replicate's multiplicities come from a Philox stream on the GPU; a host replay of the same
+    stream gives the same integer counts, sums agree to 1e-12, and the variances are statistically those of the
+    reference's host-RNG bootstrap."""
+    from lumfuncmcmc_b200 import VmaxLumFunc as V
+    from lumfuncmcmc_b200.engine import VeffEngine
+    from lumfuncmcmc_b200.sampler import philox4x32_10
+    rng = np.random.default_rng(12)
+    n, nb, seed = 200003, 30, 0xfeedbeef12345678
+    lum = rng.uniform(41.0, 43.5, n)
+    phi = 10 ** rng.uniform(-7, -5, n)
+    edges = np.linspace(lum.min() * 1.001, lum.max(), nb + 1)
+    eng = VeffEngine()
+    counts0, sums0 = eng.bin_weights(lum, phi, edges)
+    j = np.searchsorted(edges, lum, side='right') - 1
+    ok = (lum >= edges[0]) & (lum < edges[-1])
+    for rep in (0, 7):
+        bc, bs = eng.boot_bin_device(seed, rep)
+        q = np.arange((n + 3) // 4, dtype=np.uint64)
+        r = philox4x32_10(q & np.uint64(0xFFFFFFFF), q >> np.uint64(32), np.full(len(q), rep), np.zeros(len(q)), seed & 0xFFFFFFFF, seed >> 32)
+        draws = np.stack(r, axis=1).ravel()[:n].astype(np.uint64)
+        mult = np.bincount(((draws * np.uint64(n)) >> np.uint64(32)).astype(np.int64), minlength=n)
+        assert mult.sum() == n
+        assert np.array_equal(bc, np.bincount(j[ok], weights=mult[ok], minlength=nb)[:nb].astype(np.int64))
+        np.testing.assert_allclose(bs, np.bincount(j[ok], weights=(phi * mult)[ok], minlength=nb)[:nb], rtol=1e-12)
+        bc2, _ = eng.boot_bin_device(seed, rep)
+        assert np.array_equal(bc, bc2)                                   # reproducible
+    np.random.seed(3)
+    _, lf_h, var_h = V.getBootErrLog(lum, phi, 1.2, 1.9, nboot=200, nbin=nb, Larr=edges, engine=eng)
+    _, lf_d, var_d = V.getBootErrLog(lum, phi, 1.2, 1.9, nboot=200, nbin=nb, Larr=edges, engine=eng, rng='device', seed=seed)
+    assert np.array_equal(lf_h, lf_d)
+    # two independent 200-replicate variance estimates: each bin within a factor 2, the average over bins within 10 %
+    assert np.all(np.abs(np.log(var_d / var_h)) < np.log(2.0)) and abs(np.mean(var_d / var_h) - 1.0) < 0.1
+    eng.close()
