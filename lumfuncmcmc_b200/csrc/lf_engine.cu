@@ -15,172 +15,22 @@
 // underflow or leave the validated argument ranges.  Every other walker is evaluated by the "literal" kernels,
 // which follow the reference's order of operations with IEEE/libdevice arithmetic so that -inf / denormal
 // behaviour is reproduced, not imitated (lumfuncmcmc.py:370).
-#include "../../include/lf_engine.h"
-#include "lf_math.cuh"
-
-#include <cuda_runtime.h>
-#include <math.h>
-#include <stdint.h>
-#include <stdio.h>
-#include <string.h>
-
-#include <algorithm>
-#include <string>
-#include <vector>
-
-using namespace lfm;
+#include "lf_internal.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static int fail(const std::string& msg) {
+int fail(const std::string& msg) {
     g_err = msg;
     return 1;
 }
-#define CK(call)                                                                                    \
-    do {                                                                                            \
-        cudaError_t e_ = (call);                                                                    \
-        if (e_ != cudaSuccess)                                                                      \
-            return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + \
-                        std::to_string(__LINE__) + ")");                                            \
-    } while (0)
 
 extern "C" const char* lf_last_error(void) { return g_err.c_str(); }
-extern "C" const char* lf_version(void) { return "lfengine 0.1 (sm_100a)"; }
+extern "C" const char* lf_version(void) { return "lfengine 0.2 (sm_100a)"; }
 extern "C" int lf_device_count(void) {
     int n = 0;
     return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// device-side data layout
-// ------------------------------------------------------------------------------------------------
-// walker-parameter slots: wp[slot * Wcap + w]
-enum {
-    P_ALPHA = 0,   // completeness slope alpha_c
-    P_TENML = 1,   // 10^-L*
-    P_C0 = 2,      // ln ln10 + phi* ln10 - L* c1
-    P_C1 = 3,      // (alpha_s + 1) ln10
-    P_LSTAR = 4,
-    P_PHISTAR = 5,
-    P_SCHAL = 6,
-    P_LNPART0 = 7,  // source-sum part that collapses to sufficient statistics (fast class)
-    // z model: quadratic coefficients
-    P_AL = 8, P_BL = 9, P_CL = 10, P_AP = 11, P_BP = 12, P_CP = 13,
-    P_FIELD0 = 16,  // + 4*k + {0: aF = -alpha log10 F50, 1: c2 = -log2(e)/ftau, 2: F50 (cgs), 3: ftau}
-    P_NSLOTS = P_FIELD0 + 4 * LF_MAX_FIELDS
-};
-
-enum { CLS_NONE = 0, CLS_FAST = 1, CLS_LIT = 2 };
-
-struct FieldStats {          // per-field sufficient statistics and ranges of the resident sources
-    double n, sum_lum, sum_L, sum_lnom, sum_z, sum_z2;
-    double lum_min, lum_max, g_min, f_min, lnom_min, z_min, z_max;
-    double grid_g_min, grid_f_min;     // same ranges over the field's quadrature points (FREE)
-    double ln_om0;                      // ln(int(Omega_0)/sqarcsec)                        (FREE)
-    double om0_over_sq;                 // int(Omega_0)/sqarcsec                            (FREE)
-};
-
-// 16-byte aligned so a point is fetched with LDG.128s
-struct __align__(16) QuadPointFree { double g, f, x, Lx, wt, ftrue; };   // log10 flux, flux, logL, 10^logL, trapezoid*volume*area weight
-struct __align__(16) QuadPoint { double x, Lx, wt, pad; };             // FIXED / Z (weight carries integ_part)
-
-struct KArgs {
-    int model, K, S, fix_sch_al, fixed_prior_ok, force_literal, modified, prior_gate;
-    int ndim;
-    double fcmin, fcA2;                // fcA2 = |a/(1-a)|, a = (2 fcmin - 1)^2        (VmaxLumFunc.py:164-165)
-    double sch_al;
-    double Lstar_lims[2], phistar_lims[2], sch_al_lims[2], Flim_lims[2], alpha_lims[2];
-    double z1, z2, z3;
-    long long field_ind[LF_MAX_FIELDS + 1];
-    FieldStats fs[LF_MAX_FIELDS];
-    double lum_max_all;
-    double fcap;                       // cap of the flux copy used in the decay argument (see k_derive_free)
-    // resident arrays
-    const double2* src2;               // FREE: (log10 flux, flux)   Z: (lum, z)
-    const double2* csrc;               // compressed catalogue, two entries per pseudo-source: (xi = log10 f, min(10^xi, fcap)), (weight, -); or NULL
-    long long M; long long cfield_ind[LF_MAX_FIELDS + 1];
-    const float2* src2f;               // LF_PREC_F32 copy: FREE (log10 f + 17, f * 1e17)   Z: (lum - 42, z - z2)
-    int precision;                     // LF_PREC_F64 | LF_PREC_F32 (arithmetic of the walker x source loop only)
-    const double* lum;
-    const double* flux;
-    const double* z;
-    const double* om_arr;
-    const double* zarr;                // Z: quadrature redshifts (column i <-> zarr[i])
-    const QuadPointFree* qpf;
-    const QuadPoint* qp;
-    long long N, NQ;                   // sources, quadrature points (K*S*S)
-    // per-call
-    const double* thetas;
-    double* out;
-    long long W, Wcap;
-    double* wp;
-    double* colA;                      // Z: per (column, walker) ln-amplitude  [K? no: S][Wcap]
-    double* colB;                      // Z: per (column, walker) 10^-L*(z_col)
-    int* cls_count;                    // [0..2] walkers per class, [3] / [4] work-item counters of k_main<fast/literal>,
-                                       // [5] / [6] walkers per class in the quadrature lists
-    int* list_fast;
-    int* list_lit;
-    int* list_fastq;                   // walkers of each class whose quadrature THIS rank integrates (w % nshare == share)
-    int* list_litq;
-    double* partial;                   // [rows][Wcap]
-    int n_src_slabs, n_quad_slabs;
-    int share, nshare;
-    const Tables* tables;
-};
-
-// ------------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double neg_inf() { return __longlong_as_double(0xfff0000000000000LL); }
-
-__device__ __forceinline__ bool in_box(double v, const double* lims) { return (v >= lims[0]) && (v <= lims[1]); }
-__device__ __forceinline__ bool in_box_strict(double v, const double* lims) { return (v > lims[0]) && (v < lims[1]); }
-
-// literal modified-Fleming value, reference operation order (VmaxLumFunc.py:118-126, 141, 164-167)
-__device__ __forceinline__ double fleming_literal(double f, double F50, double alpha, double ftau, bool modified) {
-    double num = alpha * log10(f / F50);
-    double den = sqrt(1.0 + num * num);
-    double fc = 0.5 * (1.0 + num / den);
-    if (!modified) return fc;
-    double dec = 1.0 - exp(-f / ftau);
-    return pow(fc, 1.0 / dec);
-}
-
-// literal Schechter value (lumfuncmcmc.py:44)
-__device__ __forceinline__ double schechter_literal(double logL, double sch_al, double Lstar, double phistar) {
-    double dex = logL - Lstar;
-    return LN10 * pow(10.0, phistar) * pow(10.0, dex * (sch_al + 1.0)) * exp(-pow(10.0, dex));
-}
-
-// getQuadCoef, reference operation order (lumfuncmcmc_z.py:40-42)
-__device__ __forceinline__ void quad_coef(double y1, double y2, double y3, double z1, double z2, double z3,
-                                          double& a, double& b, double& c) {
-    a = ((y3 - y1) + (y2 - y1) * (z1 - z3) / (z2 - z1)) /
-        (z3 * z3 - z1 * z1 + (z2 * z2 - z1 * z1) * (z1 - z3) / (z2 - z1));
-    b = (y2 - y1 - a * (z2 * z2 - z1 * z1)) / (z2 - z1);
-    c = y1 - a * z1 * z1 - b * z1;
-}
-
-// ---- FP32 mode of the walker x source loop: MUFU (SFU) transcendentals, FP32 FMA pipe, chunked accumulation ----
-__device__ __forceinline__ float mufu_rsq(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float mufu_lg2(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float mufu_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float mufu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-
-// log2 of the modified Fleming completeness: 8 FP32-pipe instructions + 4 MUFU per (walker, source) term.
-//   gs = log10 f + 17, fs = f * 1e17, aFs = -alpha * log10(F50 * 1e17), c2 = -log2(e) / (ftau * 1e17)
-template <bool MODIFIED>
-__device__ __forceinline__ float fleming_log2_f32(float gs, float fs, float alpha, float aFs, float c2) {
-    float n = fmaf(alpha, gs, aFs);
-    float y = fmaf(n, n, 1.0f);
-    float q = n * mufu_rsq(y);
-    float fc = fmaf(0.5f, q, 0.5f);
-    float l2 = mufu_lg2(fc);
-    if (!MODIFIED) return l2;
-    float dec = 1.0f - mufu_ex2(fs * c2);
-    return l2 * mufu_rcp(dec);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -890,247 +740,6 @@ __global__ void k_take(long long n, const double2* __restrict__ s, int comp, dou
 }
 
 // ------------------------------------------------------------------------------------------------
-// 1/V_eff weights + binned luminosity function  (HBM-bound streaming pass)
-// ------------------------------------------------------------------------------------------------
-#define VEFF_MAX_BINS 1024
-struct VeffArgs {
-    long long n;
-    const double* flux; const double* lum; const double* vol; const unsigned char* valid;
-    double* phi;
-    int K; long long field_ind[LF_MAX_FIELDS + 1]; double F50[LF_MAX_FIELDS]; double ftau[LF_MAX_FIELDS];
-    double invF50[LF_MAX_FIELDS]; double inv_ftau[LF_MAX_FIELDS];
-    double alpha, pref, vol_int, inv_pref_vol; int modified;
-    const Tables* tables;
-    const double* edges; int nbins;
-    unsigned long long* counts; double* sumphi;     // [gridDim.x][nbins] block partials
-    const int* mult;                                 // bootstrap multiplicities (NULL: original sample)
-    short* bin;                                      // per-source bin index (-1: none), written by MODE 0/2, read by MODE 1
-};
-
-__device__ __forceinline__ int bin_of(double L, const double* e, int nb) {
-    // half-open bins [e_j, e_{j+1}), exact comparisons against the caller's edges (VmaxLumFunc.py:346-348)
-    if (!(L >= e[0]) || !(L < e[nb])) return -1;
-    int j = (int)((L - e[0]) / (e[nb] - e[0]) * nb);
-    j = j < 0 ? 0 : (j > nb - 1 ? nb - 1 : j);
-    while (j > 0 && L < e[j]) --j;
-    while (j < nb - 1 && L >= e[j + 1]) ++j;
-    return j;
-}
-
-// same search on an edge table replicated x16 in shared memory (e[j * 16 + col]: a half-warp never bank-conflicts),
-// candidate bin from a precomputed scale instead of a division; the comparisons against the caller's exact edges decide
-__device__ __forceinline__ int bin_of_rep(double L, const double* e, int col, int nb, double e0, double enb, double scale) {
-    if (!(L >= e0) || !(L < enb)) return -1;
-    int j = (int)((L - e0) * scale);
-    j = j < 0 ? 0 : (j > nb - 1 ? nb - 1 : j);
-    while (j > 0 && L < e[j * 16 + col]) --j;
-    while (j < nb - 1 && L >= e[(j + 1) * 16 + col]) ++j;
-    return j;
-}
-
-// MODE 0: compute phi from the completeness and bin; MODE 1: bootstrap replicate (multiplicities) on resident
-// lum/phi; MODE 2: bin caller-provided (resident) phi
-template <int MODE>
-__global__ void __launch_bounds__(256) k_veff(VeffArgs a) {
-    constexpr bool BOOT = MODE == 1;
-    extern __shared__ unsigned char smem_raw[];
-    double* s_edges = reinterpret_cast<double*>(smem_raw);                 // nbins+1
-    double* s_sum = s_edges + (a.nbins + 1);                               // 8 warps x nbins
-    unsigned long long* s_cnt = reinterpret_cast<unsigned long long*>(s_sum + 8 * a.nbins);
-    const int warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i <= a.nbins; i += blockDim.x) s_edges[i] = a.edges[i];
-    for (int i = threadIdx.x; i < 8 * a.nbins; i += blockDim.x) { s_sum[i] = 0.0; s_cnt[i] = 0ULL; }
-    __syncthreads();
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
-        double phi;
-        unsigned long long m = 1ULL;
-        if (BOOT) {
-            m = (unsigned long long)a.mult[i];
-            if (m == 0ULL) continue;
-            phi = a.phi[i];
-        } else if (MODE == 2) {
-            phi = a.phi[i];
-        } else {
-            int k = 0;
-            while (k + 1 < a.K && i >= a.field_ind[k + 1]) ++k;
-            double comp = fleming_literal(a.flux[i], a.F50[k], a.alpha, a.ftau[k], a.modified != 0);
-            double vol = a.vol ? a.vol[i] : a.vol_int;
-            bool ok = a.valid ? (a.valid[i] != 0) : true;
-            phi = ok ? 1.0 / (a.pref * comp * vol) : 0.0;       // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
-            a.phi[i] = phi;
-        }
-        int j = bin_of(a.lum[i], s_edges, a.nbins);
-        if (j >= 0) {
-            atomicAdd(&s_sum[warp * a.nbins + j], BOOT ? phi * (double)m : phi);
-            atomicAdd(&s_cnt[warp * a.nbins + j], m);
-        }
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < a.nbins; j += blockDim.x) {
-        double s = 0.0; unsigned long long c = 0ULL;
-        for (int wv = 0; wv < 8; ++wv) { s += s_sum[wv * a.nbins + j]; c += s_cnt[wv * a.nbins + j]; }
-        a.sumphi[(long long)blockIdx.x * a.nbins + j] = s;
-        a.counts[(long long)blockIdx.x * a.nbins + j] = c;
-    }
-}
-
-// ---- streaming version with private histogram columns (no atomics, deterministic) ----
-// Each warp owns VP_COLS = 16 columns per bin of the block's shared-memory histogram, s_sum[warp][bin][col] (f64) and
-// s_cnt[warp][bin][col] (u32); lanes l and l + 16 share column l and update it in two turns separated by __syncwarp,
-// so an update is a plain read-modify-write of a word nobody else touches in that turn (no atomics, no races, one
-// bank per column).  At the end each warp folds its columns with a fixed shuffle tree and the block adds the warps
-// in order: the result does not depend on scheduling.  Shared memory: 8 warps x nbins x 16 x 12 B (76.8 KB at the
-// reference's nbins = 50 -> two blocks = 16 warps per SM); larger histograms fall back to k_veff (atomics).
-// The per-source completeness is evaluated as exp(-ln(fc)/dec) with the ~2e-16 routines of lf_math.cuh (two 2-4 KB
-// tables) instead of libdevice pow/log10/exp/sqrt and five IEEE divisions: ~75 FP64-pipe instructions per source, so
-// the pass stays close to its HBM time (24 B per source).
-#define VP_WARPS 8
-#define VP_COLS 16
-#define VP_UNROLL 4
-static const size_t VP_SMEM_MAX = 200 * 1024;
-
-__device__ __noinline__ double inv_fleming_literal(double f, double F50, double alpha, double ftau, bool modified) {
-    return 1.0 / fleming_literal(f, F50, alpha, ftau, modified);
-}
-
-// 1 / fleming(f): VmaxLumFunc.py:118-126, 141.  Sources outside the range where the fast evaluation is accurate to
-// ~1e-15 (fc < 1e-6, decay argument < 1e-6, |ln comp| > 690) take the literal libdevice route.
-__device__ __forceinline__ double inv_fleming_stream(double f, double F50, double invF50, double alpha_log10e, double alpha,
-                                                     double ftau, double inv_ftau, bool modified, const double* s_exp,
-                                                     const double2* s_logm) {
-    const double num = alpha_log10e * log_stream(f * invF50, s_logm);       // alpha * log10(f / F50)
-    const double y = fma(num, num, 1.0);
-    double r0 = rsqrt_seed(y);
-    const double e = fma(-(y * r0), r0, 1.0);
-    const double pe = fma(0.375, e, 0.5) * e;
-    const double nr = num * r0;
-    const double fc = fma(0.5, fma(nr, pe, nr), 0.5);
-    const double x = f * inv_ftau;
-    double t = -log_stream(fc > 1.0e-300 ? fc : 1.0e-300, s_logm);
-    if (modified) t *= rcp_stream(1.0 - exp_stream(x < 690.0 ? -x : -690.0, s_exp));
-    if (!(fc > 1.0e-6) || (modified && !(x > 1.0e-6)) || !(t < 690.0)) return inv_fleming_literal(f, F50, alpha, ftau, modified);
-    return exp_stream(t, s_exp);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(32 * VP_WARPS) k_veff_priv(VeffArgs a) {
-    constexpr bool BOOT = MODE == 1;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nb = a.nbins;
-    double* s_edges = reinterpret_cast<double*>(smem_raw);                  // [nbins + 1][16] replicated
-    double* s_sum = s_edges + (nb + 1) * 16;                                // [VP_WARPS][nbins][VP_COLS]
-    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + VP_WARPS * nb * VP_COLS);
-    double2* s_logm = reinterpret_cast<double2*>(s_cnt + VP_WARPS * nb * VP_COLS);   // MODE 0 only
-    double* s_exp = reinterpret_cast<double*>(s_logm + STREAM_LOG_N);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < (nb + 1) * 16; i += blockDim.x) s_edges[i] = a.edges[i >> 4];
-    for (int i = threadIdx.x; i < VP_WARPS * nb * VP_COLS; i += blockDim.x) { s_sum[i] = 0.0; s_cnt[i] = 0u; }
-    if (MODE == 0) load_stream_tables(a.tables, s_exp, s_logm);
-    const double e0 = a.edges[0], enb = a.edges[nb], scale = (double)nb / (enb - e0);
-    __syncthreads();
-    double* my_sum = s_sum + warp * nb * VP_COLS + (lane & (VP_COLS - 1));
-    unsigned* my_cnt = s_cnt + warp * nb * VP_COLS + (lane & (VP_COLS - 1));
-    const int turn = lane >> 4;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const double alpha_log10e = a.alpha * KS[12];
-    int k = 0;                                  // sources are field-sorted: the field index only moves forward
-    // whole warps iterate together (the trip count is computed from the warp's first lane) so that __syncwarp is legal
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < a.n; i0 += stride * VP_UNROLL) {
-        const long long i = i0 + lane;
-        double lum[VP_UNROLL], phi[VP_UNROLL], flux[VP_UNROLL], vol[VP_UNROLL];
-        unsigned m[VP_UNROLL];
-        int jb[VP_UNROLL];
-        bool ok[VP_UNROLL];
-#pragma unroll
-        for (int u = 0; u < VP_UNROLL; ++u) {                                // all loads of the trip first
-            const long long ii = i + u * stride;
-            const bool in = ii < a.n;
-            m[u] = in ? 1u : 0u;
-            ok[u] = in;
-            phi[u] = 0.0;
-            if (BOOT) {                                                      // replicate: resident bin index, weight, multiplicity
-                jb[u] = in ? (int)__ldcs(a.bin + ii) : -1;
-                m[u] = in ? (unsigned)__ldcs(a.mult + ii) : 0u;
-                phi[u] = in ? __ldcs(a.phi + ii) : 0.0;
-                continue;
-            }
-            lum[u] = in ? __ldcs(a.lum + ii) : -1.0e300;                     // below every edge: lands in no bin
-            if (MODE == 2) {
-                phi[u] = in ? __ldcs(a.phi + ii) : 0.0;
-            } else {
-                flux[u] = in ? __ldcs(a.flux + ii) : 1.0;
-                vol[u] = (in && a.vol) ? __ldcs(a.vol + ii) : a.vol_int;
-                if (in && a.valid) ok[u] = a.valid[ii] != 0;
-            }
-        }
-        if (MODE == 0) {
-#pragma unroll
-            for (int u = 0; u < VP_UNROLL; ++u) {
-                const long long ii = i + u * stride;
-                while (k + 1 < a.K && ii >= a.field_ind[k + 1]) ++k;
-                const double icomp = inv_fleming_stream(flux[u], a.F50[k], a.invF50[k], alpha_log10e, a.alpha, a.ftau[k],
-                                                        a.inv_ftau[k], a.modified != 0, s_exp, s_logm);
-                const double ipv = a.vol ? 1.0 / (a.pref * vol[u]) : a.inv_pref_vol;
-                phi[u] = ok[u] ? icomp * ipv : 0.0;                          // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
-                if (ii < a.n) __stcs(a.phi + ii, phi[u]);
-            }
-        }
-        if (!BOOT) {
-#pragma unroll
-            for (int u = 0; u < VP_UNROLL; ++u) {
-                const long long ii = i + u * stride;
-                jb[u] = bin_of_rep(lum[u], s_edges, lane & 15, nb, e0, enb, scale);
-                if (ii < a.n) a.bin[ii] = (short)jb[u];                      // kept resident for the bootstrap replicates
-            }
-        }
-#pragma unroll
-        for (int tn = 0; tn < 2; ++tn) {
-            if (turn == tn) {
-#pragma unroll
-                for (int u = 0; u < VP_UNROLL; ++u)
-                    if (jb[u] >= 0 && m[u] != 0u) {
-                        my_sum[jb[u] * VP_COLS] += BOOT ? phi[u] * (double)m[u] : phi[u];
-                        my_cnt[jb[u] * VP_COLS] += m[u];
-                    }
-            }
-            __syncwarp();
-        }
-    }
-    __syncthreads();
-    // fold: warp w handles bins w, w + VP_WARPS, ...; lane l reads column l % 16 of warp-slices l / 16, l / 16 + 2, ...
-    for (int jb = warp; jb < nb; jb += VP_WARPS) {
-        double s = 0.0;
-        unsigned long long c = 0ULL;
-        for (int wv = lane >> 4; wv < VP_WARPS; wv += 2) {
-            s += s_sum[(wv * nb + jb) * VP_COLS + (lane & (VP_COLS - 1))];
-            c += s_cnt[(wv * nb + jb) * VP_COLS + (lane & (VP_COLS - 1))];
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-            s += __shfl_xor_sync(0xffffffffu, s, o);
-            c += __shfl_xor_sync(0xffffffffu, c, o);
-        }
-        if (lane == 0) {
-            a.sumphi[(long long)blockIdx.x * nb + jb] = s;
-            a.counts[(long long)blockIdx.x * nb + jb] = c;
-        }
-    }
-}
-
-// one warp per bin: lanes stride over the block partials, fixed shuffle tree (deterministic)
-__global__ void k_veff_reduce(int nblocks, int nbins, const unsigned long long* __restrict__ counts,
-                              const double* __restrict__ sumphi, long long* __restrict__ out_c, double* __restrict__ out_s) {
-    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (j >= nbins) return;
-    double s = 0.0; unsigned long long c = 0ULL;
-    for (int b = lane; b < nblocks; b += 32) { s += sumphi[(long long)b * nbins + j]; c += counts[(long long)b * nbins + j]; }
-    for (int o = 16; o > 0; o >>= 1) {
-        s += __shfl_xor_sync(0xffffffffu, s, o);
-        c += __shfl_xor_sync(0xffffffffu, c, o);
-    }
-    if (lane == 0) { out_c[j] = (long long)c; out_s[j] = s; }
-}
-
-// ------------------------------------------------------------------------------------------------
 // FP64 pipe micro-benchmark: 8 independent FMA chains per thread, registers only
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double* sink) {
@@ -1167,52 +776,6 @@ __global__ void __launch_bounds__(256) k_mufu_peak(int iters, float seed, float*
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
-// peer-memory exchange (definitions used by lf_ctx; kernels further down)
-#define PEER_MAX 16
-#define PEER_CHUNK 256                 // walkers per block = per flag
-struct PeerArgs {
-    int rank, world;
-    long long wcap;                    // capacity of one slot (doubles)
-    int nchunk_cap;
-    double* data[PEER_MAX];            // rank r's receive buffer: data[r][parity][sender][wcap]
-    unsigned* flags[PEER_MAX];         // flags[r][parity][sender][nchunk_cap]
-    const unsigned* seq;               // device counter of this rank: sequence number of the current exchange (starts at 1)
-    int* timed_out;
-};
-
-struct lf_ctx {
-    lf_config cfg;
-    int device = 0, sm_count = 148;
-    int occ_fast = 2, occ_lit = 2;     // resident blocks per SM of the persistent main kernels
-    int ndim = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    KArgs ka;
-    // resident
-    long long N = 0, NQ = 0;
-    double* d_lum = nullptr; double* d_flux = nullptr; double* d_z = nullptr; double* d_om = nullptr;
-    double* d_Lsrc = nullptr; double2* d_src2 = nullptr; float2* d_src2f = nullptr; double2* d_csrc = nullptr;
-    QuadPointFree* d_qpf = nullptr; QuadPoint* d_qp = nullptr; double* d_zarr = nullptr;
-    Tables* d_tables = nullptr;
-    bool have_sources = false, have_grid = false;
-    // per-call scratch (grown on demand)
-    long long Wcap = 0; int rows_cap = 0;
-    double* d_wp = nullptr; double* d_colA = nullptr; double* d_colB = nullptr; double* d_partial = nullptr;
-    int* d_cls = nullptr; int* d_list_fast = nullptr; int* d_list_lit = nullptr; int* d_list_fastq = nullptr; int* d_list_litq = nullptr;
-    double* d_thetas = nullptr; double* d_out = nullptr;
-    double* h_thetas = nullptr; double* h_out = nullptr;           // pinned staging
-    long long launches = 0; double last_ms = 0.0, sampler_ms = 0.0;
-    int h_cls[3] = {0, 0, 0};
-    // Veff residency
-    long long vN = 0; double* v_lum = nullptr; double* v_phi = nullptr; double* v_edges = nullptr; int v_nbins = 0;
-    unsigned long long* v_counts = nullptr; double* v_sums = nullptr; long long* v_outc = nullptr; double* v_outs = nullptr;
-    int* v_mult = nullptr; short* v_bin = nullptr; int v_blocks = 0;
-    // peer exchange
-    unsigned char* peer_base = nullptr; unsigned* peer_seq = nullptr; int* peer_timeout = nullptr; int* peer_timeout_h = nullptr;
-    size_t peer_data_bytes = 0; bool peer_connected = false; void* peer_opened[PEER_MAX] = {};
-    PeerArgs peer;
-};
-
 static int ndim_of(const lf_config& c) {
     int free_al = c.fix_sch_al ? 0 : 1;
     if (c.model == LF_MODEL_FREE) return 2 + free_al + c.nfields + 1;
@@ -1266,15 +829,7 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     CK(cudaFuncSetAttribute(k_main<false, LF_MODEL_FREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem_bytes(LF_MODEL_FREE)));
     CK(cudaFuncSetAttribute(k_main<false, LF_MODEL_FIXED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem_bytes(LF_MODEL_FIXED)));
     CK(cudaFuncSetAttribute(k_main<false, LF_MODEL_Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)main_smem_bytes(LF_MODEL_Z)));
-    {
-        const int atom_smem = (int)(sizeof(double) * (VEFF_MAX_BINS + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * VEFF_MAX_BINS);
-        CK(cudaFuncSetAttribute(k_veff<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, atom_smem));
-        CK(cudaFuncSetAttribute(k_veff<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, atom_smem));
-        CK(cudaFuncSetAttribute(k_veff<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, atom_smem));
-    }
-    CK(cudaFuncSetAttribute(k_veff_priv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
-    CK(cudaFuncSetAttribute(k_veff_priv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
-    CK(cudaFuncSetAttribute(k_veff_priv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
+    if (veff_init(c)) return 1;
     if (cfg->model == LF_MODEL_FREE) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_fast, k_main<false, LF_MODEL_FREE>, 32 * main_warps(LF_MODEL_FREE), main_smem_bytes(LF_MODEL_FREE)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&c->occ_lit, k_main<true, LF_MODEL_FREE>, 32 * main_warps(LF_MODEL_FREE), 0));
@@ -1310,22 +865,6 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     return 0;
 }
 
-struct DevBufs {                       // frees whatever was allocated when it goes out of scope
-    std::vector<void*> p;
-    ~DevBufs() { for (void* q : p) cudaFree(q); }
-    template <typename T> cudaError_t alloc(T** out, size_t bytes) {
-        cudaError_t e = cudaMalloc(out, bytes ? bytes : 8);
-        if (e == cudaSuccess) p.push_back(*out);
-        return e;
-    }
-};
-
-template <typename T>
-static void dfree(T*& p) {
-    if (p) cudaFree(p);
-    p = nullptr;
-}
-
 extern "C" void lf_destroy(lf_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
@@ -1335,9 +874,7 @@ extern "C" void lf_destroy(lf_ctx* c) {
     dfree(c->d_cls); dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_list_fastq); dfree(c->d_list_litq); dfree(c->d_thetas); dfree(c->d_out);
     dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
     dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
-    for (int r = 0; r < PEER_MAX; ++r) if (c->peer_opened[r]) cudaIpcCloseMemHandle(c->peer_opened[r]);
-    dfree(c->peer_base); dfree(c->peer_seq);
-    if (c->peer_timeout_h) cudaFreeHost(c->peer_timeout_h);
+    peer_release(c);
     if (c->h_thetas) cudaFreeHost(c->h_thetas);
     if (c->h_out) cudaFreeHost(c->h_out);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -1658,7 +1195,7 @@ static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
     n_quad = (int)rq;
 }
 
-static int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_out, cudaStream_t st) {
+int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_out, cudaStream_t st) {
     if (!c->have_sources || !c->have_grid) return fail("lf_lnprob: call lf_set_sources and lf_set_grid first");
     if (W <= 0) return 0;
     int n_src, n_quad;
@@ -1789,638 +1326,3 @@ extern "C" int lf_mufu_peak(lf_ctx* c, int32_t iters, double* mufu_per_s, double
     return 0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// peer-memory all-reduce of the per-walker partials (one process per GPU, NVLink / NVSwitch)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__global__ void __launch_bounds__(PEER_CHUNK) k_allreduce_p2p(PeerArgs a, double* __restrict__ vec, long long W) {
-    const unsigned seq = *a.seq;
-    const int par = (int)(seq & 1u);
-    const int chunk = blockIdx.x;
-    const long long w = (long long)chunk * PEER_CHUNK + threadIdx.x;
-    const size_t slot = ((size_t)par * a.world + a.rank) * (size_t)a.wcap;
-    // 1. push my values into my slot of every rank's buffer (coalesced 8-byte stores over NVLink; own buffer included)
-    if (w < W) {
-        const double v = vec[w];
-        for (int r = 0; r < a.world; ++r) a.data[r][slot + w] = v;
-    }
-    __threadfence_system();
-    __syncthreads();
-    // 2. raise my flag for this chunk on every rank
-    if (threadIdx.x < a.world)
-        st_release_sys(a.flags[threadIdx.x] + ((size_t)par * a.world + a.rank) * a.nchunk_cap + chunk, seq);
-    // 3. wait for every sender's flag on my own buffer (bounded spin: a dead peer must not hang the GPU)
-    if (threadIdx.x < a.world) {
-        const unsigned* f = a.flags[a.rank] + ((size_t)par * a.world + threadIdx.x) * a.nchunk_cap + chunk;
-        const long long t0 = clock64();
-        while ((int)(ld_acquire_sys(f) - seq) < 0) {
-            if (clock64() - t0 > 8000000000LL) { atomicExch(a.timed_out, 1); break; }
-            __nanosleep(100);
-        }
-    }
-    __syncthreads();
-    // 4. add the slots in rank order: the same sum, bit for bit, on every rank
-    if (w < W) {
-        double s = 0.0;
-        for (int r = 0; r < a.world; ++r) s += a.data[a.rank][((size_t)par * a.world + r) * (size_t)a.wcap + w];
-        vec[w] = s;
-    }
-}
-__global__ void k_seq_advance(unsigned* seq) { *seq += 1u; }
-
-extern "C" int lf_peer_buffer_create(lf_ctx* c, int32_t rank, int32_t world, int64_t wcap, unsigned char handle_out[64]) {
-    if (!c || !handle_out) return fail("lf_peer_buffer_create: null argument");
-    if (world < 1 || world > PEER_MAX || rank < 0 || rank >= world || wcap < 1) return fail("lf_peer_buffer_create: bad rank / world / capacity");
-    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle size");
-    CK(cudaSetDevice(c->device));
-    if (c->peer_base) return fail("lf_peer_buffer_create: already created");
-    const long long cap = (wcap + PEER_CHUNK - 1) / PEER_CHUNK * PEER_CHUNK;
-    const int nchunk = (int)(cap / PEER_CHUNK);
-    const size_t data_bytes = sizeof(double) * 2 * (size_t)world * cap;
-    const size_t flag_bytes = sizeof(unsigned) * 2 * (size_t)world * nchunk;
-    CK(cudaMalloc(&c->peer_base, data_bytes + flag_bytes));
-    CK(cudaMemset(c->peer_base, 0, data_bytes + flag_bytes));
-    CK(cudaMalloc(&c->peer_seq, sizeof(unsigned)));
-    const unsigned one = 1u;
-    CK(cudaMemcpy(c->peer_seq, &one, sizeof(unsigned), cudaMemcpyHostToDevice));
-    // time-out flag in mapped pinned host memory: the kernel writes it (zero-copy) only when a wait expires, the host
-    // reads it without a device round trip
-    CK(cudaHostAlloc(&c->peer_timeout_h, sizeof(int), cudaHostAllocMapped));
-    *c->peer_timeout_h = 0;
-    CK(cudaHostGetDevicePointer(&c->peer_timeout, c->peer_timeout_h, 0));
-    PeerArgs& p = c->peer;
-    memset(&p, 0, sizeof(p));
-    p.rank = rank; p.world = world; p.wcap = cap; p.nchunk_cap = nchunk;
-    p.data[rank] = reinterpret_cast<double*>(c->peer_base);
-    p.flags[rank] = reinterpret_cast<unsigned*>(c->peer_base + data_bytes);
-    p.seq = c->peer_seq; p.timed_out = c->peer_timeout;
-    c->peer_data_bytes = data_bytes;
-    cudaIpcMemHandle_t h;
-    CK(cudaIpcGetMemHandle(&h, c->peer_base));
-    memcpy(handle_out, &h, 64);
-    c->peer_connected = (world == 1);
-    return 0;
-}
-
-extern "C" int lf_peer_buffer_connect(lf_ctx* c, const unsigned char* handles) {
-    if (!c || !handles) return fail("lf_peer_buffer_connect: null argument");
-    if (!c->peer_base) return fail("lf_peer_buffer_connect: call lf_peer_buffer_create first");
-    CK(cudaSetDevice(c->device));
-    PeerArgs& p = c->peer;
-    for (int r = 0; r < p.world; ++r) {
-        if (r == p.rank) continue;
-        cudaIpcMemHandle_t h;
-        memcpy(&h, handles + 64 * r, 64);
-        void* base = nullptr;
-        CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
-        c->peer_opened[r] = base;
-        p.data[r] = reinterpret_cast<double*>(base);
-        p.flags[r] = reinterpret_cast<unsigned*>(reinterpret_cast<unsigned char*>(base) + c->peer_data_bytes);
-    }
-    c->peer_connected = true;
-    return 0;
-}
-
-extern "C" int lf_allreduce_device(lf_ctx* c, double* d_vec, int64_t W, void* stream) {
-    if (!c || (W > 0 && !d_vec)) return fail("lf_allreduce_device: null argument");
-    if (!c->peer_base || !c->peer_connected) return fail("lf_allreduce_device: peer buffers are not connected");
-    if (W > c->peer.wcap) return fail("lf_allreduce_device: vector longer than the peer buffer capacity");
-    if (W <= 0) return 0;
-    CK(cudaSetDevice(c->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    k_allreduce_p2p<<<(unsigned)((W + PEER_CHUNK - 1) / PEER_CHUNK), PEER_CHUNK, 0, st>>>(c->peer, d_vec, W);
-    k_seq_advance<<<1, 1, 0, st>>>(c->peer_seq);
-    c->launches += 2;
-    CK(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int lf_peer_status(lf_ctx* c, int32_t* timed_out) {
-    if (!c || !timed_out) return fail("lf_peer_status: null argument");
-    *timed_out = 0;
-    if (!c->peer_timeout_h) return 0;
-    *timed_out = *(volatile int*)c->peer_timeout_h;        // meaningful after the stream that ran the exchange was synchronised
-    *c->peer_timeout_h = 0;
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// set-up tables on the GPU: cosmology distances and NumPy-exact linear interpolation
-// ------------------------------------------------------------------------------------------------
-// E(z) with NumPy's order of operations and no fused multiply-adds (cosmology.py efunc)
-__device__ __forceinline__ double efunc_np(const lf_cosmology& c, double z) {
-    const double zp1 = __dadd_rn(1.0, z);
-    double t = __dadd_rn(__dmul_rn(c.Or0, zp1), c.Om0);
-    t = __dadd_rn(__dmul_rn(t, zp1), c.Ok0);
-    t = __dadd_rn(__dmul_rn(__dmul_rn(zp1, zp1), t), c.Ode0);
-    return sqrt(t);
-}
-
-__global__ void k_cosmo(lf_cosmology c, const double* __restrict__ cum, long long ncum, long long n,
-                        const double* __restrict__ z, const double* __restrict__ glx, const double* __restrict__ glw,
-                        double* __restrict__ DL, double* __restrict__ dV, int* __restrict__ bad) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double zi = z[i];
-    const long long p = (long long)floor(__ddiv_rn(zi, c.panel));
-    if (!(zi >= 0.0) || p >= ncum) { atomicExch(bad, 1); return; }
-    const double lo = __dmul_rn((double)p, c.panel);
-    const double half = __dmul_rn(0.5, __dsub_rn(zi, lo));
-    double acc = 0.0;
-    for (int q = 0; q < 8; ++q) {                                   // acc += w / E(lo + half * (1 + x)), in node order
-        const double node = __dadd_rn(lo, __dmul_rn(half, __dadd_rn(1.0, glx[q])));
-        acc = __dadd_rn(acc, __ddiv_rn(glw[q], efunc_np(c, node)));
-    }
-    const double dc = __dadd_rn(cum[p], __dmul_rn(half, acc));      // D_C / d_H
-    double dm = dc;
-    if (c.Ok0 > 0.0) { const double s = sqrt(c.Ok0); dm = __ddiv_rn(sinh(__dmul_rn(s, dc)), s); }
-    else if (c.Ok0 < 0.0) { const double s = sqrt(-c.Ok0); dm = __ddiv_rn(sin(__dmul_rn(s, dc)), s); }
-    const double dH = __ddiv_rn(299792.458, c.H0);
-    dm = __dmul_rn(dH, dm);                                         // transverse comoving distance [Mpc]
-    if (DL) DL[i] = __dmul_rn(__dadd_rn(1.0, zi), dm);
-    if (dV) dV[i] = __ddiv_rn(__dmul_rn(__dmul_rn(dH, dm), dm), efunc_np(c, zi));
-}
-
-// numpy.interp, compiled_base.c arr_interp: j = last knot <= x (candidate from the mean spacing, exact comparisons decide)
-__global__ void k_interp(long long nk, const double* __restrict__ xk, const double* __restrict__ yk, long long n,
-                         const double* __restrict__ x, double* __restrict__ y, int* __restrict__ bad) {
-    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const double xv = x[i];
-    const double x0 = xk[0], x1 = xk[nk - 1];
-    if (!(xv >= x0) || !(xv <= x1)) { atomicExch(bad, 1); y[i] = xv != xv ? xv : 0.0; return; }
-    long long j = (long long)((xv - x0) / (x1 - x0) * (double)(nk - 1));
-    j = j < 0 ? 0 : (j > nk - 1 ? nk - 1 : j);
-    int steps = 0;
-    while (j > 0 && xk[j] > xv && steps < 8) { --j; ++steps; }
-    while (j < nk - 1 && xk[j + 1] <= xv && steps < 8) { ++j; ++steps; }
-    if (steps >= 8) {                                               // knots far from uniform: plain binary search
-        long long lo = 0, hi = nk;                                  // invariant: xk[lo] <= xv, (hi == nk or xk[hi] > xv)
-        while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (xk[mid] <= xv) lo = mid; else hi = mid; }
-        j = lo;
-    }
-    double r;
-    if (j == nk - 1) r = yk[j];
-    else if (xk[j] == xv) r = yk[j];
-    else {
-        const double slope = __ddiv_rn(__dsub_rn(yk[j + 1], yk[j]), __dsub_rn(xk[j + 1], xk[j]));
-        r = __dadd_rn(__dmul_rn(slope, __dsub_rn(xv, xk[j])), yk[j]);
-        if (r != r) {
-            r = __dadd_rn(__dmul_rn(slope, __dsub_rn(xv, xk[j + 1])), yk[j + 1]);
-            if (r != r && yk[j] == yk[j + 1]) r = yk[j];
-        }
-    }
-    y[i] = r;
-}
-
-
-extern "C" int lf_cosmo_distances(int32_t device, const lf_cosmology* cosmo, const double* cum, int64_t ncum, int64_t n,
-                                  const double* z, double* DL_Mpc, double* dVdz) {
-    if (!cosmo || !cum || ncum < 1 || n < 0 || (n > 0 && !z)) return fail("lf_cosmo_distances: bad arguments");
-    if (n == 0) return 0;
-    if (!(cosmo->panel > 0.0) || !(cosmo->H0 > 0.0)) return fail("lf_cosmo_distances: need panel > 0 and H0 > 0");
-    CK(cudaSetDevice(device));
-    DevBufs bufs;
-    double *d_cum = nullptr, *d_z = nullptr, *d_DL = nullptr, *d_dV = nullptr, *d_gl = nullptr;
-    int* d_bad = nullptr;
-    CK(bufs.alloc(&d_cum, sizeof(double) * ncum));
-    CK(bufs.alloc(&d_z, sizeof(double) * n));
-    CK(bufs.alloc(&d_gl, sizeof(double) * 16));
-    CK(bufs.alloc(&d_bad, sizeof(int)));
-    if (DL_Mpc) CK(bufs.alloc(&d_DL, sizeof(double) * n));
-    if (dVdz) CK(bufs.alloc(&d_dV, sizeof(double) * n));
-    CK(cudaMemcpy(d_gl, cosmo->gl_x, sizeof(double) * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_gl + 8, cosmo->gl_w, sizeof(double) * 8, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_cum, cum, sizeof(double) * ncum, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_z, z, sizeof(double) * n, cudaMemcpyHostToDevice));
-    CK(cudaMemset(d_bad, 0, sizeof(int)));
-    k_cosmo<<<(unsigned)((n + 255) / 256), 256>>>(*cosmo, d_cum, ncum, n, d_z, d_gl, d_gl + 8, d_DL, d_dV, d_bad);
-    CK(cudaGetLastError());
-    int bad = 0;
-    CK(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
-    if (bad) return fail("lf_cosmo_distances: a redshift is negative, NaN or beyond the cumulative panel table");
-    if (DL_Mpc) CK(cudaMemcpy(DL_Mpc, d_DL, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    if (dVdz) CK(cudaMemcpy(dVdz, d_dV, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-extern "C" int lf_interp_linear(int32_t device, int64_t nk, const double* xk, const double* yk, int64_t n, const double* x,
-                                double* y) {
-    if (nk < 2 || !xk || !yk || n < 0 || (n > 0 && (!x || !y))) return fail("lf_interp_linear: bad arguments");
-    if (n == 0) return 0;
-    CK(cudaSetDevice(device));
-    DevBufs bufs;
-    double *d_xk = nullptr, *d_yk = nullptr, *d_x = nullptr, *d_y = nullptr;
-    int* d_bad = nullptr;
-    CK(bufs.alloc(&d_xk, sizeof(double) * nk));
-    CK(bufs.alloc(&d_yk, sizeof(double) * nk));
-    CK(bufs.alloc(&d_x, sizeof(double) * n));
-    CK(bufs.alloc(&d_y, sizeof(double) * n));
-    CK(bufs.alloc(&d_bad, sizeof(int)));
-    CK(cudaMemcpy(d_xk, xk, sizeof(double) * nk, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_yk, yk, sizeof(double) * nk, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(d_x, x, sizeof(double) * n, cudaMemcpyHostToDevice));
-    CK(cudaMemset(d_bad, 0, sizeof(int)));
-    k_interp<<<(unsigned)((n + 255) / 256), 256>>>(nk, d_xk, d_yk, n, d_x, d_y, d_bad);
-    CK(cudaGetLastError());
-    int bad = 0;
-    CK(cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost));
-    if (bad) return fail("lf_interp_linear: a value in x_new is outside the interpolation range (or NaN)");
-    CK(cudaMemcpy(y, d_y, sizeof(double) * n, cudaMemcpyDeviceToHost));
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// device-resident ensemble sampler (stretch move)
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1,
-                                              uint32_t out[4]) {
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0; c1 = lo1; c2 = hi0 ^ c3 ^ k1; c3 = lo0;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
-}
-__device__ __forceinline__ double u01(uint32_t x) { return __dmul_rn((double)x + 0.5, 2.3283064365386963e-10); }   // (x + 1/2) / 2^32
-
-struct SamplerArgs {
-    int W, half, ndim;
-    double a;
-    uint32_t k0, k1;
-    const long long* step;      // device counter: index of the current ensemble update
-    long long step0;            // value of *step at the first replay (chain rows are relative to it)
-    double* pos; double* lp;    // [W][ndim], [W]
-    double* prop; double* lpnew; double* lnz; double* lnu;     // [half][ndim], [half] x 3
-    double* chain; double* lnp; long long* nacc;               // [nsteps][W][ndim], [nsteps][W], [W]  (chain / lnp may be NULL)
-};
-
-// proposals for the walkers of half h (h = 0: [0, half), h = 1: [half, W)) against the other half
-__global__ void k_stretch_propose(SamplerArgs s, int h) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.half) return;
-    const int me = h * s.half + i;
-    const long long step = *s.step;
-    uint32_t r[4];
-    philox4x32_10((uint32_t)me, (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)h, s.k0, s.k1, r);
-    // z ~ g(z) propto 1/sqrt(z) on [1/a, a]:  z = ((a - 1) u + 1)^2 / a      (rounded operation by operation: the host
-    // replay in tests/ reproduces the chain bit for bit)
-    const double t = __dadd_rn(__dmul_rn(s.a - 1.0, u01(r[0])), 1.0);
-    const double z = __ddiv_rn(__dmul_rn(t, t), s.a);
-    const int partner = (1 - h) * s.half + (int)(((unsigned long long)r[1] * (unsigned long long)s.half) >> 32);
-    for (int d = 0; d < s.ndim; ++d) {
-        const double pp = s.pos[(long long)partner * s.ndim + d], pm = s.pos[(long long)me * s.ndim + d];
-        s.prop[(long long)i * s.ndim + d] = __dsub_rn(pp, __dmul_rn(__dsub_rn(pp, pm), z));
-    }
-    s.lnz[i] = (s.ndim - 1.0) * log(z);
-    s.lnu[i] = log(u01(r[2]));
-}
-
-__global__ void k_stretch_accept(SamplerArgs s, int h) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.half) return;
-    const int me = h * s.half + i;
-    const double lnratio = s.lnz[i] + s.lpnew[i] - s.lp[me];       // NaN (inf - inf) compares false: rejected
-    const bool acc = s.lnu[i] < lnratio;
-    if (acc) {
-        for (int d = 0; d < s.ndim; ++d) s.pos[(long long)me * s.ndim + d] = s.prop[(long long)i * s.ndim + d];
-        s.lp[me] = s.lpnew[i];
-        s.nacc[me] += 1;
-    }
-    const long long row = *s.step - s.step0;
-    if (s.chain)
-        for (int d = 0; d < s.ndim; ++d) s.chain[(row * s.W + me) * s.ndim + d] = s.pos[(long long)me * s.ndim + d];
-    if (s.lnp) s.lnp[row * s.W + me] = s.lp[me];
-}
-__global__ void k_step_advance(long long* step) { *step += 1; }
-
-__global__ void k_boot_draw(long long n, uint32_t k0, uint32_t k1, uint32_t rep_lo, uint32_t rep_hi, int* __restrict__ mult) {
-    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // Philox call q yields draws 4q .. 4q+3
-    if (4 * q >= n) return;
-    uint32_t r[4];
-    philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), rep_lo, rep_hi, k0, k1, r);
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-        if (4 * q + t < n) atomicAdd(&mult[(long long)(((unsigned long long)r[t] * (unsigned long long)n) >> 32)], 1);
-}
-
-extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t nsteps, uint64_t seed, double a, int64_t step0,
-                              double* chain, double* lnprob, int64_t* naccepted, double* pos_out, double* lnprob_out) {
-    if (!c || !pos0) return fail("lf_sampler_run: null argument");
-    if (W < 2 || (W & 1)) return fail("lf_sampler_run: the number of walkers must be even");
-    if (nsteps < 0 || !(a > 1.0)) return fail("lf_sampler_run: need nsteps >= 0 and a > 1");
-    if (!c->have_sources || !c->have_grid) return fail("lf_sampler_run: call lf_set_sources and lf_set_grid first");
-    CK(cudaSetDevice(c->device));
-    const int ndim = c->ndim, half = (int)(W / 2);
-    cudaStream_t st = c->stream;
-    double *d_pos = nullptr, *d_lp = nullptr, *d_prop = nullptr, *d_lpnew = nullptr, *d_lnz = nullptr, *d_lnu = nullptr;
-    double *d_chain = nullptr, *d_lnp = nullptr;
-    long long *d_nacc = nullptr, *d_step = nullptr;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t exec = nullptr;
-    int rc = 1;
-    auto cleanup = [&]() {
-        if (exec) cudaGraphExecDestroy(exec);
-        if (graph) cudaGraphDestroy(graph);
-        dfree(d_pos); dfree(d_lp); dfree(d_prop); dfree(d_lpnew); dfree(d_lnz); dfree(d_lnu);
-        dfree(d_chain); dfree(d_lnp); dfree(d_nacc); dfree(d_step);
-        return rc;
-    };
-#define SCK(call)                                                                                   \
-    do {                                                                                            \
-        cudaError_t e_ = (call);                                                                    \
-        if (e_ != cudaSuccess) {                                                                    \
-            fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + __FILE__ + ":" + std::to_string(__LINE__) + ")"); \
-            return cleanup();                                                                       \
-        }                                                                                           \
-    } while (0)
-    SCK(cudaMalloc(&d_pos, sizeof(double) * W * ndim));
-    SCK(cudaMalloc(&d_lp, sizeof(double) * W));
-    SCK(cudaMalloc(&d_prop, sizeof(double) * half * ndim));
-    SCK(cudaMalloc(&d_lpnew, sizeof(double) * half));
-    SCK(cudaMalloc(&d_lnz, sizeof(double) * half));
-    SCK(cudaMalloc(&d_lnu, sizeof(double) * half));
-    SCK(cudaMalloc(&d_nacc, sizeof(long long) * W));
-    SCK(cudaMalloc(&d_step, sizeof(long long)));
-    if (chain && nsteps > 0) SCK(cudaMalloc(&d_chain, sizeof(double) * (size_t)nsteps * W * ndim));
-    if (lnprob && nsteps > 0) SCK(cudaMalloc(&d_lnp, sizeof(double) * (size_t)nsteps * W));
-    SCK(cudaMemcpyAsync(d_pos, pos0, sizeof(double) * W * ndim, cudaMemcpyHostToDevice, st));
-    SCK(cudaMemsetAsync(d_nacc, 0, sizeof(long long) * W, st));
-    const long long s0 = step0;
-    SCK(cudaMemcpyAsync(d_step, &s0, sizeof(long long), cudaMemcpyHostToDevice, st));
-    // log-posterior of the starting ensemble, and one un-captured half-ensemble call so that every scratch buffer
-    // the captured pipeline needs already has its final size
-    // source-sharded run over several GPUs: every rank draws the same Philox proposals and the per-walker partials are
-    // summed by the peer-memory kernel inside the captured update (identical bits on every rank keep the chains equal)
-    const bool exchange = c->peer_connected && c->peer.world > 1;
-    if (exchange && W > c->peer.wcap) { fail("lf_sampler_run: more walkers than the peer buffers hold"); return cleanup(); }
-    auto lnprob_all_ranks = [&](const double* th, long long nw, double* out) -> int {
-        if (launch_pipeline(c, th, nw, out, st)) return 1;
-        if (exchange) {
-            k_allreduce_p2p<<<(unsigned)((nw + PEER_CHUNK - 1) / PEER_CHUNK), PEER_CHUNK, 0, st>>>(c->peer, out, nw);
-            k_seq_advance<<<1, 1, 0, st>>>(c->peer_seq);
-            c->launches += 2;
-        }
-        return 0;
-    };
-    if (lnprob_all_ranks(d_pos, W, d_lp)) return cleanup();
-    if (lnprob_all_ranks(d_pos, half, d_lpnew)) return cleanup();
-    SCK(cudaStreamSynchronize(st));
-    SamplerArgs sa;
-    sa.W = (int)W; sa.half = half; sa.ndim = ndim; sa.a = a;
-    sa.k0 = (uint32_t)seed; sa.k1 = (uint32_t)(seed >> 32);
-    sa.step = d_step; sa.step0 = step0;
-    sa.pos = d_pos; sa.lp = d_lp; sa.prop = d_prop; sa.lpnew = d_lpnew; sa.lnz = d_lnz; sa.lnu = d_lnu;
-    sa.chain = d_chain; sa.lnp = d_lnp; sa.nacc = d_nacc;
-    const int T = 128, G = (half + T - 1) / T;
-    const long long launches0 = c->launches;
-    if (nsteps > 0) {
-        SCK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-        bool ok = true;
-        for (int h = 0; h < 2 && ok; ++h) {
-            k_stretch_propose<<<G, T, 0, st>>>(sa, h);
-            ok = lnprob_all_ranks(d_prop, half, d_lpnew) == 0;
-            k_stretch_accept<<<G, T, 0, st>>>(sa, h);
-            c->launches += 2;
-        }
-        k_step_advance<<<1, 1, 0, st>>>(d_step);
-        c->launches += 1;
-        cudaError_t ce = cudaStreamEndCapture(st, &graph);
-        if (!ok) return cleanup();
-        SCK(ce);
-        SCK(cudaGraphInstantiate(&exec, graph, 0));
-        const long long per_step = c->launches - launches0;
-        SCK(cudaEventRecord(c->ev0, st));
-        for (int64_t t = 0; t < nsteps; ++t) SCK(cudaGraphLaunch(exec, st));
-        SCK(cudaEventRecord(c->ev1, st));
-        c->launches = launches0 + per_step * nsteps;
-    }
-    if (chain && nsteps > 0) SCK(cudaMemcpyAsync(chain, d_chain, sizeof(double) * (size_t)nsteps * W * ndim, cudaMemcpyDeviceToHost, st));
-    if (lnprob && nsteps > 0) SCK(cudaMemcpyAsync(lnprob, d_lnp, sizeof(double) * (size_t)nsteps * W, cudaMemcpyDeviceToHost, st));
-    if (naccepted) SCK(cudaMemcpyAsync(naccepted, d_nacc, sizeof(long long) * W, cudaMemcpyDeviceToHost, st));
-    if (pos_out) SCK(cudaMemcpyAsync(pos_out, d_pos, sizeof(double) * W * ndim, cudaMemcpyDeviceToHost, st));
-    if (lnprob_out) SCK(cudaMemcpyAsync(lnprob_out, d_lp, sizeof(double) * W, cudaMemcpyDeviceToHost, st));
-    SCK(cudaStreamSynchronize(st));
-    SCK(cudaGetLastError());
-    if (nsteps > 0) { float ms = 0.f; SCK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->sampler_ms = ms; }
-#undef SCK
-    rc = 0;
-    return cleanup();
-}
-
-extern "C" int lf_sampler_last_ms(lf_ctx* c, double* ms) {
-    if (!c || !ms) return fail("lf_sampler_last_ms: null argument");
-    *ms = c->sampler_ms;
-    return 0;
-}
-
-// ------------------------------------------------------------------------------------------------
-// Veff launch plan: lane-private histograms whenever they fit in shared memory, atomics otherwise
-// ------------------------------------------------------------------------------------------------
-struct VeffPlan { bool priv; int blocks, threads; size_t smem; };
-static VeffPlan veff_plan(const lf_ctx* c, long long n, int nbins) {
-    VeffPlan p;
-    const size_t priv = sizeof(double) * (nbins + 1) * 16 + (size_t)VP_WARPS * nbins * VP_COLS * (sizeof(double) + sizeof(unsigned)) +
-                        sizeof(double2) * STREAM_LOG_N + sizeof(double) * EXP_TAB_N;
-    if (priv <= VP_SMEM_MAX) {
-        int per_sm = (int)std::min<size_t>(8, (size_t)(227 * 1024) / (priv + 1024));
-        per_sm = std::max(per_sm, 1);
-        p.priv = true; p.threads = 32 * VP_WARPS; p.smem = priv;
-        p.blocks = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * per_sm,
-                                                                     (n + p.threads * VP_UNROLL - 1) / (p.threads * VP_UNROLL)));
-    } else {
-        p.priv = false; p.threads = 256;
-        p.smem = sizeof(double) * (nbins + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * (size_t)nbins;
-        p.blocks = (int)std::min<long long>((long long)c->sm_count * 8, (n + 255) / 256);
-    }
-    return p;
-}
-template <int MODE>
-static void veff_launch(const VeffPlan& p, const VeffArgs& a, cudaStream_t st) {
-    if (p.priv) k_veff_priv<MODE><<<p.blocks, p.threads, p.smem, st>>>(a);
-    else k_veff<MODE><<<p.blocks, p.threads, p.smem, st>>>(a);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Veff host entry points
-// ------------------------------------------------------------------------------------------------
-extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const double* lum, const int64_t* field_ind,
-                           int32_t nfields, const double* flim, double alpha, double fcmin, double sum_omega,
-                           double vol_int, const double* vol_per_source, const uint8_t* valid,
-                           const double* edges, int32_t nbins, double* phi_out, int64_t* counts, double* sumphi) {
-    if (!c) return fail("lf_veff_bin: null context");
-    if (n <= 0 || !flux || !lum || !field_ind || !flim || !edges || !counts || !sumphi) return fail("lf_veff_bin: bad arguments");
-    if (nfields < 1 || nfields > LF_MAX_FIELDS) return fail("lf_veff_bin: nfields out of range");
-    if (nbins < 1 || nbins > VEFF_MAX_BINS) return fail("lf_veff_bin: nbins out of range");
-    if (field_ind[0] != 0 || field_ind[nfields] != n) return fail("lf_veff_bin: field_ind must run from 0 to n");
-    CK(cudaSetDevice(c->device));
-    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
-    dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
-    const size_t nb = sizeof(double) * (size_t)n;
-    double* d_flux = nullptr; double* d_vol = nullptr; unsigned char* d_valid = nullptr;
-    CK(cudaMalloc(&d_flux, nb));
-    CK(cudaMalloc(&c->v_lum, nb));
-    CK(cudaMalloc(&c->v_phi, nb));
-    CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
-    const VeffPlan plan = veff_plan(c, n, nbins);
-    const int blocks = plan.blocks;
-    c->v_blocks = blocks; c->v_nbins = nbins; c->vN = n;
-    CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)blocks * nbins));
-    CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)blocks * nbins));
-    CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
-    CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
-    CK(cudaMalloc(&c->v_bin, sizeof(short) * (size_t)n));
-    CK(cudaMemcpyAsync(d_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
-    if (vol_per_source) {
-        CK(cudaMalloc(&d_vol, nb));
-        CK(cudaMemcpyAsync(d_vol, vol_per_source, nb, cudaMemcpyHostToDevice, c->stream));
-    }
-    if (valid) {
-        CK(cudaMalloc(&d_valid, (size_t)n));
-        CK(cudaMemcpyAsync(d_valid, valid, (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    }
-    VeffArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n = n; a.flux = d_flux; a.lum = c->v_lum; a.vol = d_vol; a.valid = d_valid; a.phi = c->v_phi;
-    a.K = nfields;
-    for (int k = 0; k <= nfields; ++k) a.field_ind[k] = field_ind[k];
-    const bool modified = fcmin != 0.0;
-    double aa = (2.0 * fcmin - 1.0) * (2.0 * fcmin - 1.0);
-    for (int k = 0; k < nfields; ++k) {
-        a.F50[k] = 1.0e-17 * flim[k];
-        // inverse_fleming, reference operation order (VmaxLumFunc.py:164-167)
-        double b = -1.0 * pow(fabs(aa / (1.0 - aa)) * pow(alpha, -2.0), 0.5);
-        a.ftau[k] = a.F50[k] * pow(10.0, b);
-        a.invF50[k] = 1.0 / a.F50[k];
-        a.inv_ftau[k] = 1.0 / a.ftau[k];
-    }
-    a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.vol_int = vol_int; a.modified = modified ? 1 : 0;
-    a.inv_pref_vol = 1.0 / (a.pref * vol_int); a.tables = c->d_tables;
-    a.edges = c->v_edges; a.nbins = nbins; a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = nullptr; a.bin = c->v_bin;
-    CK(cudaEventRecord(c->ev0, c->stream));
-    veff_launch<0>(plan, a, c->stream);
-    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
-    CK(cudaEventRecord(c->ev1, c->stream));
-    c->launches += 2;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
-    if (phi_out) CK(cudaMemcpyAsync(phi_out, c->v_phi, nb, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms; }
-    cudaFree(d_flux);
-    if (d_vol) cudaFree(d_vol);
-    if (d_valid) cudaFree(d_valid);
-    return 0;
-}
-
-extern "C" int lf_bin_weights(lf_ctx* c, int64_t n, const double* lum, const double* phi, const double* edges,
-                              int32_t nbins, int64_t* counts, double* sumphi) {
-    if (!c) return fail("lf_bin_weights: null context");
-    if (n <= 0 || !lum || !phi || !edges || !counts || !sumphi) return fail("lf_bin_weights: bad arguments");
-    if (nbins < 1 || nbins > VEFF_MAX_BINS) return fail("lf_bin_weights: nbins out of range");
-    CK(cudaSetDevice(c->device));
-    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
-    dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
-    const size_t nb = sizeof(double) * (size_t)n;
-    CK(cudaMalloc(&c->v_lum, nb));
-    CK(cudaMalloc(&c->v_phi, nb));
-    CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
-    const VeffPlan plan = veff_plan(c, n, nbins);
-    const int blocks = plan.blocks;
-    c->v_blocks = blocks; c->v_nbins = nbins; c->vN = n;
-    CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)blocks * nbins));
-    CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)blocks * nbins));
-    CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
-    CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
-    CK(cudaMalloc(&c->v_bin, sizeof(short) * (size_t)n));
-    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->v_phi, phi, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
-    VeffArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n = n; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = nbins;
-    a.counts = c->v_counts; a.sumphi = c->v_sums; a.bin = c->v_bin;
-    CK(cudaEventRecord(c->ev0, c->stream));
-    veff_launch<2>(plan, a, c->stream);
-    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
-    CK(cudaEventRecord(c->ev1, c->stream));
-    c->launches += 2;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (cudaEventQuery(c->ev1) == cudaSuccess) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
-    return 0;
-}
-
-// multiplicities of one bootstrap replicate: n uniform draws with replacement, 4 per Philox call
-__global__ void k_boot_draw(long long n, uint32_t k0, uint32_t k1, uint32_t rep_lo, uint32_t rep_hi, int* __restrict__ mult);
-
-extern "C" int lf_boot_bin_device(lf_ctx* c, uint64_t seed, int64_t replicate, int64_t* counts, double* sumphi) {
-    if (!c) return fail("lf_boot_bin_device: null context");
-    if (!c->v_phi || c->vN <= 0) return fail("lf_boot_bin_device: call lf_veff_bin or lf_bin_weights first");
-    if (!counts || !sumphi) return fail("lf_boot_bin_device: bad arguments");
-    if (c->vN >= (1LL << 32)) return fail("lf_boot_bin_device: more than 2^32 sources");
-    CK(cudaSetDevice(c->device));
-    if (!c->v_mult) CK(cudaMalloc(&c->v_mult, sizeof(int) * (size_t)c->vN));
-    CK(cudaEventRecord(c->ev0, c->stream));
-    CK(cudaMemsetAsync(c->v_mult, 0, sizeof(int) * (size_t)c->vN, c->stream));
-    const long long calls = (c->vN + 3) / 4;
-    k_boot_draw<<<(unsigned)((calls + 255) / 256), 256, 0, c->stream>>>(c->vN, (uint32_t)seed, (uint32_t)(seed >> 32),
-                                                                      (uint32_t)replicate, (uint32_t)((uint64_t)replicate >> 32), c->v_mult);
-    VeffArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
-    a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult; a.bin = c->v_bin;
-    const int nbins = c->v_nbins, blocks = c->v_blocks;
-    const VeffPlan plan = veff_plan(c, c->vN, nbins);
-    veff_launch<1>(plan, a, c->stream);
-    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
-    CK(cudaEventRecord(c->ev1, c->stream));
-    c->launches += 3;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
-    return 0;
-}
-
-extern "C" int lf_boot_bin(lf_ctx* c, const int32_t* mult, int64_t* counts, double* sumphi) {
-    if (!c) return fail("lf_boot_bin: null context");
-    if (!c->v_phi || c->vN <= 0) return fail("lf_boot_bin: call lf_veff_bin first");
-    if (!mult || !counts || !sumphi) return fail("lf_boot_bin: bad arguments");
-    CK(cudaSetDevice(c->device));
-    if (!c->v_mult) CK(cudaMalloc(&c->v_mult, sizeof(int) * (size_t)c->vN));
-    CK(cudaMemcpyAsync(c->v_mult, mult, sizeof(int) * (size_t)c->vN, cudaMemcpyHostToDevice, c->stream));
-    VeffArgs a;
-    memset(&a, 0, sizeof(a));
-    a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
-    a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult; a.bin = c->v_bin;
-    const int nbins = c->v_nbins, blocks = c->v_blocks;
-    const VeffPlan plan = veff_plan(c, c->vN, nbins);
-    CK(cudaEventRecord(c->ev0, c->stream));
-    veff_launch<1>(plan, a, c->stream);
-    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
-    CK(cudaEventRecord(c->ev1, c->stream));
-    c->launches += 2;
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (cudaEventQuery(c->ev1) == cudaSuccess) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
-    return 0;
-}

@@ -63,7 +63,7 @@ constexpr double LOG1P_C0 = 4.5474875525573243324e-13;             // folded int
 constexpr double LOG1P_C1 = 0.9999999999985449674, LOG1P_C2 = -0.50000095367660766342, LOG1P_C3 = 0.33333447770293183222;
 constexpr double EXP2_C0 = 0.99999999999998250473, EXP2_C1 = 0.69314718055993561091, EXP2_C2 = 0.24022654364935376114,
                  EXP2_C3 = 0.055504116293577099979;
-__constant__ double KC[16] = {
+static __constant__ double KC[16] = {
     MAGIC44,                // 0
     EXP2_C3,                // 1
     EXP2_C2,                // 2
@@ -302,7 +302,7 @@ __device__ __forceinline__ void fleming_terms(const double2* u, double alpha, do
 constexpr int STREAM_LOG_N = 1 << LOG_MANT_BITS;
 constexpr double LN2_HI = 0.693147180369123816490, LN2_LO = 1.90821492927058770002e-10;
 // coefficients in the constant bank (c[3][..] operands: no UMOV pairs to materialise 64-bit immediates)
-__constant__ double KS[16] = {
+static __constant__ double KS[16] = {
     -1.0 / 6.0, 0.2, 1.0 / 3.0,                      // 0-2   log1p
     LN2_HI, LN2_LO,                                  // 3-4
     256.0 * LOG2E, MAGIC52, -LN2_HI / 256.0, -LN2_LO / 256.0,   // 5-8   exp range reduction

@@ -1,0 +1,468 @@
+// lf_veff.cu -- 1/V_eff weights, binned luminosity function and bootstrap replicates behind include/lf_engine.h
+// (reference lumfuncmcmc.py:515-525, VmaxLumFunc.py:235-257, 304-378).
+#include "lf_internal.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// 1/V_eff weights + binned luminosity function  (HBM-bound streaming pass)
+// ------------------------------------------------------------------------------------------------
+#define VEFF_MAX_BINS 1024
+struct VeffArgs {
+    long long n;
+    const double* flux; const double* lum; const double* vol; const unsigned char* valid;
+    double* phi;
+    int K; long long field_ind[LF_MAX_FIELDS + 1]; double F50[LF_MAX_FIELDS]; double ftau[LF_MAX_FIELDS];
+    double invF50[LF_MAX_FIELDS]; double inv_ftau[LF_MAX_FIELDS];
+    double alpha, pref, vol_int, inv_pref_vol; int modified;
+    const Tables* tables;
+    const double* edges; int nbins;
+    unsigned long long* counts; double* sumphi;     // [gridDim.x][nbins] block partials
+    const int* mult;                                 // bootstrap multiplicities (NULL: original sample)
+    short* bin;                                      // per-source bin index (-1: none), written by MODE 0/2, read by MODE 1
+};
+
+__device__ __forceinline__ int bin_of(double L, const double* e, int nb) {
+    // half-open bins [e_j, e_{j+1}), exact comparisons against the caller's edges (VmaxLumFunc.py:346-348)
+    if (!(L >= e[0]) || !(L < e[nb])) return -1;
+    int j = (int)((L - e[0]) / (e[nb] - e[0]) * nb);
+    j = j < 0 ? 0 : (j > nb - 1 ? nb - 1 : j);
+    while (j > 0 && L < e[j]) --j;
+    while (j < nb - 1 && L >= e[j + 1]) ++j;
+    return j;
+}
+
+// same search on an edge table replicated x16 in shared memory (e[j * 16 + col]: a half-warp never bank-conflicts),
+// candidate bin from a precomputed scale instead of a division; the comparisons against the caller's exact edges decide
+__device__ __forceinline__ int bin_of_rep(double L, const double* e, int col, int nb, double e0, double enb, double scale) {
+    if (!(L >= e0) || !(L < enb)) return -1;
+    int j = (int)((L - e0) * scale);
+    j = j < 0 ? 0 : (j > nb - 1 ? nb - 1 : j);
+    while (j > 0 && L < e[j * 16 + col]) --j;
+    while (j < nb - 1 && L >= e[(j + 1) * 16 + col]) ++j;
+    return j;
+}
+
+// MODE 0: compute phi from the completeness and bin; MODE 1: bootstrap replicate (multiplicities) on resident
+// lum/phi; MODE 2: bin caller-provided (resident) phi
+template <int MODE>
+__global__ void __launch_bounds__(256) k_veff(VeffArgs a) {
+    constexpr bool BOOT = MODE == 1;
+    extern __shared__ unsigned char smem_raw[];
+    double* s_edges = reinterpret_cast<double*>(smem_raw);                 // nbins+1
+    double* s_sum = s_edges + (a.nbins + 1);                               // 8 warps x nbins
+    unsigned long long* s_cnt = reinterpret_cast<unsigned long long*>(s_sum + 8 * a.nbins);
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i <= a.nbins; i += blockDim.x) s_edges[i] = a.edges[i];
+    for (int i = threadIdx.x; i < 8 * a.nbins; i += blockDim.x) { s_sum[i] = 0.0; s_cnt[i] = 0ULL; }
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+        double phi;
+        unsigned long long m = 1ULL;
+        if (BOOT) {
+            m = (unsigned long long)a.mult[i];
+            if (m == 0ULL) continue;
+            phi = a.phi[i];
+        } else if (MODE == 2) {
+            phi = a.phi[i];
+        } else {
+            int k = 0;
+            while (k + 1 < a.K && i >= a.field_ind[k + 1]) ++k;
+            double comp = fleming_literal(a.flux[i], a.F50[k], a.alpha, a.ftau[k], a.modified != 0);
+            double vol = a.vol ? a.vol[i] : a.vol_int;
+            bool ok = a.valid ? (a.valid[i] != 0) : true;
+            phi = ok ? 1.0 / (a.pref * comp * vol) : 0.0;       // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
+            a.phi[i] = phi;
+        }
+        int j = bin_of(a.lum[i], s_edges, a.nbins);
+        if (j >= 0) {
+            atomicAdd(&s_sum[warp * a.nbins + j], BOOT ? phi * (double)m : phi);
+            atomicAdd(&s_cnt[warp * a.nbins + j], m);
+        }
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < a.nbins; j += blockDim.x) {
+        double s = 0.0; unsigned long long c = 0ULL;
+        for (int wv = 0; wv < 8; ++wv) { s += s_sum[wv * a.nbins + j]; c += s_cnt[wv * a.nbins + j]; }
+        a.sumphi[(long long)blockIdx.x * a.nbins + j] = s;
+        a.counts[(long long)blockIdx.x * a.nbins + j] = c;
+    }
+}
+
+// ---- streaming version with private histogram columns (no atomics, deterministic) ----
+// Each warp owns VP_COLS = 16 columns per bin of the block's shared-memory histogram, s_sum[warp][bin][col] (f64) and
+// s_cnt[warp][bin][col] (u32); lanes l and l + 16 share column l and update it in two turns separated by __syncwarp,
+// so an update is a plain read-modify-write of a word nobody else touches in that turn (no atomics, no races, one
+// bank per column).  At the end each warp folds its columns with a fixed shuffle tree and the block adds the warps
+// in order: the result does not depend on scheduling.  Shared memory: 8 warps x nbins x 16 x 12 B (76.8 KB at the
+// reference's nbins = 50 -> two blocks = 16 warps per SM); larger histograms fall back to k_veff (atomics).
+// The per-source completeness is evaluated as exp(-ln(fc)/dec) with the ~2e-16 routines of lf_math.cuh (two 2-4 KB
+// tables) instead of libdevice pow/log10/exp/sqrt and five IEEE divisions: ~75 FP64-pipe instructions per source, so
+// the pass stays close to its HBM time (24 B per source).
+#define VP_WARPS 8
+#define VP_COLS 16
+#define VP_UNROLL 4
+static const size_t VP_SMEM_MAX = 200 * 1024;
+
+__device__ __noinline__ double inv_fleming_literal(double f, double F50, double alpha, double ftau, bool modified) {
+    return 1.0 / fleming_literal(f, F50, alpha, ftau, modified);
+}
+
+// 1 / fleming(f): VmaxLumFunc.py:118-126, 141.  Sources outside the range where the fast evaluation is accurate to
+// ~1e-15 (fc < 1e-6, decay argument < 1e-6, |ln comp| > 690) take the literal libdevice route.
+__device__ __forceinline__ double inv_fleming_stream(double f, double F50, double invF50, double alpha_log10e, double alpha,
+                                                     double ftau, double inv_ftau, bool modified, const double* s_exp,
+                                                     const double2* s_logm) {
+    const double num = alpha_log10e * log_stream(f * invF50, s_logm);       // alpha * log10(f / F50)
+    const double y = fma(num, num, 1.0);
+    double r0 = rsqrt_seed(y);
+    const double e = fma(-(y * r0), r0, 1.0);
+    const double pe = fma(0.375, e, 0.5) * e;
+    const double nr = num * r0;
+    const double fc = fma(0.5, fma(nr, pe, nr), 0.5);
+    const double x = f * inv_ftau;
+    double t = -log_stream(fc > 1.0e-300 ? fc : 1.0e-300, s_logm);
+    if (modified) t *= rcp_stream(1.0 - exp_stream(x < 690.0 ? -x : -690.0, s_exp));
+    if (!(fc > 1.0e-6) || (modified && !(x > 1.0e-6)) || !(t < 690.0)) return inv_fleming_literal(f, F50, alpha, ftau, modified);
+    return exp_stream(t, s_exp);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32 * VP_WARPS) k_veff_priv(VeffArgs a) {
+    constexpr bool BOOT = MODE == 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nb = a.nbins;
+    double* s_edges = reinterpret_cast<double*>(smem_raw);                  // [nbins + 1][16] replicated
+    double* s_sum = s_edges + (nb + 1) * 16;                                // [VP_WARPS][nbins][VP_COLS]
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + VP_WARPS * nb * VP_COLS);
+    double2* s_logm = reinterpret_cast<double2*>(s_cnt + VP_WARPS * nb * VP_COLS);   // MODE 0 only
+    double* s_exp = reinterpret_cast<double*>(s_logm + STREAM_LOG_N);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (nb + 1) * 16; i += blockDim.x) s_edges[i] = a.edges[i >> 4];
+    for (int i = threadIdx.x; i < VP_WARPS * nb * VP_COLS; i += blockDim.x) { s_sum[i] = 0.0; s_cnt[i] = 0u; }
+    if (MODE == 0) load_stream_tables(a.tables, s_exp, s_logm);
+    const double e0 = a.edges[0], enb = a.edges[nb], scale = (double)nb / (enb - e0);
+    __syncthreads();
+    double* my_sum = s_sum + warp * nb * VP_COLS + (lane & (VP_COLS - 1));
+    unsigned* my_cnt = s_cnt + warp * nb * VP_COLS + (lane & (VP_COLS - 1));
+    const int turn = lane >> 4;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double alpha_log10e = a.alpha * KS[12];
+    int k = 0;                                  // sources are field-sorted: the field index only moves forward
+    // whole warps iterate together (the trip count is computed from the warp's first lane) so that __syncwarp is legal
+    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < a.n; i0 += stride * VP_UNROLL) {
+        const long long i = i0 + lane;
+        double lum[VP_UNROLL], phi[VP_UNROLL], flux[VP_UNROLL], vol[VP_UNROLL];
+        unsigned m[VP_UNROLL];
+        int jb[VP_UNROLL];
+        bool ok[VP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < VP_UNROLL; ++u) {                                // all loads of the trip first
+            const long long ii = i + u * stride;
+            const bool in = ii < a.n;
+            m[u] = in ? 1u : 0u;
+            ok[u] = in;
+            phi[u] = 0.0;
+            if (BOOT) {                                                      // replicate: resident bin index, weight, multiplicity
+                jb[u] = in ? (int)__ldcs(a.bin + ii) : -1;
+                m[u] = in ? (unsigned)__ldcs(a.mult + ii) : 0u;
+                phi[u] = in ? __ldcs(a.phi + ii) : 0.0;
+                continue;
+            }
+            lum[u] = in ? __ldcs(a.lum + ii) : -1.0e300;                     // below every edge: lands in no bin
+            if (MODE == 2) {
+                phi[u] = in ? __ldcs(a.phi + ii) : 0.0;
+            } else {
+                flux[u] = in ? __ldcs(a.flux + ii) : 1.0;
+                vol[u] = (in && a.vol) ? __ldcs(a.vol + ii) : a.vol_int;
+                if (in && a.valid) ok[u] = a.valid[ii] != 0;
+            }
+        }
+        if (MODE == 0) {
+#pragma unroll
+            for (int u = 0; u < VP_UNROLL; ++u) {
+                const long long ii = i + u * stride;
+                while (k + 1 < a.K && ii >= a.field_ind[k + 1]) ++k;
+                const double icomp = inv_fleming_stream(flux[u], a.F50[k], a.invF50[k], alpha_log10e, a.alpha, a.ftau[k],
+                                                        a.inv_ftau[k], a.modified != 0, s_exp, s_logm);
+                const double ipv = a.vol ? 1.0 / (a.pref * vol[u]) : a.inv_pref_vol;
+                phi[u] = ok[u] ? icomp * ipv : 0.0;                          // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
+                if (ii < a.n) __stcs(a.phi + ii, phi[u]);
+            }
+        }
+        if (!BOOT) {
+#pragma unroll
+            for (int u = 0; u < VP_UNROLL; ++u) {
+                const long long ii = i + u * stride;
+                jb[u] = bin_of_rep(lum[u], s_edges, lane & 15, nb, e0, enb, scale);
+                if (ii < a.n) a.bin[ii] = (short)jb[u];                      // kept resident for the bootstrap replicates
+            }
+        }
+#pragma unroll
+        for (int tn = 0; tn < 2; ++tn) {
+            if (turn == tn) {
+#pragma unroll
+                for (int u = 0; u < VP_UNROLL; ++u)
+                    if (jb[u] >= 0 && m[u] != 0u) {
+                        my_sum[jb[u] * VP_COLS] += BOOT ? phi[u] * (double)m[u] : phi[u];
+                        my_cnt[jb[u] * VP_COLS] += m[u];
+                    }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    // fold: warp w handles bins w, w + VP_WARPS, ...; lane l reads column l % 16 of warp-slices l / 16, l / 16 + 2, ...
+    for (int jb = warp; jb < nb; jb += VP_WARPS) {
+        double s = 0.0;
+        unsigned long long c = 0ULL;
+        for (int wv = lane >> 4; wv < VP_WARPS; wv += 2) {
+            s += s_sum[(wv * nb + jb) * VP_COLS + (lane & (VP_COLS - 1))];
+            c += s_cnt[(wv * nb + jb) * VP_COLS + (lane & (VP_COLS - 1))];
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            c += __shfl_xor_sync(0xffffffffu, c, o);
+        }
+        if (lane == 0) {
+            a.sumphi[(long long)blockIdx.x * nb + jb] = s;
+            a.counts[(long long)blockIdx.x * nb + jb] = c;
+        }
+    }
+}
+
+// one warp per bin: lanes stride over the block partials, fixed shuffle tree (deterministic)
+__global__ void k_veff_reduce(int nblocks, int nbins, const unsigned long long* __restrict__ counts,
+                              const double* __restrict__ sumphi, long long* __restrict__ out_c, double* __restrict__ out_s) {
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (j >= nbins) return;
+    double s = 0.0; unsigned long long c = 0ULL;
+    for (int b = lane; b < nblocks; b += 32) { s += sumphi[(long long)b * nbins + j]; c += counts[(long long)b * nbins + j]; }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        c += __shfl_xor_sync(0xffffffffu, c, o);
+    }
+    if (lane == 0) { out_c[j] = (long long)c; out_s[j] = s; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Veff launch plan: lane-private histograms whenever they fit in shared memory, atomics otherwise
+// ------------------------------------------------------------------------------------------------
+struct VeffPlan { bool priv; int blocks, threads; size_t smem; };
+static VeffPlan veff_plan(const lf_ctx* c, long long n, int nbins) {
+    VeffPlan p;
+    const size_t priv = sizeof(double) * (nbins + 1) * 16 + (size_t)VP_WARPS * nbins * VP_COLS * (sizeof(double) + sizeof(unsigned)) +
+                        sizeof(double2) * STREAM_LOG_N + sizeof(double) * EXP_TAB_N;
+    if (priv <= VP_SMEM_MAX) {
+        int per_sm = (int)std::min<size_t>(8, (size_t)(227 * 1024) / (priv + 1024));
+        per_sm = std::max(per_sm, 1);
+        p.priv = true; p.threads = 32 * VP_WARPS; p.smem = priv;
+        p.blocks = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * per_sm,
+                                                                     (n + p.threads * VP_UNROLL - 1) / (p.threads * VP_UNROLL)));
+    } else {
+        p.priv = false; p.threads = 256;
+        p.smem = sizeof(double) * (nbins + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * (size_t)nbins;
+        p.blocks = (int)std::min<long long>((long long)c->sm_count * 8, (n + 255) / 256);
+    }
+    return p;
+}
+template <int MODE>
+static void veff_launch(const VeffPlan& p, const VeffArgs& a, cudaStream_t st) {
+    if (p.priv) k_veff_priv<MODE><<<p.blocks, p.threads, p.smem, st>>>(a);
+    else k_veff<MODE><<<p.blocks, p.threads, p.smem, st>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Veff host entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const double* lum, const int64_t* field_ind,
+                           int32_t nfields, const double* flim, double alpha, double fcmin, double sum_omega,
+                           double vol_int, const double* vol_per_source, const uint8_t* valid,
+                           const double* edges, int32_t nbins, double* phi_out, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_veff_bin: null context");
+    if (n <= 0 || !flux || !lum || !field_ind || !flim || !edges || !counts || !sumphi) return fail("lf_veff_bin: bad arguments");
+    if (nfields < 1 || nfields > LF_MAX_FIELDS) return fail("lf_veff_bin: nfields out of range");
+    if (nbins < 1 || nbins > VEFF_MAX_BINS) return fail("lf_veff_bin: nbins out of range");
+    if (field_ind[0] != 0 || field_ind[nfields] != n) return fail("lf_veff_bin: field_ind must run from 0 to n");
+    CK(cudaSetDevice(c->device));
+    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
+    dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
+    const size_t nb = sizeof(double) * (size_t)n;
+    double* d_flux = nullptr; double* d_vol = nullptr; unsigned char* d_valid = nullptr;
+    CK(cudaMalloc(&d_flux, nb));
+    CK(cudaMalloc(&c->v_lum, nb));
+    CK(cudaMalloc(&c->v_phi, nb));
+    CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
+    const VeffPlan plan = veff_plan(c, n, nbins);
+    const int blocks = plan.blocks;
+    c->v_blocks = blocks; c->v_nbins = nbins; c->vN = n;
+    CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)blocks * nbins));
+    CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)blocks * nbins));
+    CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
+    CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
+    CK(cudaMalloc(&c->v_bin, sizeof(short) * (size_t)n));
+    CK(cudaMemcpyAsync(d_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
+    if (vol_per_source) {
+        CK(cudaMalloc(&d_vol, nb));
+        CK(cudaMemcpyAsync(d_vol, vol_per_source, nb, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (valid) {
+        CK(cudaMalloc(&d_valid, (size_t)n));
+        CK(cudaMemcpyAsync(d_valid, valid, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    }
+    VeffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.flux = d_flux; a.lum = c->v_lum; a.vol = d_vol; a.valid = d_valid; a.phi = c->v_phi;
+    a.K = nfields;
+    for (int k = 0; k <= nfields; ++k) a.field_ind[k] = field_ind[k];
+    const bool modified = fcmin != 0.0;
+    double aa = (2.0 * fcmin - 1.0) * (2.0 * fcmin - 1.0);
+    for (int k = 0; k < nfields; ++k) {
+        a.F50[k] = 1.0e-17 * flim[k];
+        // inverse_fleming, reference operation order (VmaxLumFunc.py:164-167)
+        double b = -1.0 * pow(fabs(aa / (1.0 - aa)) * pow(alpha, -2.0), 0.5);
+        a.ftau[k] = a.F50[k] * pow(10.0, b);
+        a.invF50[k] = 1.0 / a.F50[k];
+        a.inv_ftau[k] = 1.0 / a.ftau[k];
+    }
+    a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.vol_int = vol_int; a.modified = modified ? 1 : 0;
+    a.inv_pref_vol = 1.0 / (a.pref * vol_int); a.tables = c->d_tables;
+    a.edges = c->v_edges; a.nbins = nbins; a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = nullptr; a.bin = c->v_bin;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    veff_launch<0>(plan, a, c->stream);
+    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    if (phi_out) CK(cudaMemcpyAsync(phi_out, c->v_phi, nb, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms; }
+    cudaFree(d_flux);
+    if (d_vol) cudaFree(d_vol);
+    if (d_valid) cudaFree(d_valid);
+    return 0;
+}
+
+extern "C" int lf_bin_weights(lf_ctx* c, int64_t n, const double* lum, const double* phi, const double* edges,
+                              int32_t nbins, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_bin_weights: null context");
+    if (n <= 0 || !lum || !phi || !edges || !counts || !sumphi) return fail("lf_bin_weights: bad arguments");
+    if (nbins < 1 || nbins > VEFF_MAX_BINS) return fail("lf_bin_weights: nbins out of range");
+    CK(cudaSetDevice(c->device));
+    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
+    dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
+    const size_t nb = sizeof(double) * (size_t)n;
+    CK(cudaMalloc(&c->v_lum, nb));
+    CK(cudaMalloc(&c->v_phi, nb));
+    CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
+    const VeffPlan plan = veff_plan(c, n, nbins);
+    const int blocks = plan.blocks;
+    c->v_blocks = blocks; c->v_nbins = nbins; c->vN = n;
+    CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)blocks * nbins));
+    CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)blocks * nbins));
+    CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
+    CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
+    CK(cudaMalloc(&c->v_bin, sizeof(short) * (size_t)n));
+    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_phi, phi, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
+    VeffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = nbins;
+    a.counts = c->v_counts; a.sumphi = c->v_sums; a.bin = c->v_bin;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    veff_launch<2>(plan, a, c->stream);
+    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (cudaEventQuery(c->ev1) == cudaSuccess) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
+    return 0;
+}
+
+// multiplicities of one bootstrap replicate: n uniform draws with replacement, 4 per Philox call
+__global__ void k_boot_draw(long long n, uint32_t k0, uint32_t k1, uint32_t rep_lo, uint32_t rep_hi, int* __restrict__ mult) {
+    const long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x;       // Philox call q yields draws 4q .. 4q+3
+    if (4 * q >= n) return;
+    uint32_t r[4];
+    philox4x32_10((uint32_t)q, (uint32_t)(q >> 32), rep_lo, rep_hi, k0, k1, r);
+#pragma unroll
+    for (int t = 0; t < 4; ++t)
+        if (4 * q + t < n) atomicAdd(&mult[(long long)(((unsigned long long)r[t] * (unsigned long long)n) >> 32)], 1);
+}
+
+
+extern "C" int lf_boot_bin_device(lf_ctx* c, uint64_t seed, int64_t replicate, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_boot_bin_device: null context");
+    if (!c->v_phi || c->vN <= 0) return fail("lf_boot_bin_device: call lf_veff_bin or lf_bin_weights first");
+    if (!counts || !sumphi) return fail("lf_boot_bin_device: bad arguments");
+    if (c->vN >= (1LL << 32)) return fail("lf_boot_bin_device: more than 2^32 sources");
+    CK(cudaSetDevice(c->device));
+    if (!c->v_mult) CK(cudaMalloc(&c->v_mult, sizeof(int) * (size_t)c->vN));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(c->v_mult, 0, sizeof(int) * (size_t)c->vN, c->stream));
+    const long long calls = (c->vN + 3) / 4;
+    k_boot_draw<<<(unsigned)((calls + 255) / 256), 256, 0, c->stream>>>(c->vN, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                                      (uint32_t)replicate, (uint32_t)((uint64_t)replicate >> 32), c->v_mult);
+    VeffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
+    a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult; a.bin = c->v_bin;
+    const int nbins = c->v_nbins, blocks = c->v_blocks;
+    const VeffPlan plan = veff_plan(c, c->vN, nbins);
+    veff_launch<1>(plan, a, c->stream);
+    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
+    return 0;
+}
+
+extern "C" int lf_boot_bin(lf_ctx* c, const int32_t* mult, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_boot_bin: null context");
+    if (!c->v_phi || c->vN <= 0) return fail("lf_boot_bin: call lf_veff_bin first");
+    if (!mult || !counts || !sumphi) return fail("lf_boot_bin: bad arguments");
+    CK(cudaSetDevice(c->device));
+    if (!c->v_mult) CK(cudaMalloc(&c->v_mult, sizeof(int) * (size_t)c->vN));
+    CK(cudaMemcpyAsync(c->v_mult, mult, sizeof(int) * (size_t)c->vN, cudaMemcpyHostToDevice, c->stream));
+    VeffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
+    a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult; a.bin = c->v_bin;
+    const int nbins = c->v_nbins, blocks = c->v_blocks;
+    const VeffPlan plan = veff_plan(c, c->vN, nbins);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    veff_launch<1>(plan, a, c->stream);
+    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (cudaEventQuery(c->ev1) == cudaSuccess) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
+    return 0;
+}
+
+int veff_init(lf_ctx* c) {
+    (void)c;
+    {
+        const int atom_smem = (int)(sizeof(double) * (VEFF_MAX_BINS + 1) + (sizeof(double) + sizeof(unsigned long long)) * 8 * VEFF_MAX_BINS);
+        CK(cudaFuncSetAttribute(k_veff<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, atom_smem));
+        CK(cudaFuncSetAttribute(k_veff<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, atom_smem));
+        CK(cudaFuncSetAttribute(k_veff<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, atom_smem));
+    }
+    CK(cudaFuncSetAttribute(k_veff_priv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
+    CK(cudaFuncSetAttribute(k_veff_priv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
+    CK(cudaFuncSetAttribute(k_veff_priv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
+    return 0;
+}
