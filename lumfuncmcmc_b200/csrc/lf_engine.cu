@@ -939,8 +939,9 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
     CK(cudaMalloc(&c->d_lum, nb));
     CK(cudaMalloc(&c->d_Lsrc, nb));
     double* d_tmp = nullptr; double* d_scratch = nullptr;
-    CK(cudaMalloc(&d_tmp, sizeof(double) * 3 * 1024));
-    CK(cudaMalloc(&d_scratch, nb));
+    DevBufs scratch;                               // released on every exit path
+    CK(scratch.alloc(&d_tmp, sizeof(double) * 3 * 1024));
+    CK(scratch.alloc(&d_scratch, nb));
     std::vector<double> h_tmp(3 * 1024);
     const int T = 256;
     const unsigned G = (unsigned)((n + T - 1) / T);
@@ -998,8 +999,6 @@ extern "C" int lf_set_sources(lf_ctx* c, int64_t n, const double* lum, const dou
         }
     }
     CK(cudaStreamSynchronize(c->stream));
-    cudaFree(d_tmp);
-    cudaFree(d_scratch);
     a.src2 = c->d_src2; a.src2f = c->d_src2f; a.lum = c->d_lum; a.flux = c->d_flux; a.z = c->d_z; a.om_arr = c->d_om;
     c->have_sources = true;
     return 0;

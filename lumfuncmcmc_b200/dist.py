@@ -49,6 +49,57 @@ def reduce_partials(partial, group=None):
     return partial
 
 
+def walker_slice(W, rank, world):
+    """Walkers [lo, hi) of a W-walker ensemble that rank r evaluates under walker sharding (contiguous, balanced)."""
+    return shard_bounds(W, rank, world)
+
+
+def gather_walker_results(local, W, group=None):
+    """All-gather of the per-rank result slices back into the full (W,) vector, every rank gets all of it."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    sizes = [walker_slice(W, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in sizes)
+    pad = torch.full((width,), float('nan'), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    return torch.cat([p[:hi - lo] for p, (lo, hi) in zip(parts, sizes)])
+
+
+class WalkerShardedLikelihood:
+    """Small catalogues: every rank holds ALL sources and evaluates its slice of the walkers; the only
+    exchange is the all-gather of W/world results -- no sum over ranks, so results are bit-identical to one GPU."""
+
+    def __init__(self, inp, kind, device=None, group=None, precision='f64'):
+        import torch
+        import torch.distributed as dist
+        from .engine import LikelihoodEngine
+        self.torch, self.group = torch, group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.engine = LikelihoodEngine(inp, kind, device=self.device, precision=precision)
+        self.ndim = self.engine.ndim
+
+    def lnprob(self, thetas):
+        t = self.torch
+        th = np.ascontiguousarray(np.atleast_2d(np.asarray(thetas, dtype=np.float64)))
+        W = th.shape[0]
+        lo, hi = walker_slice(W, self.rank, self.world)
+        mine = self.engine.lnprob(th[lo:hi]) if hi > lo else np.zeros(0)
+        if self.world == 1:
+            return mine
+        local = t.from_numpy(np.ascontiguousarray(mine)).to(t.device('cuda', self.device))
+        return gather_walker_results(local, W, self.group).cpu().numpy()
+
+    def close(self):
+        self.engine.close()
+
+
 class ShardedLikelihood:
     """Public multi-GPU API: ``lnprob(thetas_host) -> lnprob_host`` with H2D, kernels, all-reduce, D2H.
 

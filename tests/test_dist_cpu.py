@@ -60,3 +60,34 @@ def test_shard_bounds_cover_everything_once():
             spans = [shard_bounds(n, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+
+
+def _gather_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    from lumfuncmcmc_b200.dist import gather_walker_results, walker_slice
+    os.environ['MASTER_ADDR'], os.environ['MASTER_PORT'] = '127.0.0.1', str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    out = {}
+    for W in (1, 2, 7, 100):
+        lo, hi = walker_slice(W, rank, world)
+        local = torch.arange(lo, hi, dtype=torch.float64) * 1.5 - 3.0
+        if hi > lo and lo == 0:
+            local[0] = float('-inf')
+        out[W] = gather_walker_results(local, W).numpy().copy()
+    ret[rank] = out
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_walker_sharding_gathers_the_full_vector_on_every_rank():
+    world, port = 2, 31000 + os.getpid() % 2000
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gather_worker, args=(world, port, ret), nprocs=world, join=True)
+    for W in (1, 2, 7, 100):
+        want = np.arange(W) * 1.5 - 3.0
+        want[0] = -np.inf
+        for r in range(world):
+            assert np.array_equal(ret[r][W], want)
