@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE ONLY -- CPU restatement (NumPy/SciPy) of the reference's hot path.
 
-This file is the *checker*: only ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
-``--impl reference`` legs of ``bench.py`` may import it.  The product (``lumfuncmcmc_b200``) never does, and
+This file is the *checker*: only ``tests/`` (the pytest suites and the ``tests/run_*.py`` multi-GPU / end-to-end
+check scripts), ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may
+import it.  The product (``lumfuncmcmc_b200``) never does, and
 has no CPU fallback.
 
 Each function restates one reference function on plain arrays (an "inputs" dict instead of ``self``), citing

@@ -1,6 +1,6 @@
 """BASELINE.json configs[0] and configs[2] end to end through the unchanged command-line drivers on one GPU.
 
-    python tools/config_runs.py [0|2|all] [host|device]
+    python tests/run_config_end_to_end.py [0|2|all] [host|device]
 
 configs[0]: run_lumfuncmcmc.py single-z Schechter + Fleming fit, synthetic 1e4-source catalogue drawn from known
             (logL*, logphi*, alpha) = (42.5, -2.0, -1.49), 100 walkers x 1000 steps.

@@ -1,6 +1,6 @@
 """Run under torchrun (one rank per GPU): source-sharded lnprob over NCCL equals the single-GPU result and the oracle.
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tools/multi_gpu_parity.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 tests/run_multi_gpu_parity.py
 """
 import os
 import sys

@@ -327,7 +327,7 @@ def test_compressed_catalogue_midsize_against_brute_force_and_oracle():
 def test_peer_memory_allreduce_degenerates_to_identity_on_one_rank(golden):
     """world = 1: the peer-memory exchange kernel (stores, flag, wait, rank-ordered sum) returns the vector unchanged,
     for both buffer parities and for lengths that are not a multiple of the 256-walker chunk.  The multi-rank case is
-    exercised by tools/multi_gpu_parity.py under torchrun (profiles/r01_multi_gpu_parity_2gpu_p2p.log)."""
+    exercised by tests/run_multi_gpu_parity.py under torchrun (profiles/r01_multi_gpu_parity_2gpu_p2p.log)."""
     import torch
     g = golden('free_k3_fixal')
     eng = _engine(g, 'free')
