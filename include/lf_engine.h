@@ -91,8 +91,11 @@ int lf_set_grid(lf_ctx* ctx, const double* logL, const double* zarr, const doubl
  * with (xi, w) built from the catalogue by lumfuncmcmc_b200/compress.py (piecewise Chebyshev interpolation of t in
  * g = log10 flux; truncation ~1e-15 per source for every alpha_c <= the alpha_max it was built for).  cfield_ind[K+1]
  * delimits the pseudo-sources of each field.  lf_set_sources must have been called with the real sources first: their
- * sufficient statistics, the classification bounds and the literal kernels keep using them.  M = 0 switches back. */
-int lf_set_compressed_sources(lf_ctx* ctx, int64_t M, const double* xi, const double* w, const int64_t* cfield_ind);
+ * sufficient statistics, the classification bounds and the literal kernels keep using them.  Walkers with
+ * alpha_c > alpha_max (possible only when the prior gate is off) are evaluated by the literal kernels on the real
+ * sources.  M = 0 switches back. */
+int lf_set_compressed_sources(lf_ctx* ctx, int64_t M, const double* xi, const double* w, const int64_t* cfield_ind,
+                              double alpha_max);
 
 /* Which walkers' quadrature term this context subtracts: walkers w with w % nshare == share.
  * Default (0, 1) = all.  Multi-GPU source sharding: rank r calls (r, world) and the per-rank outputs are

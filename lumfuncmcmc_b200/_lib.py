@@ -73,7 +73,7 @@ def load():
     lib.lf_fp64_peak.argtypes = [vp, C.c_int32, dp, dp]
     lib.lf_mufu_peak.argtypes = [vp, C.c_int32, dp, dp]
     lib.lf_last_kernel_ms.argtypes = [vp, dp]
-    lib.lf_set_compressed_sources.argtypes = [vp, i64, vp, vp, vp]
+    lib.lf_set_compressed_sources.argtypes = [vp, i64, vp, vp, vp, C.c_double]
     lib.lf_sampler_run.argtypes = [vp, vp, i64, i64, C.c_uint64, C.c_double, i64, vp, vp, vp, vp, vp]
     lib.lf_sampler_last_ms.argtypes = [vp, dp]
     lib.lf_cosmo_distances.argtypes = [C.c_int32, vp, vp, i64, i64, vp, vp, vp]

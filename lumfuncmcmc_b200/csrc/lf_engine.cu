@@ -128,6 +128,7 @@ __global__ void k_prologue(KArgs a) {
         if (a.model == LF_MODEL_FREE) {
             double b = -1.0 * sqrt(a.fcA2 * pow(alpha_c, -2.0));   // inverse_fleming, VmaxLumFunc.py:164-165
             if (!(alpha_c > 0.0)) rok = 0;
+            if (a.csrc != nullptr && !(alpha_c <= a.c_alpha_max)) rok = 0;      // outside the compressed catalogue's error bound
             double F50 = 1.0e-17 * th[p + k];
             double lgF = log10(F50);
             double ftau = F50 * pow(10.0, b);
@@ -1092,7 +1093,8 @@ __global__ void k_derive_compressed(long long m, const double* __restrict__ xi, 
     out[2 * i + 1] = make_double2(w[i], 0.0);
 }
 
-extern "C" int lf_set_compressed_sources(lf_ctx* c, int64_t M, const double* xi, const double* w, const int64_t* cfield_ind) {
+extern "C" int lf_set_compressed_sources(lf_ctx* c, int64_t M, const double* xi, const double* w, const int64_t* cfield_ind,
+                                         double alpha_max) {
     if (!c) return fail("lf_set_compressed_sources: null context");
     if (c->cfg.model != LF_MODEL_FREE) return fail("lf_set_compressed_sources: only the free-completeness model has a compressed form");
     if (c->cfg.precision != LF_PREC_F64) return fail("lf_set_compressed_sources: FP64 only");
@@ -1101,7 +1103,7 @@ extern "C" int lf_set_compressed_sources(lf_ctx* c, int64_t M, const double* xi,
     dfree(c->d_csrc);
     c->ka.csrc = nullptr; c->ka.M = 0;
     if (M == 0) return 0;
-    if (M < 0 || !xi || !w || !cfield_ind) return fail("lf_set_compressed_sources: bad arguments");
+    if (M < 0 || !xi || !w || !cfield_ind || !(alpha_max > 0.0)) return fail("lf_set_compressed_sources: bad arguments");
     const int K = c->cfg.nfields;
     if (cfield_ind[0] != 0 || cfield_ind[K] != M) return fail("lf_set_compressed_sources: cfield_ind must run from 0 to M");
     for (int k = 0; k < K; ++k) {
@@ -1122,7 +1124,7 @@ extern "C" int lf_set_compressed_sources(lf_ctx* c, int64_t M, const double* xi,
     k_derive_compressed<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(M, d_xi, d_w, c->ka.fcap, c->d_csrc);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
-    c->ka.csrc = c->d_csrc; c->ka.M = M;
+    c->ka.csrc = c->d_csrc; c->ka.M = M; c->ka.c_alpha_max = alpha_max;
     for (int k = 0; k <= K; ++k) c->ka.cfield_ind[k] = cfield_ind[k];
     return 0;
 }

@@ -80,6 +80,7 @@ struct KArgs {
     const double2* src2;               // FREE: (log10 flux, flux)   Z: (lum, z)
     const double2* csrc;               // compressed catalogue, two entries per pseudo-source: (xi = log10 f, min(10^xi, fcap)), (weight, -); or NULL
     long long M; long long cfield_ind[LF_MAX_FIELDS + 1];
+    double c_alpha_max;                // largest alpha_c the compressed catalogue is accurate for
     const float2* src2f;               // LF_PREC_F32 copy: FREE (log10 f + 17, f * 1e17)   Z: (lum - 42, z - z2)
     int precision;                     // LF_PREC_F64 | LF_PREC_F32 (arithmetic of the walker x source loop only)
     const double* lum;

@@ -212,12 +212,13 @@ class LikelihoodEngine(_VeffOps):
         from .compress import compress_sources
         xi, w, cfi = compress_sources(np.log10(flux), field_ind, alpha_max, nodes=nodes, bin_dex=bin_dex)
         xi, w = _f64(xi), _f64(w)
-        _lib.check(self.lib.lf_set_compressed_sources(self._ctx, xi.shape[0], _ptr(xi), _ptr(w), _ptr(cfi)), self.lib)
+        _lib.check(self.lib.lf_set_compressed_sources(self._ctx, xi.shape[0], _ptr(xi), _ptr(w), _ptr(cfi), float(alpha_max)),
+                   self.lib)
         self.npseudo = int(xi.shape[0])
         return self.npseudo
 
     def uncompress_catalogue(self):
-        _lib.check(self.lib.lf_set_compressed_sources(self._ctx, 0, None, None, None), self.lib)
+        _lib.check(self.lib.lf_set_compressed_sources(self._ctx, 0, None, None, None, 1.0), self.lib)
         self.npseudo = 0
 
     # ------------------------------------------------------------------------------------------

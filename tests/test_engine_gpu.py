@@ -320,6 +320,12 @@ def test_compressed_catalogue_midsize_against_brute_force_and_oracle():
     rel = _assert_parity(b, a, rtol=1e-12)
     _assert_parity(b[:16], lf_oracle.lnprob_batch(inp, 'free', th[:16]))
     print('compressed: %d pseudo-sources for %d sources, max rel diff vs brute force %.2e' % (comp.npseudo, 200000, rel))
+    # without the prior gate a walker may sit above the alpha_c the weights were built for: it must take the literal
+    # kernels on the real sources, not the interpolant
+    steep = th[:4].copy()
+    steep[:, -1] = 9.5
+    _assert_parity(comp.lnlike(steep), brute.lnlike(steep), rtol=1e-12)
+    assert comp.last_call_info()['literal'] == 4
     brute.close()
     comp.close()
 
