@@ -190,6 +190,9 @@ def run_reference(args):
             "config": {"workload": workload_name(args), "sample": sample},
             "cpu_baseline": {"value": value, "unit": "terms/s", "cores": procs, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "ensemble_steps": {"value": value / (float(args.nsources) * args.gpus * args.walkers), "unit": "ensemble steps/s",
+                               "note": "derived: the reference's cost is exactly linear in walkers x sources, one ensemble update = "
+                                       "one lnprob per walker over %g x %d sources" % (args.nsources, args.gpus)},
             "gpu_launches": 0}
     print(json.dumps(line))
 
