@@ -36,8 +36,14 @@ __device__ __forceinline__ int bin_of_rep(double L, const double* e, int col, in
     if (!(L >= e0) || !(L < enb)) return -1;
     int j = (int)((L - e0) * scale);
     j = j < 0 ? 0 : (j > nb - 1 ? nb - 1 : j);
-    while (j > 0 && L < e[j * 16 + col]) --j;
-    while (j < nb - 1 && L >= e[(j + 1) * 16 + col]) ++j;
+    // for (near-)uniform edges the candidate is off by at most one: branch-free fix-up, verified against the exact edges
+    j -= (int)(L < e[j * 16 + col]);
+    j += (int)(L >= e[(j + 1) * 16 + col]);
+    j = j < 0 ? 0 : (j > nb - 1 ? nb - 1 : j);
+    if (!(L >= e[j * 16 + col]) || !(L < e[(j + 1) * 16 + col])) {          // irregular edges: walk (rare)
+        while (j > 0 && L < e[j * 16 + col]) --j;
+        while (j < nb - 1 && L >= e[(j + 1) * 16 + col]) ++j;
+    }
     return j;
 }
 
@@ -144,56 +150,83 @@ __global__ void __launch_bounds__(32 * VP_WARPS) k_veff_priv(VeffArgs a) {
     double* my_sum = s_sum + warp * nb * VP_COLS + (lane & (VP_COLS - 1));
     unsigned* my_cnt = s_cnt + warp * nb * VP_COLS + (lane & (VP_COLS - 1));
     const int turn = lane >> 4;
-    const long long stride = (long long)gridDim.x * blockDim.x;
     const double alpha_log10e = a.alpha * KS[12];
-    int k = 0;                                  // sources are field-sorted: the field index only moves forward
-    // whole warps iterate together (the trip count is computed from the warp's first lane) so that __syncwarp is legal
-    for (long long i0 = blockIdx.x * (long long)blockDim.x + (threadIdx.x & ~31); i0 < a.n; i0 += stride * VP_UNROLL) {
-        const long long i = i0 + lane;
+    // Each block streams ONE contiguous chunk of the catalogue: offsets inside the chunk fit in 32 bits and the base
+    // pointers are formed once, so the loop carries no 64-bit index arithmetic; the field boundaries that fall inside
+    // the chunk and the per-field constants sit in shared memory.
+    constexpr int TRIP = 32 * VP_WARPS * VP_UNROLL;
+    const long long per_block = ((a.n + gridDim.x - 1) / gridDim.x + TRIP - 1) / TRIP * TRIP;
+    const long long start = (long long)blockIdx.x * per_block;
+    const int len = (int)(a.n - start < per_block ? (a.n - start > 0 ? a.n - start : 0) : per_block);
+    __shared__ int s_fb[LF_MAX_FIELDS + 1];
+    __shared__ double s_fk[LF_MAX_FIELDS][4];
+    if (MODE == 0 && threadIdx.x < a.K) {
+        const long long b = a.field_ind[threadIdx.x + 1] - start;
+        s_fb[threadIdx.x] = (int)(b < 0 ? 0 : (b > len ? len : b));          // end of field k inside the chunk
+        s_fk[threadIdx.x][0] = a.F50[threadIdx.x]; s_fk[threadIdx.x][1] = a.invF50[threadIdx.x];
+        s_fk[threadIdx.x][2] = a.ftau[threadIdx.x]; s_fk[threadIdx.x][3] = a.inv_ftau[threadIdx.x];
+    }
+    __syncthreads();
+    const double* __restrict__ p_lum = a.lum ? a.lum + start : nullptr;
+    const double* __restrict__ p_flux = a.flux ? a.flux + start : nullptr;
+    const double* __restrict__ p_vol = a.vol ? a.vol + start : nullptr;
+    const unsigned char* __restrict__ p_valid = a.valid ? a.valid + start : nullptr;
+    const int* __restrict__ p_mult = a.mult ? a.mult + start : nullptr;
+    double* __restrict__ p_phi = a.phi + start;
+    short* __restrict__ p_bin = a.bin + start;
+    const bool modified = a.modified != 0;
+    int k = 0, kend = MODE == 0 ? s_fb[0] : 0;  // sources are field-sorted: the field index only moves forward
+    double F50 = 0.0, iF50 = 0.0, ftau = 0.0, iftau = 0.0;
+    if (MODE == 0) { F50 = s_fk[0][0]; iF50 = s_fk[0][1]; ftau = s_fk[0][2]; iftau = s_fk[0][3]; }
+    // whole warps iterate together (the trip count depends on the block only) so that __syncwarp is legal
+    for (int t0 = 0; t0 < len; t0 += TRIP) {
         double lum[VP_UNROLL], phi[VP_UNROLL], flux[VP_UNROLL], vol[VP_UNROLL];
         unsigned m[VP_UNROLL];
         int jb[VP_UNROLL];
         bool ok[VP_UNROLL];
 #pragma unroll
         for (int u = 0; u < VP_UNROLL; ++u) {                                // all loads of the trip first
-            const long long ii = i + u * stride;
-            const bool in = ii < a.n;
+            const int off = t0 + u * (32 * VP_WARPS) + threadIdx.x;
+            const bool in = off < len;
             m[u] = in ? 1u : 0u;
             ok[u] = in;
             phi[u] = 0.0;
             if (BOOT) {                                                      // replicate: resident bin index, weight, multiplicity
-                jb[u] = in ? (int)__ldcs(a.bin + ii) : -1;
-                m[u] = in ? (unsigned)__ldcs(a.mult + ii) : 0u;
-                phi[u] = in ? __ldcs(a.phi + ii) : 0.0;
+                jb[u] = in ? (int)__ldcs(p_bin + off) : -1;
+                m[u] = in ? (unsigned)__ldcs(p_mult + off) : 0u;
+                phi[u] = in ? __ldcs(p_phi + off) : 0.0;
                 continue;
             }
-            lum[u] = in ? __ldcs(a.lum + ii) : -1.0e300;                     // below every edge: lands in no bin
+            lum[u] = in ? __ldcs(p_lum + off) : -1.0e300;                    // below every edge: lands in no bin
             if (MODE == 2) {
-                phi[u] = in ? __ldcs(a.phi + ii) : 0.0;
+                phi[u] = in ? __ldcs(p_phi + off) : 0.0;
             } else {
-                flux[u] = in ? __ldcs(a.flux + ii) : 1.0;
-                vol[u] = (in && a.vol) ? __ldcs(a.vol + ii) : a.vol_int;
-                if (in && a.valid) ok[u] = a.valid[ii] != 0;
+                flux[u] = in ? __ldcs(p_flux + off) : 1.0;
+                vol[u] = (in && p_vol) ? __ldcs(p_vol + off) : a.vol_int;
+                if (in && p_valid) ok[u] = p_valid[off] != 0;
             }
         }
         if (MODE == 0) {
 #pragma unroll
             for (int u = 0; u < VP_UNROLL; ++u) {
-                const long long ii = i + u * stride;
-                while (k + 1 < a.K && ii >= a.field_ind[k + 1]) ++k;
-                const double icomp = inv_fleming_stream(flux[u], a.F50[k], a.invF50[k], alpha_log10e, a.alpha, a.ftau[k],
-                                                        a.inv_ftau[k], a.modified != 0, s_exp, s_logm);
-                const double ipv = a.vol ? 1.0 / (a.pref * vol[u]) : a.inv_pref_vol;
+                const int off = t0 + u * (32 * VP_WARPS) + threadIdx.x;
+                while (off >= kend && k + 1 < a.K) {                         // next field (rare)
+                    ++k;
+                    kend = s_fb[k];
+                    F50 = s_fk[k][0]; iF50 = s_fk[k][1]; ftau = s_fk[k][2]; iftau = s_fk[k][3];
+                }
+                const double icomp = inv_fleming_stream(flux[u], F50, iF50, alpha_log10e, a.alpha, ftau, iftau, modified, s_exp, s_logm);
+                const double ipv = p_vol ? 1.0 / (a.pref * vol[u]) : a.inv_pref_vol;
                 phi[u] = ok[u] ? icomp * ipv : 0.0;                          // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
-                if (ii < a.n) __stcs(a.phi + ii, phi[u]);
+                if (off < len) __stcs(p_phi + off, phi[u]);
             }
         }
         if (!BOOT) {
 #pragma unroll
             for (int u = 0; u < VP_UNROLL; ++u) {
-                const long long ii = i + u * stride;
+                const int off = t0 + u * (32 * VP_WARPS) + threadIdx.x;
                 jb[u] = bin_of_rep(lum[u], s_edges, lane & 15, nb, e0, enb, scale);
-                if (ii < a.n) a.bin[ii] = (short)jb[u];                      // kept resident for the bootstrap replicates
+                if (off < len) p_bin[off] = (short)jb[u];                    // kept resident for the bootstrap replicates
             }
         }
 #pragma unroll

@@ -15,7 +15,7 @@ for l in txt.splitlines():
             ins.append((int(m.group(1), 16), m.group(2).strip()))
 loops = []
 for a, t in ins:
-    m = re.search(r'BRA\s+(?:\w+,\s*)?0x([0-9a-f]+)', t)
+    m = re.search(r'BRA(?:\.\w+)*\s+(?:!?\w+,\s*)?0x([0-9a-f]+)', t)
     if m and int(m.group(1), 16) < a:
         loops.append((int(m.group(1), 16), a))
 for lo, hi in loops:
