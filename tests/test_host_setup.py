@@ -72,3 +72,22 @@ def test_lnprob_without_gpu_fails_loudly():
     m = _build('free', n=200, nfields=2, seed=4)
     with pytest.raises(EngineError):
         m.lnprob(np.array([42.5, -2.0, -1.49, 2.72, 3.61, 4.56]))
+
+
+def test_linear_table_host_path_is_interp1d():
+    """Without a GPU (or below the size threshold) LinearTable evaluates numpy.interp = interp1d(kind='linear')."""
+    from scipy.interpolate import interp1d
+    from lumfuncmcmc_b200.setup_gpu import LinearTable
+    rng = np.random.default_rng(5)
+    xk = np.linspace(1.1, 2.0, 5001)
+    yk = np.sqrt(xk) * 321.0 + rng.normal(size=xk.size)
+    t, ref = LinearTable(xk, yk), interp1d(xk, yk)
+    x = np.concatenate([rng.uniform(1.1, 2.0, 20000), xk[:7], [xk[-1]]])
+    assert np.array_equal(t(x), ref(x))
+    assert t(1.5) == float(ref(1.5)) and np.array_equal(t(x[:6].reshape(2, 3)), ref(x[:6].reshape(2, 3)))
+    assert np.array_equal(t.x, xk) and np.array_equal(t.y, yk)
+    import pytest
+    with pytest.raises(ValueError):
+        t(np.array([2.5]))
+    with pytest.raises(ValueError):
+        LinearTable(xk[:1], yk[:1])
