@@ -462,16 +462,12 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
                 // Base 2 throughout: 2^(log2(10) lum_i - P2(z_i)), 11 FP64 instructions per term
                 const double L2T = 3.32192809488736234787;                              // log2(10)
                 const double a2 = aL * L2T, b2 = bL * L2T, c2 = cL * L2T;
-                // four sources in lock-step (four independent FP64 chains per thread), the next four prefetched
+                // four sources in lock-step (four independent FP64 chains per thread); groups are double-buffered in two
+                // register sets (no copies): the next group's loads are issued before the current group's arithmetic
                 const double2* __restrict__ ps = a.src2 + i0;
                 const int cnt = (int)(i1 - i0);
                 double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
-                double2 A0, A1, A2, A3;
-                int j = 0;
-                if (cnt >= 4) { A0 = __ldg(ps); A1 = __ldg(ps + 1); A2 = __ldg(ps + 2); A3 = __ldg(ps + 3); }
-                for (; j + 4 <= cnt; j += 4) {
-                    const double2 s0 = A0, s1 = A1, s2 = A2, s3 = A3;
-                    if (j + 8 <= cnt) { A0 = __ldg(ps + j + 4); A1 = __ldg(ps + j + 5); A2 = __ldg(ps + j + 6); A3 = __ldg(ps + j + 7); }
+                auto four = [&](const double2& s0, const double2& s1, const double2& s2, const double2& s3) {
                     const double d0 = fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2));
                     const double d1 = fma(L2T, s1.x, -fma(fma(a2, s1.y, b2), s1.y, c2));
                     const double d2 = fma(L2T, s2.x, -fma(fma(a2, s2.y, b2), s2.y, c2));
@@ -480,7 +476,17 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
                     e1 += exp2_full<false>(d1, s_exp_rep, rep16);
                     e2 += exp2_full<false>(d2, s_exp_rep, rep16);
                     e3 += exp2_full<false>(d3, s_exp_rep, rep16);
+                };
+                double2 A0, A1, A2, A3, B0, B1, B2, B3;
+                int j = 0;
+                if (cnt >= 4) { A0 = __ldg(ps); A1 = __ldg(ps + 1); A2 = __ldg(ps + 2); A3 = __ldg(ps + 3); }
+                for (; j + 8 <= cnt; j += 8) {
+                    B0 = __ldg(ps + j + 4); B1 = __ldg(ps + j + 5); B2 = __ldg(ps + j + 6); B3 = __ldg(ps + j + 7);
+                    four(A0, A1, A2, A3);
+                    if (j + 12 <= cnt) { A0 = __ldg(ps + j + 8); A1 = __ldg(ps + j + 9); A2 = __ldg(ps + j + 10); A3 = __ldg(ps + j + 11); }
+                    four(B0, B1, B2, B3);
                 }
+                if (j + 4 <= cnt) { four(A0, A1, A2, A3); j += 4; }
                 for (; j < cnt; ++j) {
                     const double2 s0 = __ldg(ps + j);
                     e0 += exp2_full<false>(fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2)), s_exp_rep, rep16);
