@@ -86,14 +86,15 @@ int lf_set_sources(lf_ctx* ctx, int64_t n, const double* lum, const double* flux
 int lf_set_grid(lf_ctx* ctx, const double* logL, const double* zarr, const double* DL_zarr,
                 const double* volume_part, const double* integ_part, const double* omega0);
 
-/* Optional (LF_MODEL_FREE): replace the fast kernels' walker x source loop by a weighted sum over M pseudo-sources,
+/* Optional (LF_MODEL_FREE, LF_MODEL_Z): replace the fast kernels' walker x source loop by a weighted sum over M pseudo-sources,
  *   sum_i t(g_i)  ->  sum_m w[m] t(xi[m]),   t(g) = ln fc(alpha_c (g - log10 F50)) / (1 - exp(-10^g / f_tau)),
  * with (xi, w) built from the catalogue by lumfuncmcmc_b200/compress.py (piecewise Chebyshev interpolation of t in
  * g = log10 flux; truncation ~1e-15 per source for every alpha_c <= the alpha_max it was built for).  cfield_ind[K+1]
  * delimits the pseudo-sources of each field.  lf_set_sources must have been called with the real sources first: their
  * sufficient statistics, the classification bounds and the literal kernels keep using them.  Walkers with
  * alpha_c > alpha_max (possible only when the prior gate is off) are evaluated by the literal kernels on the real
- * sources.  M = 0 switches back. */
+ * sources.  LF_MODEL_Z: xi are redshift nodes, w[m] = sum_i 10^lum_i l_m(z_i) (compress_sources_z), the term is
+ * sum_m w[m] 10^(-L*(xi[m])), and `alpha_max` is the largest |d(L_star)/dz| the weights are accurate for.  M = 0 switches back. */
 int lf_set_compressed_sources(lf_ctx* ctx, int64_t M, const double* xi, const double* w, const int64_t* cfield_ind,
                               double alpha_max);
 

@@ -74,3 +74,47 @@ def compress_sources(g, field_ind, alpha_max, nodes=12, bin_dex=None, chunk=1 <<
     xi = np.concatenate(xi_all) if xi_all else np.zeros(0)
     w = np.concatenate(w_all) if w_all else np.zeros(0)
     return xi, w, np.array(cfi, dtype=np.int64)
+
+
+def compress_sources_z(z, lum, field_ind, slope_max, nodes=12, bin_z=None, chunk=1 << 20):
+    """Pseudo-sources of the z-evolving model: the only term of its source sum that needs the W x N loop is
+    ``sum_i 10**(lum_i - L*(z_i)) = sum_i 10**lum_i h(z_i)`` with ``h(z) = 10**(-L*(z))`` the exponential of a quadratic
+    (reference lumfuncmcmc_z.py:63-67, :371) -- an entire function of z, so on bins of half-width
+    ``0.5 / (ln 10 * slope_max)`` its 12-node Chebyshev interpolant is exact to ~1e-15 for every walker whose
+    ``|dL*/dz| <= slope_max`` over the catalogue's redshift range.  Returns (xi, v, cfield_ind) with
+    ``v[m] = sum_{i in bin} 2**(log2(10) lum_i) l_m(z_i)``."""
+    z = np.asarray(z, dtype=np.float64)
+    L = np.exp2(3.32192809488736234787 * np.asarray(lum, dtype=np.float64))
+    fi = np.asarray(field_ind, dtype=np.int64)
+    m = int(nodes)
+    if bin_z is None:
+        bin_z = 1.0 / (np.log(10.0) * float(slope_max))
+    cn, bw = chebyshev_nodes(m)
+    xi_all, w_all, cfi = [], [], [0]
+    for k in range(len(fi) - 1):
+        zk, Lk = z[fi[k]:fi[k + 1]], L[fi[k]:fi[k + 1]]
+        if zk.size == 0:
+            cfi.append(cfi[-1])
+            continue
+        lo, hi = float(zk.min()), float(zk.max())
+        nb = max(1, int(np.ceil((hi - lo) / bin_z)))
+        width = (hi - lo) / nb if hi > lo else bin_z
+        W = np.zeros(nb * m)
+        occ = np.zeros(nb, dtype=bool)
+        for s0 in range(0, zk.size, chunk):
+            zz, LL = zk[s0:s0 + chunk], Lk[s0:s0 + chunk]
+            b = np.minimum(((zz - lo) / width).astype(np.int64), nb - 1)
+            u = np.clip(2.0 * (zz - (lo + b * width)) / width - 1.0, -1.0, 1.0)
+            B = lagrange_basis(u, cn, bw)
+            for j in range(m):
+                W += np.bincount(b * m + j, weights=B[:, j] * LL, minlength=nb * m)
+            occ |= np.bincount(b, minlength=nb) > 0
+        centres = lo + (np.arange(nb) + 0.5) * width
+        xi = (centres[:, None] + 0.5 * width * cn[None, :]).ravel()
+        keep = np.repeat(occ, m)
+        xi_all.append(xi[keep])
+        w_all.append(W[keep])
+        cfi.append(cfi[-1] + int(keep.sum()))
+    xi = np.concatenate(xi_all) if xi_all else np.zeros(0)
+    w = np.concatenate(w_all) if w_all else np.zeros(0)
+    return xi, w, np.array(cfi, dtype=np.int64)

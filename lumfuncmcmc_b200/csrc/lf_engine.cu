@@ -96,6 +96,8 @@ __global__ void k_prologue(KArgs a) {
             lb = LNLN10 + LN10 * Plo + fmin(c1 * dlo, c1 * dhi) - emax + s.lnom_min;
             if (!(emax < 690.0)) lb = -1.0e300;
             if (!(dlo > -40.0)) lb = -1.0e300;
+            // compressed catalogue: |dL*/dz| over the field's redshift range must stay inside the bound it was built for
+            if (a.csrc != nullptr && !(fmax(fabs(fma(2.0 * aL, s.z_min, bL)), fabs(fma(2.0 * aL, s.z_max, bL))) <= a.c_alpha_max)) lb = -1.0e300;
         }
     } else {
         const int K = a.K;
@@ -457,6 +459,15 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
                     sum += (double)(f0 + f1);
                 }
                 acc0 -= sum;
+            } else if (!LITERAL && a.csrc != nullptr) {
+                // compressed catalogue: sum_m v_m 2^(-P2(xi_m)) over this slab of pseudo-sources (compress_sources_z)
+                const double L2T = 3.32192809488736234787;
+                const double a2 = aL * L2T, b2 = bL * L2T, c2 = cL * L2T;
+                const long long m0 = (a.M * row) / a.n_src_slabs, m1 = (a.M * (row + 1)) / a.n_src_slabs;
+                for (long long m = m0; m < m1; ++m) {
+                    const double xi = __ldg(&a.csrc[2 * m]).x, v = __ldg(&a.csrc[2 * m + 1]).x;
+                    acc0 = fma(-v, exp2_full<false>(-fma(fma(a2, xi, b2), xi, c2), s_exp_rep, rep16), acc0);
+                }
             } else if (!LITERAL) {
                 // only sum_i 10^(lum_i - L*(z_i)) needs the walker x source loop; the rest is in P_LNPART0.
                 // Base 2 throughout: 2^(log2(10) lum_i - P2(z_i)), 11 FP64 instructions per term
@@ -1091,18 +1102,18 @@ extern "C" int lf_set_grid(lf_ctx* c, const double* logL, const double* zarr, co
 }
 
 __global__ void k_derive_compressed(long long m, const double* __restrict__ xi, const double* __restrict__ w, double fcap,
-                                    double2* __restrict__ out) {
+                                    double2* __restrict__ out, bool zmodel) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= m) return;
     const double g = xi[i];
-    out[2 * i] = make_double2(g, fmin(pow(10.0, g), fcap));
+    out[2 * i] = make_double2(g, zmodel ? 0.0 : fmin(pow(10.0, g), fcap));
     out[2 * i + 1] = make_double2(w[i], 0.0);
 }
 
 extern "C" int lf_set_compressed_sources(lf_ctx* c, int64_t M, const double* xi, const double* w, const int64_t* cfield_ind,
                                          double alpha_max) {
     if (!c) return fail("lf_set_compressed_sources: null context");
-    if (c->cfg.model != LF_MODEL_FREE) return fail("lf_set_compressed_sources: only the free-completeness model has a compressed form");
+    if (c->cfg.model == LF_MODEL_FIXED) return fail("lf_set_compressed_sources: the fixed-completeness source sum is already O(1) per walker");
     if (c->cfg.precision != LF_PREC_F64) return fail("lf_set_compressed_sources: FP64 only");
     if (!c->have_sources) return fail("lf_set_compressed_sources: call lf_set_sources first");
     CK(cudaSetDevice(c->device));
@@ -1118,8 +1129,11 @@ extern "C" int lf_set_compressed_sources(lf_ctx* c, int64_t M, const double* xi,
     }
     // every node must lie inside the range of fluxes the classification bounds were computed for
     for (int k = 0; k < K; ++k)
-        for (int64_t m = cfield_ind[k]; m < cfield_ind[k + 1]; ++m)
-            if (!(xi[m] >= c->ka.fs[k].g_min - 1.0e-9) || !(xi[m] == xi[m])) return fail("lf_set_compressed_sources: a node lies below the field's faintest source");
+        for (int64_t m = cfield_ind[k]; m < cfield_ind[k + 1]; ++m) {
+            const bool inside = c->cfg.model == LF_MODEL_FREE ? xi[m] >= c->ka.fs[k].g_min - 1.0e-9
+                                                              : (xi[m] >= c->ka.fs[k].z_min - 1.0e-9 && xi[m] <= c->ka.fs[k].z_max + 1.0e-9);
+            if (!inside || !(xi[m] == xi[m])) return fail("lf_set_compressed_sources: a node lies outside the range of the field's sources");
+        }
     double *d_xi = nullptr, *d_w = nullptr;
     DevBufs tmp;
     CK(tmp.alloc(&d_xi, sizeof(double) * M));
@@ -1127,7 +1141,7 @@ extern "C" int lf_set_compressed_sources(lf_ctx* c, int64_t M, const double* xi,
     CK(cudaMalloc(&c->d_csrc, sizeof(double2) * 2 * (size_t)M));
     CK(cudaMemcpy(d_xi, xi, sizeof(double) * M, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(d_w, w, sizeof(double) * M, cudaMemcpyHostToDevice));
-    k_derive_compressed<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(M, d_xi, d_w, c->ka.fcap, c->d_csrc);
+    k_derive_compressed<<<(unsigned)((M + 255) / 256), 256, 0, c->stream>>>(M, d_xi, d_w, c->ka.fcap, c->d_csrc, c->cfg.model == LF_MODEL_Z);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
     c->ka.csrc = c->d_csrc; c->ka.M = M; c->ka.c_alpha_max = alpha_max;
@@ -1190,7 +1204,7 @@ static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
     // relative cost of a quadrature point vs a source term
     double src_cost = model == LF_MODEL_FREE ? 1.0 : (model == LF_MODEL_Z ? 0.5 : 0.0);
     double quad_cost = model == LF_MODEL_FREE ? 1.5 : 0.6;
-    const long long n_eff = (c->d_csrc && model == LF_MODEL_FREE) ? c->ka.M : c->N;      // pseudo-sources when compressed
+    const long long n_eff = c->d_csrc ? c->ka.M : c->N;      // pseudo-sources when compressed
     double wsrc = src_cost * (double)n_eff, wq = quad_cost * (double)c->NQ;
     double tot = wsrc + wq;
     if (tot <= 0.0) { n_src = 1; n_quad = 1; return; }

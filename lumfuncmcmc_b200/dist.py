@@ -105,7 +105,7 @@ class ShardedLikelihood:
 
     ``inp`` is THIS rank's shard (already split, e.g. by :func:`shard_inputs`)."""
 
-    def __init__(self, inp, kind, device=None, group=None, precision='f64', exchange='nccl', wcap=4096):
+    def __init__(self, inp, kind, device=None, group=None, precision='f64', exchange='nccl', wcap=4096, compress=False):
         import torch
         import torch.distributed as dist
         from .engine import LikelihoodEngine
@@ -115,7 +115,7 @@ class ShardedLikelihood:
         self.rank = dist.get_rank(group) if self.world > 1 else 0
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.engine = LikelihoodEngine(inp, kind, device=self.device, quadrature_share=(self.rank, self.world),
-                                       precision=precision)
+                                       precision=precision, compress=compress)
         self.ndim = self.engine.ndim
         self._cap = 0
         if exchange not in ('nccl', 'p2p'):

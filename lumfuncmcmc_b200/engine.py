@@ -202,10 +202,17 @@ class LikelihoodEngine(_VeffOps):
         if tuple(quadrature_share) != (0, 1):
             self.set_quadrature_share(*quadrature_share)
         self.npseudo = 0
+        self._z_host, self._lum_host, self._fi_host = zz, lum, fi
+        self._z_pivots = tuple(cfg.z_pivots)
+        self._Lstar_lims = tuple(cfg.Lstar_lims)
         if compress:
-            if kind != 'free' or precision != 'f64':
-                raise ValueError("compress=True applies to the free-completeness model in FP64")
-            self.compress_catalogue(flux, fi, alpha_max=float(cfg.alpha_lims[1]), **(compress if isinstance(compress, dict) else {}))
+            if kind == 'fixed' or precision != 'f64':
+                raise ValueError("compress=True applies to the free-completeness and z-evolving models in FP64")
+            opts = compress if isinstance(compress, dict) else {}
+            if kind == 'free':
+                self.compress_catalogue(flux, fi, alpha_max=float(cfg.alpha_lims[1]), **opts)
+            else:
+                self.compress_catalogue_z(**opts)
 
     def compress_catalogue(self, flux, field_ind, alpha_max, nodes=12, bin_dex=None):
         """Switch the fast kernels' source sum to the weighted pseudo-source form (see :mod:`.compress`)."""
@@ -213,6 +220,20 @@ class LikelihoodEngine(_VeffOps):
         xi, w, cfi = compress_sources(np.log10(flux), field_ind, alpha_max, nodes=nodes, bin_dex=bin_dex)
         xi, w = _f64(xi), _f64(w)
         _lib.check(self.lib.lf_set_compressed_sources(self._ctx, xi.shape[0], _ptr(xi), _ptr(w), _ptr(cfi), float(alpha_max)),
+                   self.lib)
+        self.npseudo = int(xi.shape[0])
+        return self.npseudo
+
+    def compress_catalogue_z(self, slope_max=None, nodes=12, bin_z=None):
+        """z-evolving model: weighted pseudo-sources in redshift (see :func:`.compress.compress_sources_z`).  Walkers
+        whose |dL*/dz| exceeds ``slope_max`` over the catalogue's redshift range take the literal kernels."""
+        from .compress import compress_sources_z
+        if slope_max is None:                       # four times the steepest secant the prior box allows between pivots
+            gap = min(self._z_pivots[1] - self._z_pivots[0], self._z_pivots[2] - self._z_pivots[1])
+            slope_max = 4.0 * (self._Lstar_lims[1] - self._Lstar_lims[0]) / gap
+        xi, v, cfi = compress_sources_z(self._z_host, self._lum_host, self._fi_host, slope_max, nodes=nodes, bin_z=bin_z)
+        xi, v = _f64(xi), _f64(v)
+        _lib.check(self.lib.lf_set_compressed_sources(self._ctx, xi.shape[0], _ptr(xi), _ptr(v), _ptr(cfi), float(slope_max)),
                    self.lib)
         self.npseudo = int(xi.shape[0])
         return self.npseudo

@@ -167,7 +167,9 @@ class LFBase:
         eng = self._engines.get(kind)
         if eng is None:
             from .engine import LikelihoodEngine
-            eng = LikelihoodEngine(self.engine_inputs(), kind, device=self.device)
+            # opt-in: model.compress = True (or LF_COMPRESS=1) evaluates the source sum on weighted pseudo-sources
+            compress = (bool(getattr(self, 'compress', False)) or os.environ.get('LF_COMPRESS', '') == '1') and kind != 'fixed'
+            eng = LikelihoodEngine(self.engine_inputs(), kind, device=self.device, compress=compress)
             self._engines[kind] = eng
         return eng
 

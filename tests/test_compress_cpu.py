@@ -47,3 +47,27 @@ def test_single_source_and_degenerate_fields():
     assert abs((w * _t(xi, 4.0, -16.5)).sum() - exact) < 1e-12 * abs(exact)
     xi, w, cfi = compress_sources(np.zeros(0), np.array([0, 0]), alpha_max=7.0)
     assert len(xi) == 0 and list(cfi) == [0, 0]
+
+
+def test_z_model_pseudo_sources_reproduce_the_exponential_sum():
+    """sum_i 10**(lum_i - L*(z_i)) with a quadratic L*(z): weighted redshift nodes against the direct sum, for gentle and
+    for the steepest admitted evolution."""
+    from lumfuncmcmc_b200.compress import compress_sources_z
+    rng = np.random.default_rng(2)
+    n = 300000
+    z = rng.uniform(1.16, 1.90, n)
+    lum = 41.0 + rng.pareto(1.5, n) * 0.3
+    lum = np.minimum(lum, 44.5)
+    fi = np.array([0, n // 4, n])
+    slope_max = 60.0
+    xi, v, cfi = compress_sources_z(z, lum, fi, slope_max)
+    assert len(xi) < 5000 and cfi[-1] == len(xi)
+    for (aL, bL, cL) in ((0.0, 0.3, 42.0), (-0.9, 3.4, 39.5), (20.0, -60.0, 87.0), (-19.0, 58.0, 0.0)):
+        for k in (0, 1):
+            sl = slice(fi[k], fi[k + 1])
+            zz = z[sl]
+            assert np.max(np.abs(2 * aL * zz + bL)) <= slope_max
+            exact = np.sum(10 ** (lum[sl] - (aL * zz * zz + bL * zz + cL)))
+            xs = xi[cfi[k]:cfi[k + 1]]
+            approx = np.sum(v[cfi[k]:cfi[k + 1]] * 10 ** (-(aL * xs * xs + bL * xs + cL)))
+            assert abs(exact - approx) <= 1e-12 * abs(exact), (aL, bL, cL, k, exact, approx)

@@ -388,3 +388,24 @@ def test_device_resampled_bootstrap_equals_host_replay_of_the_philox_stream():
     # two independent 200-replicate variance estimates: each bin within a factor 2, the average over bins within 10 %
     assert np.all(np.abs(np.log(var_d / var_h)) < np.log(2.0)) and abs(np.mean(var_d / var_h) - 1.0) < 0.1
     eng.close()
+
+
+def test_compressed_catalogue_z_model(golden):
+    g = golden('z_k2_n800')
+    eng = _engine(g, 'z', compress=True)
+    assert eng.npseudo > 0
+    _assert_parity(eng.lnprob(g['thetas']), g['lnprob_ref'])
+    eng.close()
+    cat = synth.make_catalogue(200000, seed=24, evolve=(0.3, -0.2))
+    inp = synth.direct_inputs(cat, nknots=2048, size_ln=201, tabulated=True)
+    th = np.concatenate([synth.draw_thetas(inp, 'z', 64, seed=5, mode='near', scale=0.02),
+                         synth.draw_thetas(inp, 'z', 64, seed=6, mode='prior')])
+    brute, comp = _engine(inp, 'z'), _engine(inp, 'z', compress=True)
+    a, b = brute.lnprob(th), comp.lnprob(th)
+    rel = _assert_parity(b, a, rtol=1e-12)
+    info = comp.last_call_info()
+    assert info['fast'] >= 64
+    _assert_parity(b[:12], lf_oracle.lnprob_batch(inp, 'z', th[:12]))
+    print('z compressed: %d pseudo-sources, max rel diff vs brute force %.2e, classes %s' % (comp.npseudo, rel, info))
+    brute.close()
+    comp.close()
