@@ -289,6 +289,17 @@ def main():
     smp.run_mcmc(smp.chain[:, -1, :], n_samp_steps)
     torch.cuda.synchronize()
     t_steps = time.perf_counter() - t0
+    # the same ensemble on the device-resident sampler (one CUDA graph per update; over several GPUs the per-walker sum runs
+    # inside the graph, which needs the peer-memory exchange)
+    dev_big = None
+    if world == 1 or like.exchange == 'p2p':
+        like.sampler_run(thetas, 1, seed=5)
+        sync_all()
+        t0 = time.perf_counter()
+        run = like.sampler_run(thetas, n_samp_steps, seed=5)
+        t_dev_big = time.perf_counter() - t0
+        dev_big = {"steps_per_s": n_samp_steps / t_dev_big, "device_ms_per_step": run['device_ms'] / n_samp_steps,
+                   "acceptance": float(np.mean(run['naccepted'])) / n_samp_steps}
     # config-1 size on one GPU (rank 0): 10^4 sources x 100 walkers, launch/host-bound regime
     small = None
     if rank == 0:
@@ -405,7 +416,7 @@ def main():
             "ensemble_steps": {"value": n_samp_steps / (ms_steps * 1e-3), "unit": "ensemble steps/s",
                                "workload": "%d walkers x %g sources per GPU x %d GPU(s): stretch move, 2 half-ensemble "
                                            "lnprob calls per step through the public host API" % (W, args.nsources, world),
-                               "steps_timed": n_samp_steps, "small": small},
+                               "steps_timed": n_samp_steps, "device_resident": dev_big, "small": small},
             "clocks": clocks,
             "compressed_catalogue": compressed,
             "roofline": roof,
