@@ -51,3 +51,25 @@ def test_no_cpu_fallback_without_device():
     rc = lib.lf_create(ctypes.byref(ctx), ctypes.byref(cfg))
     assert rc != 0
     assert b'no CPU fallback' in lib.lf_last_error()
+
+
+def test_integration_md_binding_matches_the_header_struct():
+    """The ctypes mirror of lf_config printed in INTEGRATION.md (the stub a maintainer would paste into the reference)
+    has the same layout as the one the package itself uses."""
+    import ctypes as C
+    import os
+    import re
+    from lumfuncmcmc_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, 'INTEGRATION.md')).read()
+    m = re.search(r"class _LFConfig\(C\.Structure\):.*?\n\n", text, re.S)
+    assert m, "INTEGRATION.md lost its _LFConfig stub"
+    ns = {'C': C}
+    exec(m.group(0), ns)
+    doc = ns['_LFConfig']
+    assert C.sizeof(doc) == C.sizeof(_lib.LFConfig)
+    assert [(n, getattr(doc, n).offset, getattr(doc, n).size) for n, _ in doc._fields_] == \
+           [(n, getattr(_lib.LFConfig, n).offset, getattr(_lib.LFConfig, n).size) for n, _ in _lib.LFConfig._fields_]
+    # and every entry point the stub calls is exported
+    for sym in set(re.findall(r"_lf\.(lf_\w+)", text)):
+        assert sym in _lib.EXPORTS, sym
