@@ -264,10 +264,19 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
     const double* s_exp_rep = reinterpret_cast<const double*>(s_log);               // Z / FIXED models only
     const long long WS = a.Wcap;
     int* counter = a.cls_count + (LITERAL ? 4 : 3);
+    // the first item of every warp is assigned statically (its global warp index), the following ones come from the
+    // counter: no burst of a few thousand atomics on one address at kernel start
+    const long long total_warps = (long long)gridDim.x * (blockDim.x >> 5);
+    bool first = true;
   for (;;) {
     long long item = 0;
-    if (lane == 0) item = atomicAdd(counter, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
+    if (first) {
+        item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+        first = false;
+    } else {
+        if (lane == 0) item = total_warps + atomicAdd(counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+    }
     if (item >= n_items) break;
     // source items first (all walkers of the class), then quadrature items (the walkers this rank integrates)
     const bool is_src = item < n_src_items;
@@ -672,9 +681,9 @@ __global__ void __launch_bounds__(32 * FIN_GROUPS) k_finish(KArgs a) {
     double lnpart = 0.0, fullint = 0.0;
     if (valid) {
         const double* col = a.partial + w;
-#pragma unroll 4
+#pragma unroll 8
         for (int r = g; r < a.n_src_slabs; r += FIN_GROUPS) lnpart += col[(long long)r * WS];
-#pragma unroll 4
+#pragma unroll 8
         for (int r = a.n_src_slabs + g; r < a.n_src_slabs + a.n_quad_slabs; r += FIN_GROUPS)
             fullint += col[(long long)r * WS];
     }

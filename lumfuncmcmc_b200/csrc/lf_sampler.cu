@@ -13,13 +13,16 @@ struct SamplerArgs {
     long long step0;            // value of *step at the first replay (chain rows are relative to it)
     double* pos; double* lp;    // [W][ndim], [W]
     double* prop; double* lpnew; double* lnz; double* lnu;     // [half][ndim], [half] x 3
+    double* lp_next;            // [W] second log-posterior buffer: steps with odd index read lp_next and write lp
     double* chain; double* lnp; long long* nacc;               // [nsteps][W][ndim], [nsteps][W], [W]  (chain / lnp may be NULL)
 };
 
-// proposals for the walkers of half h (h = 0: [0, half), h = 1: [half, W)) against the other half
+// proposals for the walkers of half h (h = 0: [0, half), h = 1: [half, W)) against the other half.
+// One thread per (walker, parameter): the Philox call and z are recomputed per parameter (cheap), the copies run in parallel.
 __global__ void k_stretch_propose(SamplerArgs s, int h) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.half) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.half * s.ndim) return;
+    const int i = idx / s.ndim, d = idx - i * s.ndim;
     const int me = h * s.half + i;
     const long long step = *s.step;
     uint32_t r[4];
@@ -29,29 +32,38 @@ __global__ void k_stretch_propose(SamplerArgs s, int h) {
     const double t = __dadd_rn(__dmul_rn(s.a - 1.0, u01(r[0])), 1.0);
     const double z = __ddiv_rn(__dmul_rn(t, t), s.a);
     const int partner = (1 - h) * s.half + (int)(((unsigned long long)r[1] * (unsigned long long)s.half) >> 32);
-    for (int d = 0; d < s.ndim; ++d) {
-        const double pp = s.pos[(long long)partner * s.ndim + d], pm = s.pos[(long long)me * s.ndim + d];
-        s.prop[(long long)i * s.ndim + d] = __dsub_rn(pp, __dmul_rn(__dsub_rn(pp, pm), z));
+    const double pp = s.pos[(long long)partner * s.ndim + d], pm = s.pos[(long long)me * s.ndim + d];
+    s.prop[(long long)i * s.ndim + d] = __dsub_rn(pp, __dmul_rn(__dsub_rn(pp, pm), z));
+    if (d == 0) {
+        s.lnz[i] = (s.ndim - 1.0) * log(z);
+        s.lnu[i] = log(u01(r[2]));
     }
-    s.lnz[i] = (s.ndim - 1.0) * log(z);
-    s.lnu[i] = log(u01(r[2]));
 }
 
+// accept / reject and chain write, one thread per (walker, parameter).  The log-posteriors ping-pong between two buffers
+// by step parity (every thread of a walker reads the OLD value from one buffer, the d == 0 thread writes the other), so
+// no thread can see a half-updated state.
 __global__ void k_stretch_accept(SamplerArgs s, int h) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= s.half) return;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= s.half * s.ndim) return;
+    const int i = idx / s.ndim, d = idx - i * s.ndim;
     const int me = h * s.half + i;
-    const double lnratio = s.lnz[i] + s.lpnew[i] - s.lp[me];       // NaN (inf - inf) compares false: rejected
+    const long long step = *s.step;
+    const double* lp_cur = (step & 1) ? s.lp_next : s.lp;
+    double* lp_out = (step & 1) ? s.lp : s.lp_next;
+    const double lp_old = lp_cur[me], lp_new = s.lpnew[i];
+    const double lnratio = s.lnz[i] + lp_new - lp_old;              // NaN (inf - inf) compares false: rejected
     const bool acc = s.lnu[i] < lnratio;
-    if (acc) {
-        for (int d = 0; d < s.ndim; ++d) s.pos[(long long)me * s.ndim + d] = s.prop[(long long)i * s.ndim + d];
-        s.lp[me] = s.lpnew[i];
-        s.nacc[me] += 1;
+    const long long row = step - s.step0;
+    const double v = acc ? s.prop[(long long)i * s.ndim + d] : s.pos[(long long)me * s.ndim + d];
+    if (acc) s.pos[(long long)me * s.ndim + d] = v;
+    if (s.chain) s.chain[(row * s.W + me) * s.ndim + d] = v;
+    if (d == 0) {
+        const double lp_keep = acc ? lp_new : lp_old;
+        lp_out[me] = lp_keep;
+        if (acc) s.nacc[me] += 1;
+        if (s.lnp) s.lnp[row * s.W + me] = lp_keep;
     }
-    const long long row = *s.step - s.step0;
-    if (s.chain)
-        for (int d = 0; d < s.ndim; ++d) s.chain[(row * s.W + me) * s.ndim + d] = s.pos[(long long)me * s.ndim + d];
-    if (s.lnp) s.lnp[row * s.W + me] = s.lp[me];
 }
 __global__ void k_step_advance(long long* step) { *step += 1; }
 
@@ -65,7 +77,7 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
     const int ndim = c->ndim, half = (int)(W / 2);
     cudaStream_t st = c->stream;
     double *d_pos = nullptr, *d_lp = nullptr, *d_prop = nullptr, *d_lpnew = nullptr, *d_lnz = nullptr, *d_lnu = nullptr;
-    double *d_chain = nullptr, *d_lnp = nullptr;
+    double *d_chain = nullptr, *d_lnp = nullptr, *d_lpnext = nullptr;
     long long *d_nacc = nullptr, *d_step = nullptr;
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
@@ -74,7 +86,7 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
         if (exec) cudaGraphExecDestroy(exec);
         if (graph) cudaGraphDestroy(graph);
         dfree(d_pos); dfree(d_lp); dfree(d_prop); dfree(d_lpnew); dfree(d_lnz); dfree(d_lnu);
-        dfree(d_chain); dfree(d_lnp); dfree(d_nacc); dfree(d_step);
+        dfree(d_chain); dfree(d_lnp); dfree(d_nacc); dfree(d_step); dfree(d_lpnext);
         return rc;
     };
 #define SCK(call)                                                                                   \
@@ -91,6 +103,7 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
     SCK(cudaMalloc(&d_lpnew, sizeof(double) * half));
     SCK(cudaMalloc(&d_lnz, sizeof(double) * half));
     SCK(cudaMalloc(&d_lnu, sizeof(double) * half));
+    SCK(cudaMalloc(&d_lpnext, sizeof(double) * W));
     SCK(cudaMalloc(&d_nacc, sizeof(long long) * W));
     SCK(cudaMalloc(&d_step, sizeof(long long)));
     if (chain && nsteps > 0) SCK(cudaMalloc(&d_chain, sizeof(double) * (size_t)nsteps * W * ndim));
@@ -112,7 +125,8 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
         }
         return 0;
     };
-    if (lnprob_all_ranks(d_pos, W, d_lp)) return cleanup();
+    // the update with index `step` reads the log-posteriors from lp (even step) or lp_next (odd step) and writes the other
+    if (lnprob_all_ranks(d_pos, W, (step0 & 1) ? d_lpnext : d_lp)) return cleanup();
     if (lnprob_all_ranks(d_pos, half, d_lpnew)) return cleanup();
     SCK(cudaStreamSynchronize(st));
     SamplerArgs sa;
@@ -120,8 +134,8 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
     sa.k0 = (uint32_t)seed; sa.k1 = (uint32_t)(seed >> 32);
     sa.step = d_step; sa.step0 = step0;
     sa.pos = d_pos; sa.lp = d_lp; sa.prop = d_prop; sa.lpnew = d_lpnew; sa.lnz = d_lnz; sa.lnu = d_lnu;
-    sa.chain = d_chain; sa.lnp = d_lnp; sa.nacc = d_nacc;
-    const int T = 128, G = (half + T - 1) / T;
+    sa.chain = d_chain; sa.lnp = d_lnp; sa.nacc = d_nacc; sa.lp_next = d_lpnext;
+    const int T = 128, G = (half * ndim + T - 1) / T;
     const long long launches0 = c->launches;
     if (nsteps > 0) {
         SCK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
@@ -148,7 +162,7 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
     if (lnprob && nsteps > 0) SCK(cudaMemcpyAsync(lnprob, d_lnp, sizeof(double) * (size_t)nsteps * W, cudaMemcpyDeviceToHost, st));
     if (naccepted) SCK(cudaMemcpyAsync(naccepted, d_nacc, sizeof(long long) * W, cudaMemcpyDeviceToHost, st));
     if (pos_out) SCK(cudaMemcpyAsync(pos_out, d_pos, sizeof(double) * W * ndim, cudaMemcpyDeviceToHost, st));
-    if (lnprob_out) SCK(cudaMemcpyAsync(lnprob_out, d_lp, sizeof(double) * W, cudaMemcpyDeviceToHost, st));
+    if (lnprob_out) SCK(cudaMemcpyAsync(lnprob_out, ((step0 + nsteps) & 1) ? d_lpnext : d_lp, sizeof(double) * W, cudaMemcpyDeviceToHost, st));
     SCK(cudaStreamSynchronize(st));
     SCK(cudaGetLastError());
     if (nsteps > 0) { float ms = 0.f; SCK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->sampler_ms = ms; }
