@@ -92,7 +92,7 @@ __global__ void k_prologue(KArgs a) {
             if (aL != 0.0) { double zv = -bL / (2.0 * aL); if (zv > s.z_min && zv < s.z_max) { double v = fma(fma(aL, zv, bL), zv, cL); Llo = fmin(Llo, v); Lhi = fmax(Lhi, v); } }
             if (aP != 0.0) { double zv = -bP / (2.0 * aP); if (zv > s.z_min && zv < s.z_max) { double v = fma(fma(aP, zv, bP), zv, cP); Plo = fmin(Plo, v); } }
             double dlo = s.lum_min - Lhi, dhi = s.lum_max - Llo;
-            double emax = pow(10.0, dhi);
+            double emax = exp10(dhi);
             lb = LNLN10 + LN10 * Plo + fmin(c1 * dlo, c1 * dhi) - emax + s.lnom_min;
             if (!(emax < 690.0)) lb = -1.0e300;
             if (!(dlo > -40.0)) lb = -1.0e300;
@@ -117,8 +117,10 @@ __global__ void k_prologue(KArgs a) {
         }
         rejected = gate && !ok;
         // certain underflow: exp(-10^(lum_max - L*)) == 0 makes Phi == 0 for the brightest source
-        if (!rejected && a.N > 0 && exp(-pow(10.0, a.lum_max_all - Lstar)) == 0.0) rejected = true;
-        double tenmL = pow(10.0, -Lstar);
+        // exp10 instead of the generic pow: same <= 1 ulp accuracy, a fraction of the latency (the prologue is a chain of
+        // dependent transcendentals; it matters for small ensembles)
+        if (!rejected && a.N > 0 && exp(-exp10(a.lum_max_all - Lstar)) == 0.0) rejected = true;
+        double tenmL = exp10(-Lstar);
         double c1 = (sal + 1.0) * LN10;
         double c0 = LNLN10 + phistar * LN10 - Lstar * c1;
         if (k == 0 && live && !rejected) {
@@ -128,12 +130,12 @@ __global__ void k_prologue(KArgs a) {
         }
         double tmin = 0.0, lnom = 0.0;
         if (a.model == LF_MODEL_FREE) {
-            double b = -1.0 * sqrt(a.fcA2 * pow(alpha_c, -2.0));   // inverse_fleming, VmaxLumFunc.py:164-165
+            double b = -1.0 * sqrt(a.fcA2 / (alpha_c * alpha_c));   // inverse_fleming, VmaxLumFunc.py:164-165
             if (!(alpha_c > 0.0)) rok = 0;
             if (a.csrc != nullptr && !(alpha_c <= a.c_alpha_max)) rok = 0;      // outside the compressed catalogue's error bound
             double F50 = 1.0e-17 * th[p + k];
             double lgF = log10(F50);
-            double ftau = F50 * pow(10.0, b);
+            double ftau = F50 * exp10(b);
             if (live && !rejected) {
                 wp[(P_FIELD0 + 4 * k + 0) * WS] = -alpha_c * lgF;
                 wp[(P_FIELD0 + 4 * k + 1) * WS] = -LOG2E / ftau;
@@ -151,8 +153,8 @@ __global__ void k_prologue(KArgs a) {
         }
         if (s.n != 0.0) {
             // Schechter exponent S(l) = c0 + c1 l - 10^(l - L*) is concave in l: minimum at an end of the range
-            double s_lo = fmin(c0 + c1 * s.lum_min - pow(10.0, s.lum_min - Lstar),
-                               c0 + c1 * s.lum_max - pow(10.0, s.lum_max - Lstar));
+            double s_lo = fmin(c0 + c1 * s.lum_min - exp10(s.lum_min - Lstar),
+                               c0 + c1 * s.lum_max - exp10(s.lum_max - Lstar));
             if (a.model == LF_MODEL_FREE) {
                 lb = s_lo + lnom + tmin;
                 part = s.n * (c0 + lnom) + c1 * s.sum_lum - tenmL * s.sum_L;
@@ -199,7 +201,7 @@ __global__ void k_zcolumns(KArgs a) {
     double Ps = wp[P_AP * WS] * z * z + wp[P_BP * WS] * z + wp[P_CP * WS];
     double c1 = wp[P_C1 * WS];
     a.colA[(long long)i * WS + w] = LNLN10 + LN10 * Ps - c1 * Ls;
-    a.colB[(long long)i * WS + w] = pow(10.0, -Ls);
+    a.colB[(long long)i * WS + w] = exp10(-Ls);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -681,9 +683,9 @@ __global__ void __launch_bounds__(32 * FIN_GROUPS) k_finish(KArgs a) {
     double lnpart = 0.0, fullint = 0.0;
     if (valid) {
         const double* col = a.partial + w;
-#pragma unroll 8
+#pragma unroll 4
         for (int r = g; r < a.n_src_slabs; r += FIN_GROUPS) lnpart += col[(long long)r * WS];
-#pragma unroll 8
+#pragma unroll 4
         for (int r = a.n_src_slabs + g; r < a.n_src_slabs + a.n_quad_slabs; r += FIN_GROUPS)
             fullint += col[(long long)r * WS];
     }
