@@ -31,7 +31,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FP64_INSTR_PER_TERM = 23          # DFMA/DADD/DMUL per (walker, source) term in k_main<false> (tools/sass_loop_mix.py)
+FP64_INSTR_PER_TERM = 23          # DFMA/DADD/DMUL per (walker, source) term in k_main<false, FREE> (tools/sass_loop_mix.py)
+FP64_INSTR_PER_TERM_BY_KIND = {'free': 23, 'z': 11, 'fixed': 0}    # fixed: the source sum is sufficient statistics (quadrature only)
+MUFU_PER_TERM_BY_KIND = {'free': 4, 'z': 1, 'fixed': 0}
 MUFU_PER_TERM = 4                 # rsqrt, lg2, ex2, rcp per term in the FP32 mode of the loop
 BYTES_PER_SOURCE = 16             # (log10 flux, flux) per source per sweep
 METRIC = "walker x source lnL terms/sec (batched lnprob, free-completeness single-z, FP64)"
@@ -376,14 +378,15 @@ def main():
         bytes_per_source = 8 if f32 else BYTES_PER_SOURCE
         alg_bytes = n * bytes_per_source + W * like.ndim * 8 + W * 8
         if f32:
-            roof = {"bound": "mufu", "achieved": per_gpu * MUFU_PER_TERM / 1e12, "peak": peak_mufu / 1e12, "unit": "T MUFU instr/s",
+            roof = {"bound": "mufu", "achieved": per_gpu * MUFU_PER_TERM_BY_KIND[args.kind] / 1e12, "peak": peak_mufu / 1e12, "unit": "T MUFU instr/s",
                     "note": "FP32 mode of k_main<false> is SFU bound: achieved = terms/s/GPU x %d MUFU instr/term (rsqrt, lg2, ex2, "
-                            "rcp); peak = ex2.approx.f32 rate measured live on this GPU (lf_mufu_peak)" % MUFU_PER_TERM}
+                            "rcp; z model: one ex2); peak = ex2.approx.f32 rate measured live on this GPU (lf_mufu_peak)" % MUFU_PER_TERM_BY_KIND[args.kind]}
         else:
-            roof = {"bound": "fp64", "achieved": per_gpu * FP64_INSTR_PER_TERM * 2 / 1e12, "peak": peak_dfma * 2 / 1e12, "unit": "TFLOP/s",
+            roof = {"bound": "fp64", "achieved": per_gpu * FP64_INSTR_PER_TERM_BY_KIND[args.kind] * 2 / 1e12, "peak": peak_dfma * 2 / 1e12, "unit": "TFLOP/s",
                     "note": "FP64-FMA-pipe bound kernel k_main<false> (no tensor cores; HBM traffic ~0.02 B/term): achieved = terms/s/GPU "
                             "x %d FP64-pipe instr/term (counted in SASS, tools/sass_loop_mix.py) x 2 FLOP; peak = register-only DFMA "
-                            "rate measured live on this GPU (lf_fp64_peak: %.3e DFMA/s) x 2 FLOP" % (FP64_INSTR_PER_TERM, peak_dfma)}
+                            "rate measured live on this GPU (lf_fp64_peak: %.3e DFMA/s) x 2 FLOP; the per-walker quadrature (K S^2 points) is "
+                            "extra work not counted as terms" % (FP64_INSTR_PER_TERM_BY_KIND[args.kind], peak_dfma)}
         roof["frac"] = roof["achieved"] / roof["peak"]
         # DRAM bytes of one k_main launch from the committed ncu --set full capture of this workload (profiles/), if any
         roof["traffic"] = None
