@@ -75,7 +75,7 @@ static __constant__ double KC[16] = {
     LOG2E,                  // 8
     0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
 
-struct Tables {                 // device-global master copies (filled by the host at lf_create)
+struct __align__(16) Tables {    // device-global master copies (filled by the host at lf_create)
     double exp2_frac[EXP_TAB_N];        // 2^(j/256)
     double exp2_big[EXPB_N + 1];        // 2^(k/256), k = EXPB_KMIN .. 0
     double2 log_tab[LOG_TAB_N + 1];     // bin b <-> argument bits (hi >> 12) == LOG_TAB_BASE + b:
@@ -107,7 +107,11 @@ __device__ __forceinline__ void load_exp_replicated(const Tables* __restrict__ t
 }
 __device__ __forceinline__ void load_tables(const Tables* __restrict__ t, double* s_exp, double2* s_log) {
 #if LF_EXP_BIG
-    for (int i = threadIdx.x; i < EXPB_N; i += blockDim.x) s_exp[i] = t->exp2_big[i];
+    {   // 16-byte copies (the table has EXPB_N + 1 = an even number of doubles; both sides are 16-byte aligned)
+        const double2* __restrict__ src = reinterpret_cast<const double2*>(t->exp2_big);
+        double2* dst = reinterpret_cast<double2*>(s_exp);
+        for (int i = threadIdx.x; i < (EXPB_N + 1) / 2; i += blockDim.x) dst[i] = src[i];
+    }
 #else
     for (int i = threadIdx.x; i < EXP_TAB_N * EXP_TAB_REP; i += blockDim.x) s_exp[i] = t->exp2_frac[i / EXP_TAB_REP];
 #endif
