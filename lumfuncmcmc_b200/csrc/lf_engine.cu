@@ -17,6 +17,10 @@
 // behaviour is reproduced, not imitated (lumfuncmcmc.py:370).
 #include "lf_internal.cuh"
 
+#ifndef LF_PDL
+#define LF_PDL 1          /* programmatic dependent launch of the fast main kernel (its table fill overlaps the prologue) */
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
@@ -47,6 +51,9 @@ extern "C" int lf_device_count(void) {
 // and thread y == 0 combines the fields in index order, so the sums are the same as a sequential loop over fields.
 #define PRO_WALKERS 32
 __global__ void k_prologue(KArgs a) {
+#if LF_PDL
+    asm volatile("griddepcontrol.launch_dependents;");          // the next kernel's blocks may start their table fill now
+#endif
     __shared__ double s_part[LF_MAX_FIELDS][PRO_WALKERS], s_lb[LF_MAX_FIELDS][PRO_WALKERS];
     __shared__ int s_rok[LF_MAX_FIELDS][PRO_WALKERS];
     const int wl = threadIdx.x, k = threadIdx.y;
@@ -189,6 +196,9 @@ __global__ void k_prologue(KArgs a) {
 // Z model: per (column i, walker) constants of the quadrature integrand
 //   colA = ln ln10 + ln10 phi*(z_i) - c1 L*(z_i),   colB = 10^-L*(z_i)
 __global__ void k_zcolumns(KArgs a) {
+#if LF_PDL
+    asm volatile("griddepcontrol.launch_dependents;");
+#endif
     long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const int nf = a.cls_count[CLS_FAST];
     if (idx >= (long long)a.S * nf) return;
@@ -247,17 +257,22 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
     double* s_exp = reinterpret_cast<double*>(s_log + LOG_TAB_N * LOG_TAB_REP);     // FREE only
     double2* s_stage = reinterpret_cast<double2*>(smem_tables + main_table_bytes(MODEL)) + (threadIdx.x >> 5) * (QSTAGE * 3);
     const int cls = LITERAL ? CLS_LIT : CLS_FAST;
-    const int count_src = a.cls_count[cls], count_quad = a.cls_count[LITERAL ? 6 : 5];
-    const int n_wg = (count_src + 31) >> 5, n_wgq = (count_quad + 31) >> 5;
-    if (n_wg == 0) return;
-    const long long n_src_items = (long long)n_wg * a.n_src_slabs;
-    const long long n_items = n_src_items + (long long)n_wgq * a.n_quad_slabs;
     if (!LITERAL) {
-        // FREE: log table + (big) exp table; Z / FIXED: no log table, the small replicated exp table takes its place
+        // FREE: log table + (big) exp table; Z / FIXED: no log table, the small replicated exp table takes its place.
+        // The fast kernel is launched with programmatic stream serialisation: its blocks become resident while the
+        // prologue is still running and fill their tables (which do not depend on it) in its shadow; everything the
+        // prologue writes is read only after griddepcontrol.wait.
         if (MODEL == LF_MODEL_FREE) load_tables(a.tables, s_exp, s_log);
         else load_exp_replicated(a.tables, reinterpret_cast<double*>(s_log));
+#if LF_PDL
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
         __syncthreads();
     }
+    const int count_src = a.cls_count[cls], count_quad = a.cls_count[LITERAL ? 6 : 5];
+    const int n_wg = (count_src + 31) >> 5, n_wgq = (count_quad + 31) >> 5;      // n_wg == 0: n_items == 0, the loop exits at once
+    const long long n_src_items = (long long)n_wg * a.n_src_slabs;
+    const long long n_items = n_src_items + (long long)n_wgq * a.n_quad_slabs;
     // persistent warps: every warp pulls (walker group, slab) items from a global counter until none are left.
     // Items are small (tens per warp slot), so SMs finish within one item of each other (no wave tail), and each
     // item owns its own partial[] row, so the result does not depend on which warp ran it.
@@ -1253,15 +1268,26 @@ int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_ou
     const long long need = (items + wpb - 1) / wpb;      // never more blocks than items
     const unsigned bf = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_fast);
     const unsigned bl = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_lit);
-    if (c->cfg.model == LF_MODEL_FREE) {
-        k_main<false, LF_MODEL_FREE><<<bf, 32 * main_warps(LF_MODEL_FREE), main_smem_bytes(LF_MODEL_FREE), st>>>(a);
-        k_main<true, LF_MODEL_FREE><<<bl, 32 * main_warps(LF_MODEL_FREE), 0, st>>>(a);
-    } else if (c->cfg.model == LF_MODEL_FIXED) {
-        k_main<false, LF_MODEL_FIXED><<<bf, 32 * main_warps(LF_MODEL_FIXED), main_smem_bytes(LF_MODEL_FIXED), st>>>(a);
-        k_main<true, LF_MODEL_FIXED><<<bl, 32 * main_warps(LF_MODEL_FIXED), 0, st>>>(a);
-    } else {
-        k_main<false, LF_MODEL_Z><<<bf, 32 * main_warps(LF_MODEL_Z), main_smem_bytes(LF_MODEL_Z), st>>>(a);
-        k_main<true, LF_MODEL_Z><<<bl, 32 * main_warps(LF_MODEL_Z), 0, st>>>(a);
+    {
+        // fast kernel: launched programmatically dependent on the kernel before it (prologue, or k_zcolumns for the Z model)
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3(bf); lc.blockDim = dim3(32 * main_warps(c->cfg.model)); lc.dynamicSmemBytes = main_smem_bytes(c->cfg.model);
+        lc.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = LF_PDL;
+        lc.attrs = attr; lc.numAttrs = 1;
+        if (c->cfg.model == LF_MODEL_FREE) {
+            CK(cudaLaunchKernelEx(&lc, k_main<false, LF_MODEL_FREE>, a));
+            k_main<true, LF_MODEL_FREE><<<bl, 32 * main_warps(LF_MODEL_FREE), 0, st>>>(a);
+        } else if (c->cfg.model == LF_MODEL_FIXED) {
+            CK(cudaLaunchKernelEx(&lc, k_main<false, LF_MODEL_FIXED>, a));
+            k_main<true, LF_MODEL_FIXED><<<bl, 32 * main_warps(LF_MODEL_FIXED), 0, st>>>(a);
+        } else {
+            CK(cudaLaunchKernelEx(&lc, k_main<false, LF_MODEL_Z>, a));
+            k_main<true, LF_MODEL_Z><<<bl, 32 * main_warps(LF_MODEL_Z), 0, st>>>(a);
+        }
     }
     k_finish<<<(unsigned)((W + 31) / 32), 32 * FIN_GROUPS, 0, st>>>(a);
     c->launches += 3;
