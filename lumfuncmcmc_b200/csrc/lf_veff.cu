@@ -17,7 +17,8 @@ struct VeffArgs {
     const double* edges; int nbins;
     unsigned long long* counts; double* sumphi;     // [gridDim.x][nbins] block partials
     const int* mult;                                 // bootstrap multiplicities (NULL: original sample)
-    short* bin;                                      // per-source bin index (-1: none), written by MODE 0/2, read by MODE 1
+    short* bin;                                      // per-source histogram row (bin + 1; 0 / nbins + 1: none), written by MODE 0/2, read by MODE 1
+    int fast; double bscale, bC; int hi_lo; unsigned hi_span;   // lean route (edges_fast_ok)
 };
 
 __device__ __forceinline__ int bin_of(double L, const double* e, int nb) {
@@ -94,67 +95,122 @@ __global__ void __launch_bounds__(256) k_veff(VeffArgs a) {
 }
 
 // ---- streaming version with private histogram columns (no atomics, deterministic) ----
-// Each warp owns VP_COLS = 16 columns per bin of the block's shared-memory histogram, s_sum[warp][bin][col] (f64) and
-// s_cnt[warp][bin][col] (u32); lanes l and l + 16 share column l and update it in two turns separated by __syncwarp,
-// so an update is a plain read-modify-write of a word nobody else touches in that turn (no atomics, no races, one
-// bank per column).  At the end each warp folds its columns with a fixed shuffle tree and the block adds the warps
-// in order: the result does not depend on scheduling.  Shared memory: 8 warps x nbins x 16 x 12 B (76.8 KB at the
-// reference's nbins = 50 -> two blocks = 16 warps per SM); larger histograms fall back to k_veff (atomics).
-// The per-source completeness is evaluated as exp(-ln(fc)/dec) with the ~2e-16 routines of lf_math.cuh (two 2-4 KB
-// tables) instead of libdevice pow/log10/exp/sqrt and five IEEE divisions: ~75 FP64-pipe instructions per source, so
-// the pass stays close to its HBM time (24 B per source).
+// Each warp owns VP_COLS = 16 columns per histogram row of the block's shared memory, s_sum[warp][row][col] (f64);
+// lanes l and l + 16 share column l and update it in two turns separated by __syncwarp, so an update is a plain
+// read-modify-write of a word nobody else touches in that turn (no floating-point atomics, no races, one bank per
+// column).  The integer counts s_cnt[warp][row] use shared-memory atomics (integer addition is order-independent).  Rows 1 .. nbins are the bins; rows 0 and nbins + 1 collect what falls in no bin, so the update
+// itself needs no branch.  At the end each warp folds its columns with a fixed shuffle tree and the block adds the
+// warps in order: the result does not depend on scheduling.  Shared memory at the reference's nbins = 50: 68 KB ->
+// three blocks = 24 warps per SM; larger histograms fall back to k_veff (atomics).
+// The per-source completeness is exp(-ln(fc)/dec) with the ~2e-16 routines of lf_math.cuh (two small tables).
+// A trip (VP_UNROLL x 256 consecutive sources) that is complete, lies inside one field and needs no per-source volume
+// takes the lean route: no bounds predicates, no field search, a branch-free bin search (edge table with -inf / +inf
+// sentinels, candidate bin from one fma), integer guards, one deferred test per trip for the literal fall-back --
+// ~60 FP64-pipe + ~60 other instructions per source, so the pass runs near its HBM time (26 B per source).
 #define VP_WARPS 8
 #define VP_COLS 16
 #define VP_UNROLL 4
+#define VP_BOOT_UNROLL 8
 static const size_t VP_SMEM_MAX = 200 * 1024;
+static const double VP_BIN_MAGIC = 6597069766656.0;                         // 1.5 * 2^42: 10 fraction bits in the low word
 
 __device__ __noinline__ double inv_fleming_literal(double f, double F50, double alpha, double ftau, bool modified) {
     return 1.0 / fleming_literal(f, F50, alpha, ftau, modified);
 }
 
-// 1 / fleming(f): VmaxLumFunc.py:118-126, 141.  Sources outside the range where the fast evaluation is accurate to
-// ~1e-15 (fc < 1e-6, decay argument < 1e-6, |ln comp| > 690) take the literal libdevice route.
-__device__ __forceinline__ double inv_fleming_stream(double f, double F50, double invF50, double alpha_log10e, double alpha,
-                                                     double ftau, double inv_ftau, bool modified, const double* s_exp,
-                                                     const double2* s_logm) {
+// 1 / fleming(f): VmaxLumFunc.py:118-126, 141.  `bad` is set for sources outside the range where this evaluation is
+// accurate to ~1e-15 (fc <= 1e-6, decay argument <= 1e-6, |ln comp| >= 690, non-finite input); the caller redoes those
+// with inv_fleming_literal.  The guards compare high words (positive doubles order like their bit patterns).
+template <bool MODIFIED>
+__device__ __forceinline__ double inv_fleming_stream(double f, double invF50, double alpha_log10e, double inv_ftau,
+                                                     const double* s_exp, const double2* s_logm, bool& bad) {
     const double num = alpha_log10e * log_stream(f * invF50, s_logm);       // alpha * log10(f / F50)
     const double y = fma(num, num, 1.0);
-    double r0 = rsqrt_seed(y);
+    const double r0 = rsqrt_seed(y);
     const double e = fma(-(y * r0), r0, 1.0);
     const double pe = fma(0.375, e, 0.5) * e;
     const double nr = num * r0;
     const double fc = fma(0.5, fma(nr, pe, nr), 0.5);
-    const double x = f * inv_ftau;
-    double t = -log_stream(fc > 1.0e-300 ? fc : 1.0e-300, s_logm);
-    if (modified) t *= rcp_stream(1.0 - exp_stream(x < 690.0 ? -x : -690.0, s_exp));
-    if (!(fc > 1.0e-6) || (modified && !(x > 1.0e-6)) || !(t < 690.0)) return inv_fleming_literal(f, F50, alpha, ftau, modified);
-    return exp_stream(t, s_exp);
+    int lowest = __double2hiint(fc);                                        // fc > 1e-6
+    double t = log_stream(fc, s_logm);                                      // ln fc <= 0
+    if (MODIFIED) {
+        const double x = f * inv_ftau;
+        const int hx = __double2hiint(x);
+        lowest = min(lowest, hx);                                           // x > 1e-6
+        const double xm = hx < 0x40859000 ? x : 690.0;                      // beyond 690 the decay factor is 1 anyway
+        t *= rcp_stream(exp_stream(-xm, s_exp) - 1.0);                      // -ln(fc) / (1 - e^-x) >= 0
+    } else {
+        t = -t;
+    }
+    const bool ok = (lowest > 0x3eb0c6f7) & ((unsigned)__double2hiint(t) < 0x40859000u);   // and 0 <= t < 690
+    bad = !ok;
+    return exp_stream(ok ? t : 0.0, s_exp);
 }
 
+// histogram row of L on the sentinel edge table e_col = &s_edges[(2 + 0) * 16 + col] (entries j = -2 .. nbins + 2),
+// for edges the host found near-uniform (edges_fast_ok): the candidate from one fma is off by at most one, two exact
+// comparisons against the caller's edges decide (VmaxLumFunc.py:346-348).  Row 0 / nbins + 1: below / above all bins.
+__device__ __forceinline__ int row_fast(double L, const double* e_col, double scale, double C, int hi_lo, unsigned hi_span) {
+    const bool inr = (unsigned)(__double2hiint(L) - hi_lo) <= hi_span;     // L within a fraction of a bin of [e_0, e_nb]
+    int j = __double2loint(fma(L, scale, C)) >> 10;
+    j = inr ? j : -2;
+    j -= (int)(L < e_col[j * 16]);
+    j += (int)(L >= e_col[(j + 1) * 16]);
+    return inr ? j + 1 : 0;
+}
+
+// one trip's histogram update: counts by integer atomics, sums in the thread's private column in two turns.  sum_col /
+// cnt_w point at row 0 of the thread's column / the warp's count array; whole warps call this together.
+template <int U, bool UNIT>
+__device__ __forceinline__ void hist_update(double* sum_col, unsigned* cnt_w, int turn, const int (&row)[U],
+                                            const double (&phi)[U], const unsigned (&m)[U]) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) atomicAdd(cnt_w + row[u], UNIT ? 1u : m[u]);
+#pragma unroll
+    for (int tn = 0; tn < 2; ++tn) {
+        if (turn == tn) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) sum_col[row[u] * VP_COLS] += phi[u];
+        }
+        __syncwarp();
+    }
+}
+
+// MODE 0: compute phi from the completeness and bin; MODE 1: bootstrap replicate (multiplicities) on resident
+// rows / phi; MODE 2: bin caller-provided (resident) phi
 template <int MODE>
 __global__ void __launch_bounds__(32 * VP_WARPS) k_veff_priv(VeffArgs a) {
     constexpr bool BOOT = MODE == 1;
+    constexpr int U = BOOT ? VP_BOOT_UNROLL : VP_UNROLL;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int nb = a.nbins;
-    double* s_edges = reinterpret_cast<double*>(smem_raw);                  // [nbins + 1][16] replicated
-    double* s_sum = s_edges + (nb + 1) * 16;                                // [VP_WARPS][nbins][VP_COLS]
-    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + VP_WARPS * nb * VP_COLS);
-    double2* s_logm = reinterpret_cast<double2*>(s_cnt + VP_WARPS * nb * VP_COLS);   // MODE 0 only
+    const int nb = a.nbins, nrow = nb + 2;
+    double2* s_logm = reinterpret_cast<double2*>(smem_raw);                 // math tables first: compile-time offsets
     double* s_exp = reinterpret_cast<double*>(s_logm + STREAM_LOG_N);
+    double* s_edges = s_exp + EXP_TAB_N;                                    // [nbins + 5][16] replicated, j = -2 .. nbins + 2
+    double* s_sum = s_edges + (nb + 5) * 16;                                // [VP_WARPS][nrow][VP_COLS]
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_sum + VP_WARPS * nrow * VP_COLS);   // [VP_WARPS][nrow]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < (nb + 1) * 16; i += blockDim.x) s_edges[i] = a.edges[i >> 4];
-    for (int i = threadIdx.x; i < VP_WARPS * nb * VP_COLS; i += blockDim.x) { s_sum[i] = 0.0; s_cnt[i] = 0u; }
+    for (int i = threadIdx.x; i < (nb + 5) * 16; i += blockDim.x) {
+        const int j = (i >> 4) - 2;
+        s_edges[i] = j < 0 ? -INFINITY : (j > nb ? INFINITY : a.edges[j]);
+    }
+    for (int i = threadIdx.x; i < VP_WARPS * nrow * VP_COLS; i += blockDim.x) s_sum[i] = 0.0;
+    for (int i = threadIdx.x; i < VP_WARPS * nrow; i += blockDim.x) s_cnt[i] = 0u;
     if (MODE == 0) load_stream_tables(a.tables, s_exp, s_logm);
     const double e0 = a.edges[0], enb = a.edges[nb], scale = (double)nb / (enb - e0);
-    __syncthreads();
-    double* my_sum = s_sum + warp * nb * VP_COLS + (lane & (VP_COLS - 1));
-    unsigned* my_cnt = s_cnt + warp * nb * VP_COLS + (lane & (VP_COLS - 1));
+    const double* e_rep = s_edges + 2 * 16;                                 // e_rep[j * 16 + col] = edge j
+    const double* e_col = e_rep + (lane & 15);
+    // per-thread offsets are made opaque so that they stay in registers instead of being recomputed every trip
+    int sum_off = warp * nrow * VP_COLS + (lane & (VP_COLS - 1)), cnt_off = warp * nrow;
+    asm volatile("" : "+r"(sum_off), "+r"(cnt_off));
+    double* my_sum = s_sum + sum_off;
+    unsigned* my_cnt = s_cnt + cnt_off;              // counts: shared-memory integer atomics (order-independent)
     const int turn = lane >> 4;
     const double alpha_log10e = a.alpha * KS[12];
     // Each block streams ONE contiguous chunk of the catalogue: offsets inside the chunk fit in 32 bits and the base
     // pointers are formed once, so the loop carries no 64-bit index arithmetic; the field boundaries that fall inside
     // the chunk and the per-field constants sit in shared memory.
-    constexpr int TRIP = 32 * VP_WARPS * VP_UNROLL;
+    constexpr int STRIDE = 32 * VP_WARPS, TRIP = STRIDE * U;
     const long long per_block = ((a.n + gridDim.x - 1) / gridDim.x + TRIP - 1) / TRIP * TRIP;
     const long long start = (long long)blockIdx.x * per_block;
     const int len = (int)(a.n - start < per_block ? (a.n - start > 0 ? a.n - start : 0) : per_block);
@@ -162,7 +218,8 @@ __global__ void __launch_bounds__(32 * VP_WARPS) k_veff_priv(VeffArgs a) {
     __shared__ double s_fk[LF_MAX_FIELDS][4];
     if (MODE == 0 && threadIdx.x < a.K) {
         const long long b = a.field_ind[threadIdx.x + 1] - start;
-        s_fb[threadIdx.x] = (int)(b < 0 ? 0 : (b > len ? len : b));          // end of field k inside the chunk
+        // end of field k inside the chunk; the last field is open-ended
+        s_fb[threadIdx.x] = threadIdx.x == a.K - 1 ? 0x7fffffff : (int)(b < 0 ? 0 : (b > len ? len : b));
         s_fk[threadIdx.x][0] = a.F50[threadIdx.x]; s_fk[threadIdx.x][1] = a.invF50[threadIdx.x];
         s_fk[threadIdx.x][2] = a.ftau[threadIdx.x]; s_fk[threadIdx.x][3] = a.inv_ftau[threadIdx.x];
     }
@@ -173,73 +230,104 @@ __global__ void __launch_bounds__(32 * VP_WARPS) k_veff_priv(VeffArgs a) {
     const unsigned char* __restrict__ p_valid = a.valid ? a.valid + start : nullptr;
     const int* __restrict__ p_mult = a.mult ? a.mult + start : nullptr;
     double* __restrict__ p_phi = a.phi + start;
-    short* __restrict__ p_bin = a.bin + start;
+    short* __restrict__ p_row = a.bin + start;
     const bool modified = a.modified != 0;
-    int k = 0, kend = MODE == 0 ? s_fb[0] : 0;  // sources are field-sorted: the field index only moves forward
-    double F50 = 0.0, iF50 = 0.0, ftau = 0.0, iftau = 0.0;
-    if (MODE == 0) { F50 = s_fk[0][0]; iF50 = s_fk[0][1]; ftau = s_fk[0][2]; iftau = s_fk[0][3]; }
+    const bool lean = a.fast != 0;
+    int kU = 0;                                      // field of the trip's first source (sources are field-sorted)
     // whole warps iterate together (the trip count depends on the block only) so that __syncwarp is legal
     for (int t0 = 0; t0 < len; t0 += TRIP) {
-        double lum[VP_UNROLL], phi[VP_UNROLL], flux[VP_UNROLL], vol[VP_UNROLL];
-        unsigned m[VP_UNROLL];
-        int jb[VP_UNROLL];
-        bool ok[VP_UNROLL];
+        double phi[U];
+        unsigned m[U];
+        int row[U];
+        const int base = t0 + threadIdx.x;
+        if (MODE == 0) while (t0 >= s_fb[kU]) ++kU;                          // block-uniform; s_fb[K - 1] = INT_MAX
+        if (BOOT) {                                                          // replicate: resident row, weight, multiplicity
 #pragma unroll
-        for (int u = 0; u < VP_UNROLL; ++u) {                                // all loads of the trip first
-            const int off = t0 + u * (32 * VP_WARPS) + threadIdx.x;
-            const bool in = off < len;
-            m[u] = in ? 1u : 0u;
-            ok[u] = in;
-            phi[u] = 0.0;
-            if (BOOT) {                                                      // replicate: resident bin index, weight, multiplicity
-                jb[u] = in ? (int)__ldcs(p_bin + off) : -1;
+            for (int u = 0; u < U; ++u) {
+                const int off = base + u * STRIDE;
+                const bool in = off < len;
+                row[u] = in ? (int)__ldcs(p_row + off) : 0;
                 m[u] = in ? (unsigned)__ldcs(p_mult + off) : 0u;
                 phi[u] = in ? __ldcs(p_phi + off) : 0.0;
-                continue;
             }
-            lum[u] = in ? __ldcs(p_lum + off) : -1.0e300;                    // below every edge: lands in no bin
+#pragma unroll
+            for (int u = 0; u < U; ++u)                                      // weight x multiplicity (exact conversion, no I2F)
+                phi[u] = m[u] ? phi[u] * (__hiloint2double(0x43300000, (int)m[u]) - 4503599627370496.0) : 0.0;
+            hist_update<U, false>(my_sum, my_cnt, turn, row, phi, m);
+        } else if (lean && t0 + TRIP <= len && (MODE != 0 || t0 + TRIP <= s_fb[kU])) {
+            // ---- lean trip: complete, one field, constant volume ----
+            double lum[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) lum[u] = __ldcs(p_lum + base + u * STRIDE);
             if (MODE == 2) {
-                phi[u] = in ? __ldcs(p_phi + off) : 0.0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) phi[u] = __ldcs(p_phi + base + u * STRIDE);
             } else {
-                flux[u] = in ? __ldcs(p_flux + off) : 1.0;
-                vol[u] = (in && p_vol) ? __ldcs(p_vol + off) : a.vol_int;
-                if (in && p_valid) ok[u] = p_valid[off] != 0;
-            }
-        }
-        if (MODE == 0) {
+                double flux[U];
 #pragma unroll
-            for (int u = 0; u < VP_UNROLL; ++u) {
-                const int off = t0 + u * (32 * VP_WARPS) + threadIdx.x;
-                while (off >= kend && k + 1 < a.K) {                         // next field (rare)
-                    ++k;
-                    kend = s_fb[k];
-                    F50 = s_fk[k][0]; iF50 = s_fk[k][1]; ftau = s_fk[k][2]; iftau = s_fk[k][3];
-                }
-                const double icomp = inv_fleming_stream(flux[u], F50, iF50, alpha_log10e, a.alpha, ftau, iftau, modified, s_exp, s_logm);
-                const double ipv = p_vol ? 1.0 / (a.pref * vol[u]) : a.inv_pref_vol;
-                phi[u] = ok[u] ? icomp * ipv : 0.0;                          // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
-                if (off < len) __stcs(p_phi + off, phi[u]);
-            }
-        }
-        if (!BOOT) {
+                for (int u = 0; u < U; ++u) flux[u] = __ldcs(p_flux + base + u * STRIDE);
+                const double iF50 = s_fk[kU][1], iftau = s_fk[kU][3];
+                unsigned badmask = 0u;
+                if (modified) {
 #pragma unroll
-            for (int u = 0; u < VP_UNROLL; ++u) {
-                const int off = t0 + u * (32 * VP_WARPS) + threadIdx.x;
-                jb[u] = bin_of_rep(lum[u], s_edges, lane & 15, nb, e0, enb, scale);
-                if (off < len) p_bin[off] = (short)jb[u];                    // kept resident for the bootstrap replicates
-            }
-        }
-#pragma unroll
-        for (int tn = 0; tn < 2; ++tn) {
-            if (turn == tn) {
-#pragma unroll
-                for (int u = 0; u < VP_UNROLL; ++u)
-                    if (jb[u] >= 0 && m[u] != 0u) {
-                        my_sum[jb[u] * VP_COLS] += BOOT ? phi[u] * (double)m[u] : phi[u];
-                        my_cnt[jb[u] * VP_COLS] += m[u];
+                    for (int u = 0; u < U; ++u) {
+                        bool bad;
+                        phi[u] = inv_fleming_stream<true>(flux[u], iF50, alpha_log10e, iftau, s_exp, s_logm, bad);
+                        badmask |= bad ? 1u << u : 0u;
                     }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        bool bad;
+                        phi[u] = inv_fleming_stream<false>(flux[u], iF50, alpha_log10e, iftau, s_exp, s_logm, bad);
+                        badmask |= bad ? 1u << u : 0u;
+                    }
+                }
+                if (badmask) {                                               // rare: outside the fast range
+#pragma unroll
+                    for (int u = 0; u < U; ++u)
+                        if (badmask >> u & 1u) phi[u] = inv_fleming_literal(flux[u], s_fk[kU][0], a.alpha, s_fk[kU][2], modified);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    phi[u] *= a.inv_pref_vol;                                // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
+                    __stcs(p_phi + base + u * STRIDE, phi[u]);
+                }
             }
-            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                row[u] = row_fast(lum[u], e_col, a.bscale, a.bC, a.hi_lo, a.hi_span);
+                p_row[base + u * STRIDE] = (short)row[u];                    // kept resident for the bootstrap replicates
+            }
+            hist_update<U, true>(my_sum, my_cnt, turn, row, phi, m);
+        } else {
+            // ---- general trip: partial, field boundary inside, per-source volume / validity, irregular edges ----
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int off = base + u * STRIDE;
+                const bool in = off < len;
+                m[u] = in ? 1u : 0u;
+                const double lum = in ? __ldcs(p_lum + off) : -1.0e300;      // below every edge: lands in no bin
+                if (MODE == 2) {
+                    phi[u] = in ? __ldcs(p_phi + off) : 0.0;
+                } else {
+                    const double flux = in ? __ldcs(p_flux + off) : 1.0;
+                    const double vol = (in && p_vol) ? __ldcs(p_vol + off) : a.vol_int;
+                    const bool ok = in && (p_valid ? p_valid[off] != 0 : true);
+                    int k = kU;
+                    while (off >= s_fb[k]) ++k;
+                    bool bad;
+                    double icomp = modified ? inv_fleming_stream<true>(flux, s_fk[k][1], alpha_log10e, s_fk[k][3], s_exp, s_logm, bad)
+                                            : inv_fleming_stream<false>(flux, s_fk[k][1], alpha_log10e, s_fk[k][3], s_exp, s_logm, bad);
+                    if (bad) icomp = inv_fleming_literal(flux, s_fk[k][0], a.alpha, s_fk[k][2], modified);
+                    const double ipv = p_vol ? 1.0 / (a.pref * vol) : a.inv_pref_vol;
+                    phi[u] = ok ? icomp * ipv : 0.0;                         // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
+                    if (in) __stcs(p_phi + off, phi[u]);
+                }
+                row[u] = bin_of_rep(lum, e_rep, lane & 15, nb, e0, enb, scale) + 1;
+                if (in) p_row[off] = (short)row[u];
+            }
+            hist_update<U, false>(my_sum, my_cnt, turn, row, phi, m);
         }
     }
     __syncthreads();
@@ -247,10 +335,8 @@ __global__ void __launch_bounds__(32 * VP_WARPS) k_veff_priv(VeffArgs a) {
     for (int jb = warp; jb < nb; jb += VP_WARPS) {
         double s = 0.0;
         unsigned long long c = 0ULL;
-        for (int wv = lane >> 4; wv < VP_WARPS; wv += 2) {
-            s += s_sum[(wv * nb + jb) * VP_COLS + (lane & (VP_COLS - 1))];
-            c += s_cnt[(wv * nb + jb) * VP_COLS + (lane & (VP_COLS - 1))];
-        }
+        for (int wv = lane >> 4; wv < VP_WARPS; wv += 2) s += s_sum[(wv * nrow + jb + 1) * VP_COLS + (lane & (VP_COLS - 1))];
+        if (lane < VP_WARPS) c = s_cnt[lane * nrow + jb + 1];
         for (int o = 16; o > 0; o >>= 1) {
             s += __shfl_xor_sync(0xffffffffu, s, o);
             c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -282,7 +368,7 @@ __global__ void k_veff_reduce(int nblocks, int nbins, const unsigned long long* 
 struct VeffPlan { bool priv; int blocks, threads; size_t smem; };
 static VeffPlan veff_plan(const lf_ctx* c, long long n, int nbins) {
     VeffPlan p;
-    const size_t priv = sizeof(double) * (nbins + 1) * 16 + (size_t)VP_WARPS * nbins * VP_COLS * (sizeof(double) + sizeof(unsigned)) +
+    const size_t priv = sizeof(double) * (nbins + 5) * 16 + (size_t)VP_WARPS * (nbins + 2) * (VP_COLS * sizeof(double) + sizeof(unsigned)) +
                         sizeof(double2) * STREAM_LOG_N + sizeof(double) * EXP_TAB_N;
     if (priv <= VP_SMEM_MAX) {
         int per_sm = (int)std::min<size_t>(8, (size_t)(227 * 1024) / (priv + 1024));
@@ -297,6 +383,24 @@ static VeffPlan veff_plan(const lf_ctx* c, long long n, int nbins) {
     }
     return p;
 }
+// Lean-route test for the caller's edges (k_veff_priv, row_fast): positive, increasing, every edge within 0.4 bin of a
+// uniform grid (numpy.linspace edges are within 1e-13), bins much wider than the high-word granule of a double.
+static inline int hi_word(double v) { unsigned long long u; memcpy(&u, &v, sizeof(u)); return (int)(u >> 32); }
+static void edges_fast_setup(const double* e, int nb, VeffArgs& a) {
+    a.fast = 0;
+    if (!(e[0] > 0.0) || !std::isfinite(e[nb]) || !(e[nb] > e[0])) return;
+    const double scale = (double)nb / (e[nb] - e[0]);
+    if (!std::isfinite(scale)) return;
+    for (int j = 0; j <= nb; ++j) {
+        if (j > 0 && !(e[j] > e[j - 1])) return;
+        if (!(fabs((e[j] - e[0]) * scale - (double)j) <= 0.4)) return;
+    }
+    if (!(ldexp(e[nb], -19) * scale <= 0.25)) return;
+    a.bscale = scale; a.bC = VP_BIN_MAGIC - e[0] * scale;
+    a.hi_lo = hi_word(e[0]); a.hi_span = (unsigned)(hi_word(e[nb]) - hi_word(e[0]));
+    a.fast = 1;
+}
+
 template <int MODE>
 static void veff_launch(const VeffPlan& p, const VeffArgs& a, cudaStream_t st) {
     if (p.priv) k_veff_priv<MODE><<<p.blocks, p.threads, p.smem, st>>>(a);
@@ -361,6 +465,7 @@ extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const doubl
     a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.vol_int = vol_int; a.modified = modified ? 1 : 0;
     a.inv_pref_vol = 1.0 / (a.pref * vol_int); a.tables = c->d_tables;
     a.edges = c->v_edges; a.nbins = nbins; a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = nullptr; a.bin = c->v_bin;
+    if (!vol_per_source && !valid) edges_fast_setup(edges, nbins, a);
     CK(cudaEventRecord(c->ev0, c->stream));
     veff_launch<0>(plan, a, c->stream);
     k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
@@ -405,6 +510,7 @@ extern "C" int lf_bin_weights(lf_ctx* c, int64_t n, const double* lum, const dou
     memset(&a, 0, sizeof(a));
     a.n = n; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = nbins;
     a.counts = c->v_counts; a.sumphi = c->v_sums; a.bin = c->v_bin;
+    edges_fast_setup(edges, nbins, a);
     CK(cudaEventRecord(c->ev0, c->stream));
     veff_launch<2>(plan, a, c->stream);
     k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);

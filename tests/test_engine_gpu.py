@@ -223,6 +223,69 @@ def test_veff_bit_exact_counts_large(nbins):
     eng.close()
 
 
+@pytest.mark.parametrize('fcmin', [0.1, 0.0])
+@pytest.mark.parametrize('edge_kind', ['linspace', 'irregular'])
+def test_veff_routes_agree_with_numpy(fcmin, edge_kind):
+    """The streaming kernel's lean route (complete single-field trips, near-uniform edges) and its general route
+    (irregular edges, field boundaries, tails) against NumPy: counts bit-exact, weights 1e-13; plain Fleming
+    (fcmin = 0), sources outside the fast-math range (literal fall-back), non-finite and out-of-range luminosities."""
+    rng = np.random.default_rng(11)
+    n = 600000 + 77
+    nbins = 50
+    lum = rng.uniform(40.5, 44.5, n)
+    flux = 10 ** rng.uniform(-17.5, -14.0, n)
+    if edge_kind == 'linspace':
+        edges = np.linspace(41.0, 44.0, nbins + 1)
+    else:
+        edges = np.sort(np.concatenate([[41.0, 44.0], rng.uniform(41.0, 44.0, nbins - 1)]))
+    # out-of-range luminosities carry the extreme fluxes, so the per-bin sums stay finite
+    lum[:64] = 40.0
+    flux[:64] = 10 ** rng.uniform(-24.0, -19.0, 64)            # decay argument < 1e-6 / |ln comp| > 690: literal route
+    flux[64:96] = 10 ** rng.uniform(-13.0, -11.0, 32)          # f / f_tau > 690
+    lum[64:96] = rng.uniform(41.0, 44.0, 32)
+    lum[100:104] = [np.nan, np.inf, -np.inf, 1e300]
+    lum[200:200 + nbins + 1] = edges                           # exactly on every edge
+    lum[300:300 + nbins + 1] = np.nextafter(edges, -np.inf)    # one ulp below every edge
+    fi = np.array([0, 1000, 1000, 250001, n], dtype=np.int64)  # an empty field, boundaries inside trips
+    flim = [2.72, 3.61, 2.55, 3.31]
+    from lumfuncmcmc_b200.engine import LikelihoodEngine
+    eng = LikelihoodEngine(synth.direct_inputs(synth.make_catalogue(300, seed=1, nfields=3), nknots=64), 'free', device=0)
+    phi, counts, sums = eng.veff_bin(flux, lum, fi, flim, 4.56, fcmin, 1.0e6, 3.0e10, edges)
+    with np.errstate(invalid='ignore'):
+        ok = (lum >= edges[0]) & (lum < edges[-1])
+    j = np.searchsorted(edges, lum[ok], side='right') - 1
+    want = np.bincount(j, minlength=nbins)[:nbins]
+    assert np.array_equal(counts, want)
+    assert counts.sum() == ok.sum()
+    flims_arr = np.repeat(flim, np.diff(fi))
+    with np.errstate(all='ignore'):
+        ref_phi = lf_oracle.veff_weights(flux, flims_arr, 4.56, fcmin, 1.0e6, 3.0e10, 0.0)
+    fin = np.isfinite(ref_phi)
+    assert np.array_equal(np.isfinite(phi), fin)
+    # fc = (1 + n / sqrt(1 + n^2)) / 2 cancels for faint sources: NumPy's own value carries eps / fc (times the
+    # exponent 1 / (1 - e^-x) of the modified form), and so does any other evaluation order
+    with np.errstate(all='ignore'):
+        nn = 4.56 * np.log10(flux / (1.0e-17 * flims_arr))
+        cond = 1.0 / (0.5 * (1.0 + nn / np.sqrt(1.0 + nn * nn)))
+        if fcmin:
+            cond = cond / -np.expm1(-flux / (1.0e-17 * flims_arr) * 10 ** (np.sqrt(abs((2 * fcmin - 1) ** 2 / (1 - (2 * fcmin - 1) ** 2))) / 4.56))
+    assert np.all(np.abs(phi[fin] - ref_phi[fin]) <= (1e-13 + 1e-15 * cond[fin]) * ref_phi[fin])
+    typical = fin & (cond < 50.0)
+    assert typical.sum() > 0.8 * n
+    np.testing.assert_allclose(phi[typical], ref_phi[typical], rtol=1e-13)
+    np.testing.assert_allclose(sums, np.bincount(j, weights=ref_phi[ok], minlength=nbins)[:nbins], rtol=1e-12)
+    # the resident rows feed the bootstrap replicates
+    mult = np.bincount(rng.integers(0, n, n), minlength=n)
+    bc, bs = eng.boot_bin(mult)
+    assert np.array_equal(bc, np.bincount(j, weights=mult[ok], minlength=nbins)[:nbins].astype(np.int64))
+    np.testing.assert_allclose(bs, np.bincount(j, weights=(ref_phi * mult)[ok], minlength=nbins)[:nbins], rtol=1e-12)
+    # binning caller-provided weights (getBootErrLog's entry point) takes the same routes
+    c2, s2 = eng.bin_weights(lum, np.where(fin, ref_phi, 0.0), edges)
+    assert np.array_equal(c2, want)
+    np.testing.assert_allclose(s2, np.bincount(j, weights=np.where(fin, ref_phi, 0.0)[ok], minlength=nbins)[:nbins], rtol=1e-12)
+    eng.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # optional FP32 mode of the walker x source loop: 1e-5 relative (BASELINE.json north_star)
 # ---------------------------------------------------------------------------------------------------------------
