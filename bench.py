@@ -320,12 +320,14 @@ def main():
         from lumfuncmcmc_b200.sampler import DeviceEnsembleSampler
         dev_s = DeviceEnsembleSampler(100, eng_s.ndim, eng_s, seed=17)
         dev_s.run_mcmc(th_s, 50)
-        t0 = time.perf_counter()
-        dev_s.run_mcmc(dev_s.chain[:, -1, :], 2000)
-        dt_d = time.perf_counter() - t0
+        dt_d = 1e9
+        for _ in range(3):                      # the first long run also pays the first touch of the host chain arrays
+            t0 = time.perf_counter()
+            dev_s.run_mcmc(dev_s.chain[:, -1, :], 2000)
+            dt_d = min(dt_d, time.perf_counter() - t0)
         small = {"workload": "BASELINE.json configs[0] size: 1e4 sources x 100 walkers, 1 GPU",
-                 "steps_per_s": 2000 / dt_d, "sampler": "device-resident (lf_sampler_run), 2000 updates, wall clock incl. chain D2H",
-                 "device_ms_per_step": dev_s.device_ms / 2050, "steps_per_s_device_time": 2050.0e3 / dev_s.device_ms, "acceptance": float(np.mean(dev_s.acceptance_fraction)),
+                 "steps_per_s": 2000 / dt_d, "sampler": "device-resident (lf_sampler_run), best of 3 runs of 2000 updates, wall clock incl. chain D2H",
+                 "device_ms_per_step": dev_s.device_ms / 6050, "steps_per_s_device_time": 6050.0e3 / dev_s.device_ms, "acceptance": float(np.mean(dev_s.acceptance_fraction)),
                  "host_sampler": {"steps_per_s": 200 / dt_s, "lnprob_calls_per_s": 400 / dt_s,
                                   "acceptance": float(np.mean(smp_s.acceptance_fraction))}}
         eng_s.close()
