@@ -270,7 +270,11 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
         __syncthreads();
     }
     const int count_src = a.cls_count[cls], count_quad = a.cls_count[LITERAL ? 6 : 5];
-    const int n_wg = (count_src + 31) >> 5, n_wgq = (count_quad + 31) >> 5;      // n_wg == 0: n_items == 0, the loop exits at once
+    // Z fast kernel: a source item covers TWO walkers per lane (64 per warp), so every broadcast source load feeds two
+    // terms -- the loop is bound by the load-store data path (16 B x 32 lanes per source), not by the FP64 pipe
+    constexpr bool PAIR = MODEL == LF_MODEL_Z && !LITERAL;
+    const int n_wg = PAIR ? (count_src + 63) >> 6 : (count_src + 31) >> 5;      // n_wg == 0: n_items == 0, the loop exits at once
+    const int n_wgq = (count_quad + 31) >> 5;
     const long long n_src_items = (long long)n_wg * a.n_src_slabs;
     const long long n_items = n_src_items + (long long)n_wgq * a.n_quad_slabs;
     // persistent warps: every warp pulls (walker group, slab) items from a global counter until none are left.
@@ -303,11 +307,13 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
     const int row = (int)(it / groups) + (is_src ? 0 : a.n_src_slabs);
     const int count = is_src ? count_src : count_quad;
     const int* list = is_src ? (LITERAL ? a.list_lit : a.list_fast) : (LITERAL ? a.list_litq : a.list_fastq);
-    const int slot = wg * 32 + lane;
+    const int slot = (PAIR && is_src ? wg * 64 : wg * 32) + lane;
     const bool active = slot < count;
     const long long w = list[active ? slot : count - 1];       // inactive lanes shadow a valid walker
     const double* wp = a.wp + w;
-    double acc0 = 0.0, acc1 = 0.0;
+    const bool activeB = PAIR && is_src && slot + 32 < count;   // second walker of the lane (Z source items)
+    const long long wB = PAIR ? list[activeB ? slot + 32 : count - 1] : w;
+    double acc0 = 0.0, acc1 = 0.0, accB = 0.0;
 
     if (row < a.n_src_slabs) {
         // ---------------- source slab ----------------
@@ -458,77 +464,97 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
             }
         } else {
             const double aL = wp[P_AL * WS], bL = wp[P_BL * WS], cL = wp[P_CL * WS];
-            if (!LITERAL && a.precision == LF_PREC_F32) {
-                // FP32 mode: L*(z) re-centred on the middle pivot and on 42 so the float polynomial keeps ~1e-7 dex
-                const double z2 = a.z2;
-                const float q2 = (float)aL, q1 = (float)(bL + 2.0 * aL * z2);
-                const float q0 = (float)((fma(fma(aL, z2, bL), z2, cL) - 42.0));
-                const float L2T = 3.3219280948873623f;                              // log2(10)
-                const float2* __restrict__ pf = a.src2f + i0;
-                const long long cnt = i1 - i0;
-                double sum = 0.0;
-                for (long long j0 = 0; j0 < cnt; j0 += 64) {
-                    const long long j1 = j0 + 64 < cnt ? j0 + 64 : cnt;
-                    float f0 = 0.f, f1 = 0.f;
-                    long long j = j0;
-                    for (; j + 8 <= j1; j += 8) {                   // eight independent MUFU chains per thread
-                        float2 u[8];
-                        float e[8];
+            if (!LITERAL && (a.precision == LF_PREC_F32 || a.csrc != nullptr)) {
+              // FP32 mode / compressed catalogue: one walker of the pair after the other
+              for (int h = 0; h < 2; ++h) {
+                const double* wq = h == 0 ? wp : a.wp + wB;
+                const double aL = wq[P_AL * WS], bL = wq[P_BL * WS], cL = wq[P_CL * WS];
+                double accH = 0.0;
+                if (a.precision == LF_PREC_F32) {
+                    // FP32 mode: L*(z) re-centred on the middle pivot and on 42 so the float polynomial keeps ~1e-7 dex
+                    const double z2 = a.z2;
+                    const float q2 = (float)aL, q1 = (float)(bL + 2.0 * aL * z2);
+                    const float q0 = (float)((fma(fma(aL, z2, bL), z2, cL) - 42.0));
+                    const float L2T = 3.3219280948873623f;                              // log2(10)
+                    const float2* __restrict__ pf = a.src2f + i0;
+                    const long long cnt = i1 - i0;
+                    double sum = 0.0;
+                    for (long long j0 = 0; j0 < cnt; j0 += 64) {
+                        const long long j1 = j0 + 64 < cnt ? j0 + 64 : cnt;
+                        float f0 = 0.f, f1 = 0.f;
+                        long long j = j0;
+                        for (; j + 8 <= j1; j += 8) {                   // eight independent MUFU chains per thread
+                            float2 u[8];
+                            float e[8];
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) u[t] = __ldg(pf + j + t);
+                            for (int t = 0; t < 8; ++t) u[t] = __ldg(pf + j + t);
 #pragma unroll
-                        for (int t = 0; t < 8; ++t) e[t] = mufu_ex2((u[t].x - fmaf(fmaf(q2, u[t].y, q1), u[t].y, q0)) * L2T);
+                            for (int t = 0; t < 8; ++t) e[t] = mufu_ex2((u[t].x - fmaf(fmaf(q2, u[t].y, q1), u[t].y, q0)) * L2T);
 #pragma unroll
-                        for (int t = 0; t < 8; t += 2) { f0 += e[t]; f1 += e[t + 1]; }
+                            for (int t = 0; t < 8; t += 2) { f0 += e[t]; f1 += e[t + 1]; }
+                        }
+                        for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += mufu_ex2((u0.x - fmaf(fmaf(q2, u0.y, q1), u0.y, q0)) * L2T); }
+                        sum += (double)(f0 + f1);
                     }
-                    for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += mufu_ex2((u0.x - fmaf(fmaf(q2, u0.y, q1), u0.y, q0)) * L2T); }
-                    sum += (double)(f0 + f1);
+                    accH -= sum;
+                } else {
+                    // compressed catalogue: sum_m v_m 2^(-P2(xi_m)) over this slab of pseudo-sources (compress_sources_z)
+                    const double L2T = 3.32192809488736234787;
+                    const double a2 = aL * L2T, b2 = bL * L2T, c2 = cL * L2T;
+                    const long long m0 = (a.M * row) / a.n_src_slabs, m1 = (a.M * (row + 1)) / a.n_src_slabs;
+                    for (long long m = m0; m < m1; ++m) {
+                        const double xi = __ldg(&a.csrc[2 * m]).x, v = __ldg(&a.csrc[2 * m + 1]).x;
+                        accH = fma(-v, exp2_full<false>(-fma(fma(a2, xi, b2), xi, c2), s_exp_rep, rep16), accH);
+                    }
                 }
-                acc0 -= sum;
-            } else if (!LITERAL && a.csrc != nullptr) {
-                // compressed catalogue: sum_m v_m 2^(-P2(xi_m)) over this slab of pseudo-sources (compress_sources_z)
-                const double L2T = 3.32192809488736234787;
-                const double a2 = aL * L2T, b2 = bL * L2T, c2 = cL * L2T;
-                const long long m0 = (a.M * row) / a.n_src_slabs, m1 = (a.M * (row + 1)) / a.n_src_slabs;
-                for (long long m = m0; m < m1; ++m) {
-                    const double xi = __ldg(&a.csrc[2 * m]).x, v = __ldg(&a.csrc[2 * m + 1]).x;
-                    acc0 = fma(-v, exp2_full<false>(-fma(fma(a2, xi, b2), xi, c2), s_exp_rep, rep16), acc0);
-                }
+                if (h == 0) acc0 = accH; else accB = accH;
+              }
             } else if (!LITERAL) {
                 // only sum_i 10^(lum_i - L*(z_i)) needs the walker x source loop; the rest is in P_LNPART0.
-                // Base 2 throughout: 2^(log2(10) lum_i - P2(z_i)), 11 FP64 instructions per term
+                // Base 2 and centred: with u = z - z2 (middle pivot) L*(z) = aL u^2 + b' u + L*(z2), so
+                // 10^(lum - L*) = 10^(42 - L*(z2)) 2^(x - (a2 u + b2) u) with x = log2(10) (lum - 42) stored per source:
+                // 9 FP64 instructions per term, the factor is applied once per work item
                 const double L2T = 3.32192809488736234787;                              // log2(10)
-                const double a2 = aL * L2T, b2 = bL * L2T, c2 = cL * L2T;
-                // four sources in lock-step (four independent FP64 chains per thread); groups are double-buffered in two
-                // register sets (no copies): the next group's loads are issued before the current group's arithmetic
+                const double zp = a.z2;
+                const double* wq = a.wp + wB;                                            // the lane's second walker
+                const double aLB = wq[P_AL * WS], bLB = wq[P_BL * WS], cLB = wq[P_CL * WS];
+                const double a2 = aL * L2T, b2 = fma(2.0 * aL, zp, bL) * L2T;
+                const double a2B = aLB * L2T, b2B = fma(2.0 * aLB, zp, bLB) * L2T;
+                const double scale = exp2_full<false>(L2T * (42.0 - fma(fma(aL, zp, bL), zp, cL)), s_exp_rep, rep16);
+                const double scaleB = exp2_full<false>(L2T * (42.0 - fma(fma(aLB, zp, bLB), zp, cLB)), s_exp_rep, rep16);
+                // two sources x two walkers in lock-step (four independent FP64 chains per thread); groups of four sources
+                // are double-buffered in two register sets (no copies): the next group's loads are issued before the
+                // current group's arithmetic
                 const double2* __restrict__ ps = a.src2 + i0;
                 const int cnt = (int)(i1 - i0);
-                double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
-                auto four = [&](const double2& s0, const double2& s1, const double2& s2, const double2& s3) {
-                    const double d0 = fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2));
-                    const double d1 = fma(L2T, s1.x, -fma(fma(a2, s1.y, b2), s1.y, c2));
-                    const double d2 = fma(L2T, s2.x, -fma(fma(a2, s2.y, b2), s2.y, c2));
-                    const double d3 = fma(L2T, s3.x, -fma(fma(a2, s3.y, b2), s3.y, c2));
+                double e0 = 0.0, e1 = 0.0, f0 = 0.0, f1 = 0.0;
+                auto two = [&](const double2& s0, const double2& s1) {
+                    const double d0 = fma(-fma(a2, s0.y, b2), s0.y, s0.x);
+                    const double d1 = fma(-fma(a2, s1.y, b2), s1.y, s1.x);
+                    const double g0 = fma(-fma(a2B, s0.y, b2B), s0.y, s0.x);
+                    const double g1 = fma(-fma(a2B, s1.y, b2B), s1.y, s1.x);
                     e0 += exp2_full<false>(d0, s_exp_rep, rep16);
                     e1 += exp2_full<false>(d1, s_exp_rep, rep16);
-                    e2 += exp2_full<false>(d2, s_exp_rep, rep16);
-                    e3 += exp2_full<false>(d3, s_exp_rep, rep16);
+                    f0 += exp2_full<false>(g0, s_exp_rep, rep16);
+                    f1 += exp2_full<false>(g1, s_exp_rep, rep16);
                 };
                 double2 A0, A1, A2, A3, B0, B1, B2, B3;
                 int j = 0;
                 if (cnt >= 4) { A0 = __ldg(ps); A1 = __ldg(ps + 1); A2 = __ldg(ps + 2); A3 = __ldg(ps + 3); }
                 for (; j + 8 <= cnt; j += 8) {
                     B0 = __ldg(ps + j + 4); B1 = __ldg(ps + j + 5); B2 = __ldg(ps + j + 6); B3 = __ldg(ps + j + 7);
-                    four(A0, A1, A2, A3);
+                    two(A0, A1); two(A2, A3);
                     if (j + 12 <= cnt) { A0 = __ldg(ps + j + 8); A1 = __ldg(ps + j + 9); A2 = __ldg(ps + j + 10); A3 = __ldg(ps + j + 11); }
-                    four(B0, B1, B2, B3);
+                    two(B0, B1); two(B2, B3);
                 }
-                if (j + 4 <= cnt) { four(A0, A1, A2, A3); j += 4; }
+                if (j + 4 <= cnt) { two(A0, A1); two(A2, A3); j += 4; }
                 for (; j < cnt; ++j) {
                     const double2 s0 = __ldg(ps + j);
-                    e0 += exp2_full<false>(fma(L2T, s0.x, -fma(fma(a2, s0.y, b2), s0.y, c2)), s_exp_rep, rep16);
+                    e0 += exp2_full<false>(fma(-fma(a2, s0.y, b2), s0.y, s0.x), s_exp_rep, rep16);
+                    f0 += exp2_full<false>(fma(-fma(a2B, s0.y, b2B), s0.y, s0.x), s_exp_rep, rep16);
                 }
-                acc0 -= (e0 + e1) + (e2 + e3);
+                acc0 = -scale * (e0 + e1);
+                accB = -scaleB * (f0 + f1);
             } else {
                 const double aP = wp[P_AP * WS], bP = wp[P_BP * WS], cP = wp[P_CP * WS], sal = wp[P_SCHAL * WS];
                 for (long long i = i0; i < i1; ++i) {                                 // lumfuncmcmc_z.py:371
@@ -675,6 +701,7 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
         }
     }
     if (active) a.partial[(long long)row * WS + w] = acc0 + acc1;
+    if (PAIR && activeB) a.partial[(long long)row * WS + wB] = accB;
   }
 }
 
@@ -736,7 +763,9 @@ __global__ void k_derive_z(long long n, const double* __restrict__ lum, const do
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     if (src2f) src2f[i] = make_float2((float)(lum[i] - 42.0), (float)(z[i] - zref));
-    src2[i] = make_double2(lum[i], z[i]);
+    // fast FP64 loop: (log2(10) (lum - 42), z - z_pivot2): the walker's quadratic L*(z) is evaluated about the middle
+    // pivot, its constant term leaves the loop as one factor per walker
+    src2[i] = make_double2((lum[i] - 42.0) * 3.32192809488736234787, z[i] - zref);
 }
 __global__ void k_pow10(long long n, const double* __restrict__ lum, double* __restrict__ Lsrc) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
