@@ -270,9 +270,9 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
         __syncthreads();
     }
     const int count_src = a.cls_count[cls], count_quad = a.cls_count[LITERAL ? 6 : 5];
-    // Z fast kernel: a source item covers TWO walkers per lane (64 per warp), so every broadcast source load feeds two
-    // terms -- the loop is bound by the load-store data path (16 B x 32 lanes per source), not by the FP64 pipe
-    constexpr bool PAIR = MODEL == LF_MODEL_Z && !LITERAL;
+    // FREE / Z fast kernels: a source item covers TWO walkers per lane (64 per warp), so every broadcast source load
+    // (16 B x 32 lanes = 4 wavefronts of the load-store data path, the busiest unit of these loops) feeds two terms
+    constexpr bool PAIR = (MODEL == LF_MODEL_Z || MODEL == LF_MODEL_FREE) && !LITERAL;
     const int n_wg = PAIR ? (count_src + 63) >> 6 : (count_src + 31) >> 5;      // n_wg == 0: n_items == 0, the loop exits at once
     const int n_wgq = (count_quad + 31) >> 5;
     const long long n_src_items = (long long)n_wg * a.n_src_slabs;
@@ -318,143 +318,200 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
     if (row < a.n_src_slabs) {
         // ---------------- source slab ----------------
         long long i0 = (a.N * row) / a.n_src_slabs, i1 = (a.N * (row + 1)) / a.n_src_slabs;
-        if (MODEL == LF_MODEL_FREE && !LITERAL && a.csrc != nullptr) {
-            // compressed catalogue: sum_m w_m t(xi_m) over this slab of pseudo-sources (see lumfuncmcmc_b200/compress.py)
-            const double alpha = wp[P_ALPHA * WS];
-            long long m0 = (a.M * row) / a.n_src_slabs, m1 = (a.M * (row + 1)) / a.n_src_slabs;
-            int k = 0;
-            while (k + 1 < a.K && m0 >= a.cfield_ind[k + 1]) ++k;
-            while (m0 < m1) {
-                const long long seg_end = a.cfield_ind[k + 1] < m1 ? a.cfield_ind[k + 1] : m1;
-                const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], c2 = wp[(P_FIELD0 + 4 * k + 1) * WS];
-                long long m = m0;
-                for (; m + 1 < seg_end; m += 2) {
-                    const double2 u0 = __ldg(&a.csrc[2 * m]), u1 = __ldg(&a.csrc[2 * m + 2]);
-                    const double w0 = __ldg(&a.csrc[2 * m + 1]).x, w1 = __ldg(&a.csrc[2 * m + 3]).x;
-                    double lg0, rd0, lg1, rd1;
-                    if (a.modified) {
-                        fleming_log_parts<true>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
-                        fleming_log_parts<true>(u1.x, u1.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg1, rd1);
-                    } else {
-                        fleming_log_parts<false>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
-                        fleming_log_parts<false>(u1.x, u1.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg1, rd1);
-                    }
-                    acc0 = fma(w0 * lg0, rd0, acc0);
-                    acc1 = fma(w1 * lg1, rd1, acc1);
-                }
-                if (m < seg_end) {
-                    const double2 u0 = __ldg(&a.csrc[2 * m]);
-                    const double w0 = __ldg(&a.csrc[2 * m + 1]).x;
-                    double lg0, rd0;
-                    if (a.modified) fleming_log_parts<true>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
-                    else fleming_log_parts<false>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
-                    acc0 = fma(w0 * lg0, rd0, acc0);
-                }
-                m0 = seg_end;
-                ++k;
-            }
-        } else if (MODEL == LF_MODEL_FREE) {
-            const double alpha = wp[P_ALPHA * WS];
+        if (MODEL == LF_MODEL_FREE && PAIR && a.precision != LF_PREC_F32 && a.csrc == nullptr && a.modified) {
+            // FP64 walker x source loop, two walkers per lane: every broadcast source load (4 wavefronts of the
+            // load-store data path for 16 B x 32 lanes) feeds two terms.  Chains: (s0, A), (s0, B), (s1, A), (s1, B).
+            const double* wq = a.wp + wB;
+            const double alphaA = wp[P_ALPHA * WS], alphaB = wq[P_ALPHA * WS];
+            const double al[4] = {alphaA, alphaB, alphaA, alphaB};
+            double accv[4] = {0.0, 0.0, 0.0, 0.0};
             int k = field_of(a, i0);
             while (i0 < i1) {
-                long long seg_end = a.field_ind[k + 1] < i1 ? a.field_ind[k + 1] : i1;
-                if (!LITERAL && a.precision == LF_PREC_F32) {
-                    // FP32 mode: MUFU transcendentals; partial sums in FP32 over 64-source chunks, flushed to FP64
-                    const double aFd = wp[(P_FIELD0 + 4 * k + 0) * WS];           // -alpha*log10(F50)
-                    const float af = (float)alpha;
-                    const float aFs = (float)(aFd - 17.0 * alpha);                 // -alpha*log10(F50*1e17)
-                    const float c2 = (float)(wp[(P_FIELD0 + 4 * k + 1) * WS] * 1.0e-17);
-                    const float2* __restrict__ pf = a.src2f + i0;
-                    const int cnt = (int)(seg_end - i0);
-                    double sum = 0.0;
-                    for (int j0 = 0; j0 < cnt; j0 += 64) {
-                        const int j1 = min(j0 + 64, cnt);
-                        float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
-                        int j = j0;
-                        if (a.modified) {
-#ifndef LF_F32_ILP
-#define LF_F32_ILP 16
-#endif
-                            for (; j + LF_F32_ILP <= j1; j += LF_F32_ILP) {
-                                float2 u[LF_F32_ILP];
-                                float tt[LF_F32_ILP];
-#pragma unroll
-                                for (int t = 0; t < LF_F32_ILP; ++t) u[t] = __ldg(pf + j + t);
-#pragma unroll
-                                for (int t = 0; t < LF_F32_ILP; ++t) tt[t] = fleming_log2_f32<true>(u[t].x, u[t].y, af, aFs, c2);
-#pragma unroll
-                                for (int t = 0; t < LF_F32_ILP; t += 4) { f0 += tt[t]; f1 += tt[t + 1]; f2 += tt[t + 2]; f3 += tt[t + 3]; }
-                            }
-                            for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += fleming_log2_f32<true>(u0.x, u0.y, af, aFs, c2); }
-                        } else {
-                            for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += fleming_log2_f32<false>(u0.x, u0.y, af, aFs, c2); }
-                        }
-                        sum += (double)((f0 + f1) + (f2 + f3));
-                    }
-                    acc0 = fma(sum, LN2, acc0);
-                } else if (!LITERAL) {
-                    const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], c2 = wp[(P_FIELD0 + 4 * k + 1) * WS];
-                    long long i = i0;
-                    if (a.modified) {
-                        // LF_ILP sources per group, evaluated in lock-step (LF_ILP independent FP64 chains per thread);
-                        // groups are double-buffered: the next group's broadcast loads are issued before the current
-                        // group's arithmetic.  32-bit trip counter.
-                        const double2* __restrict__ ps = a.src2 + i;
-                        const int cnt = (int)(seg_end - i);
-                        constexpr int NT = LF_ILP;
-                        double2 A[NT], B[NT];
-                        double accv[NT];
-#pragma unroll
-                        for (int t = 0; t < NT; ++t) accv[t] = 0.0;
-                        int j = 0;
-                        if (cnt >= NT) {
-#pragma unroll
-                            for (int t = 0; t < NT; ++t) A[t] = __ldg(ps + t);
-                        }
-                        for (; j + 2 * NT <= cnt; j += 2 * NT) {
-#pragma unroll
-                            for (int t = 0; t < NT; ++t) B[t] = __ldg(ps + j + NT + t);
-                            fleming_terms<NT>(A, alpha, aF, c2, s_exp, s_log, rep16, rep8, accv);
-                            if (j + 3 * NT <= cnt) {
-#pragma unroll
-                                for (int t = 0; t < NT; ++t) A[t] = __ldg(ps + j + 2 * NT + t);
-                            }
-                            fleming_terms<NT>(B, alpha, aF, c2, s_exp, s_log, rep16, rep8, accv);
-                        }
-                        if (j + NT <= cnt) {
-                            fleming_terms<NT>(A, alpha, aF, c2, s_exp, s_log, rep16, rep8, accv);
-                            j += NT;
-                        }
-#pragma unroll
-                        for (int t = 0; t < NT; t += 2) { acc0 += accv[t]; acc1 += accv[t + 1]; }
-                        for (; j < cnt; ++j) {
-                            double2 s0 = __ldg(ps + j);
-                            double lg0, rd0;
-                            fleming_log_parts<true>(s0.x, s0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
-                            acc0 = fma(lg0, rd0, acc0);
-                        }
-                    } else {
-                        for (; i < seg_end; ++i) {
-                            double2 s0 = __ldg(&a.src2[i]);
-                            double lg0, rd0;
-                            fleming_log_parts<false>(s0.x, s0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
-                            acc0 += lg0;
-                        }
-                    }
-                } else {
-                    // reference order: log( Phi_i * (int(Omega_0)/sqarcsec * fleming(f_i)) )  (lumfuncmcmc.py:370)
-                    const double F50 = wp[(P_FIELD0 + 4 * k + 2) * WS], ftau = wp[(P_FIELD0 + 4 * k + 3) * WS];
-                    const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
-                    const double om = a.fs[k].om0_over_sq;
-                    for (long long i = i0; i < seg_end; ++i) {
-                        double phi = schechter_literal(__ldg(&a.lum[i]), sal, Lstar, phistar);
-                        double Om = om * fleming_literal(__ldg(&a.flux[i]), F50, alpha, ftau, a.modified != 0);
-                        acc0 += log(phi * Om);
-                    }
+                const long long seg_end = a.field_ind[k + 1] < i1 ? a.field_ind[k + 1] : i1;
+                const double aFA = wp[(P_FIELD0 + 4 * k + 0) * WS], c2A = wp[(P_FIELD0 + 4 * k + 1) * WS];
+                const double aFB = wq[(P_FIELD0 + 4 * k + 0) * WS], c2B = wq[(P_FIELD0 + 4 * k + 1) * WS];
+                const double af[4] = {aFA, aFB, aFA, aFB}, cc[4] = {c2A, c2B, c2A, c2B};
+                auto two = [&](const double2& s0, const double2& s1) {
+                    const double ux[4] = {s0.x, s0.x, s1.x, s1.x}, uy[4] = {s0.y, s0.y, s1.y, s1.y};
+                    fleming_terms_v<4>(ux, uy, al, af, cc, s_exp, s_log, rep16, rep8, accv);
+                };
+                // groups of four sources are double-buffered: the next group's broadcast loads are issued before the
+                // current group's arithmetic.  32-bit trip counter.
+                const double2* __restrict__ ps = a.src2 + i0;
+                const int cnt = (int)(seg_end - i0);
+                double2 A0, A1, A2, A3, B0, B1, B2, B3;
+                int j = 0;
+                if (cnt >= 4) { A0 = __ldg(ps); A1 = __ldg(ps + 1); A2 = __ldg(ps + 2); A3 = __ldg(ps + 3); }
+                for (; j + 8 <= cnt; j += 8) {
+                    B0 = __ldg(ps + j + 4); B1 = __ldg(ps + j + 5); B2 = __ldg(ps + j + 6); B3 = __ldg(ps + j + 7);
+                    two(A0, A1); two(A2, A3);
+                    if (j + 12 <= cnt) { A0 = __ldg(ps + j + 8); A1 = __ldg(ps + j + 9); A2 = __ldg(ps + j + 10); A3 = __ldg(ps + j + 11); }
+                    two(B0, B1); two(B2, B3);
+                }
+                if (j + 4 <= cnt) { two(A0, A1); two(A2, A3); j += 4; }
+                for (; j < cnt; ++j) {
+                    const double2 s0 = __ldg(ps + j);
+                    double lg0, rd0;
+                    fleming_log_parts<true>(s0.x, s0.y, alphaA, aFA, c2A, s_exp, s_log, rep16, rep8, lg0, rd0);
+                    accv[0] = fma(lg0, rd0, accv[0]);
+                    fleming_log_parts<true>(s0.x, s0.y, alphaB, aFB, c2B, s_exp, s_log, rep16, rep8, lg0, rd0);
+                    accv[1] = fma(lg0, rd0, accv[1]);
                 }
                 i0 = seg_end;
                 ++k;
             }
+            acc0 = accv[0] + accv[2];
+            accB = accv[1] + accv[3];
+        } else if (MODEL == LF_MODEL_FREE) {
+          // every other route of the free-completeness model: one walker of the lane after the other
+          const long long i0s = i0;
+          double& out0 = acc0;
+          double& out1 = acc1;
+          const int nh = PAIR && wg * 64 + 32 < count ? 2 : 1;               // warp-uniform
+          for (int h = 0; h < nh; ++h) {
+            const double* wp = a.wp + (h ? wB : w);
+            long long i0 = i0s;
+            double acc0 = 0.0, acc1 = 0.0;
+            if (!LITERAL && a.csrc != nullptr) {
+                // compressed catalogue: sum_m w_m t(xi_m) over this slab of pseudo-sources (see lumfuncmcmc_b200/compress.py)
+                const double alpha = wp[P_ALPHA * WS];
+                long long m0 = (a.M * row) / a.n_src_slabs, m1 = (a.M * (row + 1)) / a.n_src_slabs;
+                int k = 0;
+                while (k + 1 < a.K && m0 >= a.cfield_ind[k + 1]) ++k;
+                while (m0 < m1) {
+                    const long long seg_end = a.cfield_ind[k + 1] < m1 ? a.cfield_ind[k + 1] : m1;
+                    const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], c2 = wp[(P_FIELD0 + 4 * k + 1) * WS];
+                    long long m = m0;
+                    for (; m + 1 < seg_end; m += 2) {
+                        const double2 u0 = __ldg(&a.csrc[2 * m]), u1 = __ldg(&a.csrc[2 * m + 2]);
+                        const double w0 = __ldg(&a.csrc[2 * m + 1]).x, w1 = __ldg(&a.csrc[2 * m + 3]).x;
+                        double lg0, rd0, lg1, rd1;
+                        if (a.modified) {
+                            fleming_log_parts<true>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            fleming_log_parts<true>(u1.x, u1.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg1, rd1);
+                        } else {
+                            fleming_log_parts<false>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                            fleming_log_parts<false>(u1.x, u1.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg1, rd1);
+                        }
+                        acc0 = fma(w0 * lg0, rd0, acc0);
+                        acc1 = fma(w1 * lg1, rd1, acc1);
+                    }
+                    if (m < seg_end) {
+                        const double2 u0 = __ldg(&a.csrc[2 * m]);
+                        const double w0 = __ldg(&a.csrc[2 * m + 1]).x;
+                        double lg0, rd0;
+                        if (a.modified) fleming_log_parts<true>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                        else fleming_log_parts<false>(u0.x, u0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                        acc0 = fma(w0 * lg0, rd0, acc0);
+                    }
+                    m0 = seg_end;
+                    ++k;
+                }
+            } else {
+                const double alpha = wp[P_ALPHA * WS];
+                int k = field_of(a, i0);
+                while (i0 < i1) {
+                    long long seg_end = a.field_ind[k + 1] < i1 ? a.field_ind[k + 1] : i1;
+                    if (!LITERAL && a.precision == LF_PREC_F32) {
+                        // FP32 mode: MUFU transcendentals; partial sums in FP32 over 64-source chunks, flushed to FP64
+                        const double aFd = wp[(P_FIELD0 + 4 * k + 0) * WS];           // -alpha*log10(F50)
+                        const float af = (float)alpha;
+                        const float aFs = (float)(aFd - 17.0 * alpha);                 // -alpha*log10(F50*1e17)
+                        const float c2 = (float)(wp[(P_FIELD0 + 4 * k + 1) * WS] * 1.0e-17);
+                        const float2* __restrict__ pf = a.src2f + i0;
+                        const int cnt = (int)(seg_end - i0);
+                        double sum = 0.0;
+                        for (int j0 = 0; j0 < cnt; j0 += 64) {
+                            const int j1 = min(j0 + 64, cnt);
+                            float f0 = 0.f, f1 = 0.f, f2 = 0.f, f3 = 0.f;
+                            int j = j0;
+                            if (a.modified) {
+#ifndef LF_F32_ILP
+#define LF_F32_ILP 16
+#endif
+                                for (; j + LF_F32_ILP <= j1; j += LF_F32_ILP) {
+                                    float2 u[LF_F32_ILP];
+                                    float tt[LF_F32_ILP];
+#pragma unroll
+                                    for (int t = 0; t < LF_F32_ILP; ++t) u[t] = __ldg(pf + j + t);
+#pragma unroll
+                                    for (int t = 0; t < LF_F32_ILP; ++t) tt[t] = fleming_log2_f32<true>(u[t].x, u[t].y, af, aFs, c2);
+#pragma unroll
+                                    for (int t = 0; t < LF_F32_ILP; t += 4) { f0 += tt[t]; f1 += tt[t + 1]; f2 += tt[t + 2]; f3 += tt[t + 3]; }
+                                }
+                                for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += fleming_log2_f32<true>(u0.x, u0.y, af, aFs, c2); }
+                            } else {
+                                for (; j < j1; ++j) { float2 u0 = __ldg(pf + j); f0 += fleming_log2_f32<false>(u0.x, u0.y, af, aFs, c2); }
+                            }
+                            sum += (double)((f0 + f1) + (f2 + f3));
+                        }
+                        acc0 = fma(sum, LN2, acc0);
+                    } else if (!LITERAL) {
+                        const double aF = wp[(P_FIELD0 + 4 * k + 0) * WS], c2 = wp[(P_FIELD0 + 4 * k + 1) * WS];
+                        long long i = i0;
+                        if (a.modified) {
+                            // LF_ILP sources per group, evaluated in lock-step (LF_ILP independent FP64 chains per thread);
+                            // groups are double-buffered: the next group's broadcast loads are issued before the current
+                            // group's arithmetic.  32-bit trip counter.
+                            const double2* __restrict__ ps = a.src2 + i;
+                            const int cnt = (int)(seg_end - i);
+                            constexpr int NT = LF_ILP;
+                            double2 A[NT], B[NT];
+                            double accv[NT];
+#pragma unroll
+                            for (int t = 0; t < NT; ++t) accv[t] = 0.0;
+                            int j = 0;
+                            if (cnt >= NT) {
+#pragma unroll
+                                for (int t = 0; t < NT; ++t) A[t] = __ldg(ps + t);
+                            }
+                            for (; j + 2 * NT <= cnt; j += 2 * NT) {
+#pragma unroll
+                                for (int t = 0; t < NT; ++t) B[t] = __ldg(ps + j + NT + t);
+                                fleming_terms<NT>(A, alpha, aF, c2, s_exp, s_log, rep16, rep8, accv);
+                                if (j + 3 * NT <= cnt) {
+#pragma unroll
+                                    for (int t = 0; t < NT; ++t) A[t] = __ldg(ps + j + 2 * NT + t);
+                                }
+                                fleming_terms<NT>(B, alpha, aF, c2, s_exp, s_log, rep16, rep8, accv);
+                            }
+                            if (j + NT <= cnt) {
+                                fleming_terms<NT>(A, alpha, aF, c2, s_exp, s_log, rep16, rep8, accv);
+                                j += NT;
+                            }
+#pragma unroll
+                            for (int t = 0; t < NT; t += 2) { acc0 += accv[t]; acc1 += accv[t + 1]; }
+                            for (; j < cnt; ++j) {
+                                double2 s0 = __ldg(ps + j);
+                                double lg0, rd0;
+                                fleming_log_parts<true>(s0.x, s0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                                acc0 = fma(lg0, rd0, acc0);
+                            }
+                        } else {
+                            for (; i < seg_end; ++i) {
+                                double2 s0 = __ldg(&a.src2[i]);
+                                double lg0, rd0;
+                                fleming_log_parts<false>(s0.x, s0.y, alpha, aF, c2, s_exp, s_log, rep16, rep8, lg0, rd0);
+                                acc0 += lg0;
+                            }
+                        }
+                    } else {
+                        // reference order: log( Phi_i * (int(Omega_0)/sqarcsec * fleming(f_i)) )  (lumfuncmcmc.py:370)
+                        const double F50 = wp[(P_FIELD0 + 4 * k + 2) * WS], ftau = wp[(P_FIELD0 + 4 * k + 3) * WS];
+                        const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
+                        const double om = a.fs[k].om0_over_sq;
+                        for (long long i = i0; i < seg_end; ++i) {
+                            double phi = schechter_literal(__ldg(&a.lum[i]), sal, Lstar, phistar);
+                            double Om = om * fleming_literal(__ldg(&a.flux[i]), F50, alpha, ftau, a.modified != 0);
+                            acc0 += log(phi * Om);
+                        }
+                    }
+                    i0 = seg_end;
+                    ++k;
+                }
+            }
+            if (h == 0) { out0 = acc0; out1 = acc1; } else accB = acc0 + acc1;
+          }
         } else if (MODEL == LF_MODEL_FIXED) {
             // fast class: the whole source sum is in P_LNPART0 (sufficient statistics); literal class sums terms
             if (LITERAL) {
@@ -466,7 +523,8 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
             const double aL = wp[P_AL * WS], bL = wp[P_BL * WS], cL = wp[P_CL * WS];
             if (!LITERAL && (a.precision == LF_PREC_F32 || a.csrc != nullptr)) {
               // FP32 mode / compressed catalogue: one walker of the pair after the other
-              for (int h = 0; h < 2; ++h) {
+              const int nh = wg * 64 + 32 < count ? 2 : 1;                   // warp-uniform
+              for (int h = 0; h < nh; ++h) {
                 const double* wq = h == 0 ? wp : a.wp + wB;
                 const double aL = wq[P_AL * WS], bL = wq[P_BL * WS], cL = wq[P_CL * WS];
                 double accH = 0.0;

@@ -218,17 +218,20 @@ __device__ __forceinline__ void fleming_log_parts(double g, double f, double alp
 // pipe issues one warp instruction per 2 cycles only while consecutive DFMAs come from the SAME warp (3 cycles when the
 // scheduler has to alternate between warps, tools/microbench/fp64_mix.cu), so a warp must offer >= 4 independent DFMAs
 // at every point of the chain (DFMA latency 8 cycles).
+// Chain i evaluates the source (ux[i], uy[i]) for the walker constants (al[i], af[i], cc[i]); the arrays are register
+// names, so chains that share a source or a walker cost no extra registers.
 template <int NT>
-__device__ __forceinline__ void fleming_terms(const double2* u, double alpha, double aF, double c2, const double* s_exp,
-                                              const double2* s_log, int repe, int repl, double* acc) {
+__device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const double (&uy)[NT], const double (&al)[NT],
+                                                const double (&af)[NT], const double (&cc)[NT], const double* s_exp,
+                                                const double2* s_log, int repe, int repl, double* acc) {
     double n[NT], y[NT], r0[NT], e[NT], q[NT], fc[NT], lg[NT], dec[NT];
     double t[NT], r[NT], Ts[NT], p[NT];
     double2 tb[NT];
     int k[NT];
 #pragma unroll
-    for (int i = 0; i < NT; ++i) n[i] = fma(alpha, u[i].x, aF);
+    for (int i = 0; i < NT; ++i) n[i] = fma(al[i], ux[i], af[i]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) t[i] = fma(u[i].y, c2, KC[0]);
+    for (int i = 0; i < NT; ++i) t[i] = fma(uy[i], cc[i], KC[0]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = fma(n[i], n[i], 1.0);
 #pragma unroll
@@ -250,7 +253,7 @@ __device__ __forceinline__ void fleming_terms(const double2* u, double alpha, do
 #endif
     }
 #pragma unroll
-    for (int i = 0; i < NT; ++i) r[i] = fma(u[i].y, c2, -t[i]);
+    for (int i = 0; i < NT; ++i) r[i] = fma(uy[i], cc[i], -t[i]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) p[i] = fma(r[i], KC[1], KC[2]);
     // rsqrt correction
@@ -298,6 +301,16 @@ __device__ __forceinline__ void fleming_terms(const double2* u, double alpha, do
     for (int i = 0; i < NT; ++i) lg[i] = fma(fc[i], lg[i], tb[i].y);
 #pragma unroll
     for (int i = 0; i < NT; ++i) acc[i] = fma(lg[i], r0[i], acc[i]);
+}
+
+// NT sources of one walker
+template <int NT>
+__device__ __forceinline__ void fleming_terms(const double2* u, double alpha, double aF, double c2, const double* s_exp,
+                                              const double2* s_log, int repe, int repl, double* acc) {
+    double ux[NT], uy[NT], al[NT], af[NT], cc[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) { ux[i] = u[i].x; uy[i] = u[i].y; al[i] = alpha; af[i] = aF; cc[i] = c2; }
+    fleming_terms_v<NT>(ux, uy, al, af, cc, s_exp, s_log, repe, repl, acc);
 }
 
 // ---- libm-grade (~2e-16) routines for the streaming 1/V_eff kernel: its per-source weights are compared at 1e-13 and
