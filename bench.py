@@ -32,7 +32,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 FP64_INSTR_PER_TERM = 23          # DFMA/DADD/DMUL per (walker, source) term in k_main<false, FREE> (tools/sass_loop_mix.py)
-FP64_INSTR_PER_TERM_BY_KIND = {'free': 23, 'z': 11, 'fixed': 0}    # fixed: the source sum is sufficient statistics (quadrature only)
+FP64_INSTR_PER_TERM_BY_KIND = {'free': 23, 'z': 9, 'fixed': 0}    # fixed: the source sum is sufficient statistics (quadrature only)
 MUFU_PER_TERM_BY_KIND = {'free': 4, 'z': 1, 'fixed': 0}
 MUFU_PER_TERM = 4                 # rsqrt, lg2, ex2, rcp per term in the FP32 mode of the loop
 BYTES_PER_SOURCE = 16             # (log10 flux, flux) per source per sweep
