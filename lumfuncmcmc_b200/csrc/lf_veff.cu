@@ -424,7 +424,8 @@ extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const doubl
     dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
     const size_t nb = sizeof(double) * (size_t)n;
     double* d_flux = nullptr; double* d_vol = nullptr; unsigned char* d_valid = nullptr;
-    CK(cudaMalloc(&d_flux, nb));
+    DevBufs call_bufs;                             // per-call inputs: released on every exit path
+    CK(call_bufs.alloc(&d_flux, nb));
     CK(cudaMalloc(&c->v_lum, nb));
     CK(cudaMalloc(&c->v_phi, nb));
     CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
@@ -440,11 +441,11 @@ extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const doubl
     CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
     if (vol_per_source) {
-        CK(cudaMalloc(&d_vol, nb));
+        CK(call_bufs.alloc(&d_vol, nb));
         CK(cudaMemcpyAsync(d_vol, vol_per_source, nb, cudaMemcpyHostToDevice, c->stream));
     }
     if (valid) {
-        CK(cudaMalloc(&d_valid, (size_t)n));
+        CK(call_bufs.alloc(&d_valid, (size_t)n));
         CK(cudaMemcpyAsync(d_valid, valid, (size_t)n, cudaMemcpyHostToDevice, c->stream));
     }
     VeffArgs a;
@@ -477,9 +478,6 @@ extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const doubl
     if (phi_out) CK(cudaMemcpyAsync(phi_out, c->v_phi, nb, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms; }
-    cudaFree(d_flux);
-    if (d_vol) cudaFree(d_vol);
-    if (d_valid) cudaFree(d_valid);
     return 0;
 }
 
