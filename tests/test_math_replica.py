@@ -1,0 +1,21 @@
+"""Accuracy of the streaming log / exp routines of the 1/V_eff kernel, measured on a host replica that performs the
+same operations in the same order (tools/math/stream_accuracy.cpp).  CPU only: needs g++."""
+import os
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason="needs g++")
+def test_streaming_log_and_exp_are_libm_grade(tmp_path):
+    exe = str(tmp_path / 'stream_accuracy')
+    subprocess.run(['g++', '-O2', '-o', exe, os.path.join(ROOT, 'tools', 'math', 'stream_accuracy.cpp')], check=True)
+    out = subprocess.run([exe, '2000000'], check=True, capture_output=True, text=True).stdout
+    # "log: max abs err A, max err / max(|ln|, 1) B; exp: max rel err C"
+    nums = [float(tok.rstrip(',;')) for tok in out.replace(';', ' ').split() if tok[0].isdigit() and 'e-' in tok]
+    assert len(nums) == 3, out
+    log_abs, log_rel, exp_rel = nums
+    assert log_rel < 3.0e-16 and exp_rel < 3.0e-16 and log_abs < 1.0e-14, out

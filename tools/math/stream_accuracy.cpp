@@ -1,8 +1,12 @@
-// host replica of the streaming log / exp routines (lf_math.cuh) to measure their error against long double
+// Host replica of the streaming log / exp routines (lf_math.cuh: log_stream, exp_stream -- the same operations in the
+// same order, fma for fma) to measure their error against long double.
+//     g++ -O2 -o stream_accuracy stream_accuracy.cpp && ./stream_accuracy [samples]
+// Prints the three maxima on one line; tests/test_math_replica.py runs it with 2e6 samples.
 #include <cmath>
 #include <cstdio>
 #include <cstdint>
 #include <cstring>
+#include <cstdlib>
 #include <random>
 static double tabx[256], taby[256], e2[256];
 static const double LN2_HI = 0.693147180369123816490, LN2_LO = 1.90821492927058770002e-10, LOG2E = 1.4426950408889634074;
@@ -36,7 +40,8 @@ static double exp_stream(double x) {
     p = p * r;
     return fma(Ts, p, Ts);
 }
-int main() {
+int main(int argc, char** argv) {
+    const long nsamp = argc > 1 ? atol(argv[1]) : 20000000L;
     for (int j = 0; j < 256; ++j) {
         e2[j] = (double)exp2l((long double)j / 256);
         long double cm = 1.0L + ((long double)j + 0.5L) / 256;
@@ -46,7 +51,7 @@ int main() {
     std::mt19937_64 g(1);
     std::uniform_real_distribution<double> ue(-60.0, 20.0), ux(-700.0, 700.0);
     double worst_abs = 0, worst_rel = 0, worst_e = 0;
-    for (int i = 0; i < 20000000; ++i) {
+    for (long i = 0; i < nsamp; ++i) {
         double v = exp2(ue(g));
         long double ref = logl((long double)v);
         double got = log_stream(v);
