@@ -19,3 +19,14 @@ def test_streaming_log_and_exp_are_libm_grade(tmp_path):
     assert len(nums) == 3, out
     log_abs, log_rel, exp_rel = nums
     assert log_rel < 3.0e-16 and exp_rel < 3.0e-16 and log_abs < 1.0e-14, out
+
+
+@pytest.mark.skipif(shutil.which('g++') is None, reason="needs g++")
+def test_fast_term_of_the_free_model_stays_inside_its_error_budget(tmp_path):
+    """One walker x source term of k_main<false, FREE> (math v4) on its host replica: relative deviation from long double
+    arithmetic below 3e-12 for MUFU seeds anywhere inside their measured bounds (tolerance on lnprob: 1e-10 relative)."""
+    exe = str(tmp_path / 'term_accuracy')
+    subprocess.run(['g++', '-O2', '-o', exe, os.path.join(ROOT, 'tools', 'math', 'term_accuracy.cpp')], check=True)
+    out = subprocess.run([exe, '2000000'], check=True, capture_output=True, text=True).stdout
+    rel = float(out.split('max err / max(|t|, 1)')[1].split(',')[0])
+    assert rel < 3.0e-12, out
