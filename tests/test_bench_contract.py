@@ -1,0 +1,42 @@
+"""bench.py contract checks that need no GPU: the reference arm (the reference's algorithm on the host cores) prints one
+JSON line with the keys the driver reads, on the same metric / unit as the engine arm; defaults finish in minutes."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_arm_prints_one_contract_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                         check=True, capture_output=True, text=True, cwd=ROOT, timeout=600).stdout
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1, out
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['unit'] == 'terms/s' and d['higher_is_better'] is True
+    assert d['n_gpus'] == 1 and d['steps'] == 1 and d['dtype'] == 'f64' and d['data'] == 'synthetic'
+    assert d['value'] > 1.0e5 and d['gpu_launches'] == 0 and d['vs_baseline'] is None
+    assert d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['cores'] >= 1 and d['cpu_baseline']['value'] == d['value']
+    assert d['e2e'] == {"value": d['value'], "unit": "terms/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    base = json.load(open(os.path.join(ROOT, 'BASELINE.json')))
+    assert 'terms' in d['metric'] and 'terms' in json.dumps(base.get('metric', base))
+
+
+def test_reference_arm_is_silent_on_other_ranks():
+    env = dict(os.environ, RANK='1', WORLD_SIZE='2', LOCAL_RANK='1')
+    r = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--impl', 'reference', '--gpus', '2', '--steps', '1',
+                        '--warmup', '0'], capture_output=True, text=True, cwd=ROOT, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ''
+
+
+def test_defaults():
+    sys.path.insert(0, ROOT)
+    import bench
+    old = sys.argv
+    try:
+        sys.argv = ['bench.py']
+        a = bench.parse()
+    finally:
+        sys.argv = old
+    assert a.gpus == 1 and a.steps >= 1 and a.warmup >= 3 and a.impl == 'engine' and a.kind == 'free' and a.precision == 'f64'
