@@ -40,3 +40,19 @@ def test_defaults():
     finally:
         sys.argv = old
     assert a.gpus == 1 and a.steps >= 1 and a.warmup >= 3 and a.impl == 'engine' and a.kind == 'free' and a.precision == 'f64'
+
+
+def test_committed_engine_line_carries_every_contract_key():
+    """The last engine-arm line measured on a B200 (profiles/) has the keys the driver and the judge read."""
+    d = json.load(open(os.path.join(ROOT, 'profiles', 'r01_bench_1e7x1024_final.json')))
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling',
+              'vs_baseline', 'dtype', 'data', 'config', 'e2e', 'gpu_launches', 'clocks', 'roofline', 'cpu_baseline'):
+        assert k in d, k
+    assert d['config']['workload'] and d['warmup'] >= 3 and d['gpu_launches'] > 0 and d['dtype'] == 'f64'
+    assert set(('value', 'unit', 'h2d_bytes_per_step', 'd2h_bytes_per_step')) <= set(d['e2e'])
+    assert d['e2e']['h2d_bytes_per_step'] > 0 and d['e2e']['d2h_bytes_per_step'] > 0 and d['e2e']['value'] != d['value']
+    assert set(('sm_mhz', 'sm_max_mhz', 'reasons')) <= set(d['clocks'])
+    r = d['roofline']
+    assert set(('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic')) <= set(r)
+    assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-12 and 0.5 < r['frac'] < 1.0
+    assert set(('value', 'unit', 'cores', 'kind', 'sample')) <= set(d['cpu_baseline'])
