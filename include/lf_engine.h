@@ -61,6 +61,12 @@ typedef struct lf_config {
     double z_pivots[3];      /* LF_MODEL_Z: z1, z2, z3 (lumfuncmcmc_z.py:191)                         */
 } lf_config;
 
+/* LambdaCDM parameters + quadrature rule of the set-up / volume entry points (see lf_cosmo_distances) */
+typedef struct lf_cosmology {
+    double H0, Om0, Ode0, Or0, Ok0, panel;
+    double gl_x[8], gl_w[8];     /* Gauss-Legendre nodes / weights on [-1, 1], as numpy.polynomial.legendre.leggauss(8) */
+} lf_cosmology;
+
 /* theta layout (row-major, `ndim` doubles per walker), as set_parameters_from_list:
  *   FREE : L*, phi*, [alpha_s], F50_0..F50_{K-1}, alpha_c      ndim = 2 + !fix_sch_al + K + 1
  *   FIXED: L*, phi*, [alpha_s]                                  ndim = 2 + !fix_sch_al
@@ -127,9 +133,41 @@ int lf_veff_bin(lf_ctx* ctx, int64_t n, const double* flux, const double* lum, c
                 double vol_int, const double* vol_per_source, const uint8_t* valid_or_null,
                 const double* edges, int32_t nbins, double* phi_out, int64_t* counts, double* sumphi);
 
+/* The same pass for a sample that STAYS on the device between calls -- VeffLF runs after every fit and once more per
+ * posterior summary with new completeness parameters on the same catalogue (lumfuncmcmc.py:541, :567, :650):
+ *   lf_veff_set_sample     upload flux (cgs), lum and the field offsets once
+ *   lf_veff_bin_resident   weights + binning on the resident sample: nothing per-source crosses PCIe unless phi_out is
+ *                          given (phi stays resident: lf_veff_get_phi downloads it on demand, lf_bin_weights(NULL, NULL)
+ *                          and lf_boot_bin* read it in place).  use_device_volumes = 1 takes the per-source volume and
+ *                          validity lf_veff_volumes left on the device (vol_int is then ignored).
+ *   lf_veff_get_phi        the resident per-source weights -> host */
+int lf_veff_set_sample(lf_ctx* ctx, int64_t n, const double* flux, const double* lum, const int64_t* field_ind,
+                       int32_t nfields);
+int lf_veff_bin_resident(lf_ctx* ctx, const double* flim, double alpha, double fcmin, double sum_omega, double vol_int,
+                         int32_t use_device_volumes, const double* edges, int32_t nbins, double* phi_out,
+                         int64_t* counts, double* sumphi);
+int lf_veff_get_phi(lf_ctx* ctx, double* phi_out);
+
+/* min_comp_frac > 0 (lumfuncmcmc.py:521-524): every source of the resident sample integrates dV/dz only up to the
+ * redshift where its luminosity drops to its field's minimum flux.  The reference finds that redshift with one fsolve
+ * per source (V.getMaxz, VmaxLumFunc.py:739-753: 4 pi (D_L(z) cm)^2 fmin = 10^lum, xtol 1.5e-8) and the volume with one
+ * QUADPACK call per source on the linear interpolant dVdzf (V.lumfunc, VmaxLumFunc.py:235-257, 1.5e-8).  Here:
+ *   zmax_i  = min(zmax, root)   by Newton on the D_L of lf_cosmo_distances (same arithmetic, converged to ~1e-15)
+ *   vol_i   = int_zmin^zmax_i dVdzf dz   EXACTLY (cumulative trapezoids of the piecewise-linear interpolant + partial segment)
+ *   valid_i = zmax_i > zmin
+ * so the two agree to the reference's own solver tolerances (tested at 1e-7 on weights, exact on counts).
+ *   lf_veff_set_volume_table  cosmology (as lf_cosmo_distances) + the knots (zk, dVk) of dVdzf; kept until replaced
+ *   lf_veff_volumes           fmin[K] = minimum flux per field (cgs); DL_zmin / DL_zmax = D_L [Mpc] at zmin / zmax;
+ *                             results stay resident for lf_veff_bin_resident(use_device_volumes = 1); the three host
+ *                             outputs (n each) may be NULL */
+int lf_veff_set_volume_table(lf_ctx* ctx, const lf_cosmology* cosmo, const double* cum, int64_t ncum, int64_t nk,
+                             const double* zk, const double* dVk);
+int lf_veff_volumes(lf_ctx* ctx, double zmin, double zmax, double DL_zmin, double DL_zmax, const double* fmin,
+                    double* zmax_out, double* vol_out, uint8_t* valid_out);
+
 /* Bin caller-provided weights: counts[j], sumphi[j] of (lum_i, phi_i) over [edges[j], edges[j+1]); keeps lum/phi
  * resident for lf_boot_bin.  This is the original-sample pass of V.getBootErrLog when phi is an input
- * (VmaxLumFunc.py:345-350). */
+ * (VmaxLumFunc.py:345-350).  lum == NULL and phi == NULL: bin the sample and weights already resident (n is ignored). */
 int lf_bin_weights(lf_ctx* ctx, int64_t n, const double* lum, const double* phi, const double* edges,
                    int32_t nbins, int64_t* counts, double* sumphi);
 
@@ -158,11 +196,19 @@ int lf_mufu_peak(lf_ctx* ctx, int32_t iters, double* mufu_per_s, double* ms);
  *   lf_peer_buffer_create   allocate this rank's receive buffer for vectors of up to wcap doubles; returns its CUDA IPC handle
  *   lf_peer_buffer_connect  open the world handles (row r = rank r's handle, own row ignored)
  *   lf_allreduce_device     in-place SUM over ranks of d_vec[W] on `stream` (asynchronous)
- *   lf_peer_status          0, or non-zero if a wait for a peer timed out (~4 s) since the last call */
+ *   lf_peer_status          0, or non-zero if a wait for a peer has timed out.  The flag is STICKY: the exchange that
+ *                           timed out and every later one return NaN in d_vec (never a stale partial sum),
+ *                           lf_allreduce_device / lf_sampler_run fail, until lf_peer_reset acknowledges it
+ *   lf_peer_set_timeout     bound of one wait in seconds (default ~30 s: first-call module loads and host pauses fit)
+ * All ranks must create their buffers with the same world and wcap (the slot offsets are computed from them); the
+ * Python binding all-gathers (rank, world, wcap) with the handles and refuses a mismatch.  An all-zero handle row in
+ * lf_peer_buffer_connect means "no peer mapped for that rank" (used by the time-out test). */
 int lf_peer_buffer_create(lf_ctx* ctx, int32_t rank, int32_t world, int64_t wcap, unsigned char handle_out[64]);
 int lf_peer_buffer_connect(lf_ctx* ctx, const unsigned char* handles);
 int lf_allreduce_device(lf_ctx* ctx, double* d_vec, int64_t W, void* stream);
 int lf_peer_status(lf_ctx* ctx, int32_t* timed_out);
+int lf_peer_reset(lf_ctx* ctx);
+int lf_peer_set_timeout(lf_ctx* ctx, double seconds);
 
 /* ---- set-up tables on the GPU (the step before the path; reference lumfuncmcmc.py:180-202, VmaxLumFunc.py:14-17) ----
  * Context-free: they take a device ordinal and host buffers.
@@ -172,10 +218,6 @@ int lf_peer_status(lf_ctx* ctx, int32_t* timed_out);
  * as lumfuncmcmc_b200/cosmology.py (cumulative 8-point Gauss-Legendre panels of width `panel` + one 8-point closure per
  * redshift), operation for operation, so the two agree to the last ulp of sin/sinh.  cum[ncum] is the host's
  * cumulative panel integral of dz/E (cum[p] = int_0^{p*panel}). */
-typedef struct lf_cosmology {
-    double H0, Om0, Ode0, Or0, Ok0, panel;
-    double gl_x[8], gl_w[8];     /* Gauss-Legendre nodes / weights on [-1, 1], as numpy.polynomial.legendre.leggauss(8) */
-} lf_cosmology;
 int lf_cosmo_distances(int32_t device, const lf_cosmology* cosmo, const double* cum, int64_t ncum, int64_t n,
                        const double* z, double* DL_Mpc, double* dVdz);
 

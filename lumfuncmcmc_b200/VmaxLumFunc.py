@@ -97,7 +97,7 @@ def veff_weights_gpu(flux, lum, field_ind, Flim, alpha, fcmin, sum_omega, vol_in
 
 
 def getBootErrLog(L, phi, minz, maxz, nboot=100, nbin=25, Fmin=1.0e-20, Larr=None, correct_low=False, device=0,
-                  engine=None, return_counts=False, rng='host', seed=None):
+                  engine=None, return_counts=False, rng='host', seed=None, Lrange=None):
     """Binned luminosity function dn/dlogL with bootstrap variances (reference VmaxLumFunc.py:304-364).
 
     Bin edges ``linspace(min(L)*1.001, max(L), nbin+1)`` unless ``Larr`` is given; bins are half-open
@@ -109,23 +109,32 @@ def getBootErrLog(L, phi, minz, maxz, nboot=100, nbin=25, Fmin=1.0e-20, Larr=Non
     ``rng='device'`` (additive option) resamples on the GPU instead: a Philox stream keyed by ``seed`` (default: one draw
     from NumPy's global stream) generates every replicate's indices and multiplicities on the device -- statistically
     equivalent variances, 100 replicates of 1e7 sources in a fraction of a second instead of half a minute of host RNG.
+
+    ``phi=None`` (with ``engine``): the sample and its weights are the ones ``engine`` already holds on the device (left
+    there by ``veff_bin_resident``) -- nothing per-source is uploaded.  ``Lrange=(min(L), max(L))`` spares the two passes
+    over ``L`` when the caller knows them.
     """
     if correct_low:
         raise NotImplementedError("correct_low=True is outside the supported path (the MCMC classes never pass it)")
     L = np.ascontiguousarray(L, dtype=np.float64)
-    phi = np.ascontiguousarray(phi, dtype=np.float64)
+    resident = phi is None
+    if resident and engine is None:
+        raise ValueError("phi=None needs the engine that holds the weights")
+    if not resident:
+        phi = np.ascontiguousarray(phi, dtype=np.float64)
     if Larr is None:
         print("Min Luminosity:", np.log10(get_L_constF(Fmin, maxz)))
-        Larr = np.linspace(min(L) * 1.001, max(L), nbin + 1)
+        lo, hi = Lrange if Lrange is not None else (np.min(L), np.max(L))
+        Larr = np.linspace(lo * 1.001, hi, nbin + 1)
     Larr = np.ascontiguousarray(Larr, dtype=np.float64)
     nb = len(Larr) - 1
     Lavg = np.linspace((Larr[0] + Larr[1]) / 2.0, (Larr[-1] + Larr[-2]) / 2.0, nb)
     dL = Lavg[1] - Lavg[0]
     eng = engine or _veff_engine(device)
-    counts, sums = eng.bin_weights(L, phi, Larr)
+    counts, sums = eng.bin_weights(None, None, Larr) if resident else eng.bin_weights(L, phi, Larr)
     lfbinorig = np.where(counts > 0, sums / dL, 0.0)
     lfbin = np.zeros((nboot, nb))
-    n = len(phi)
+    n = len(L)
     if rng not in ('host', 'device'):
         raise ValueError("rng must be 'host' or 'device'")
     if rng == 'device' and seed is None:

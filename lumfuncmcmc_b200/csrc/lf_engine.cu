@@ -952,6 +952,7 @@ extern "C" int lf_create(lf_ctx** out, const lf_config* cfg) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev0));
     CK(cudaEventCreate(&c->ev1));
+    CK(cudaEventCreateWithFlags(&c->ev_scratch, cudaEventDisableTiming));
     Tables t;
     fill_tables(t);
     CK(cudaMalloc(&c->d_tables, sizeof(Tables)));
@@ -1005,6 +1006,9 @@ extern "C" void lf_destroy(lf_ctx* c) {
     dfree(c->d_cls); dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_list_fastq); dfree(c->d_list_litq); dfree(c->d_thetas); dfree(c->d_out);
     dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
     dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
+    dfree(c->v_flux); dfree(c->v_vol); dfree(c->v_valid);
+    dfree(c->v_cum); dfree(c->v_gl); dfree(c->v_zk); dfree(c->v_dVk); dfree(c->v_cumV);
+    if (c->ev_scratch) cudaEventDestroy(c->ev_scratch);
     peer_release(c);
     if (c->h_thetas) cudaFreeHost(c->h_thetas);
     if (c->h_out) cudaFreeHost(c->h_out);
@@ -1277,6 +1281,11 @@ extern "C" int lf_set_quadrature_share(lf_ctx* c, int32_t share, int32_t nshare)
 }
 
 static int ensure_scratch(lf_ctx* c, long long W, int rows) {
+    if ((W > c->Wcap || rows > c->rows_cap) && c->scratch_pending) {
+        // the scratch is about to be re-allocated: whoever still uses it (on any stream) has to finish first
+        CK(cudaStreamSynchronize(c->scratch_stream));
+        c->scratch_pending = false;
+    }
     if (W > c->Wcap) {
         long long cap = std::max<long long>(64, W);
         cap = (cap + 31) / 32 * 32;
@@ -1329,12 +1338,31 @@ static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
     n_quad = (int)rq;
 }
 
+static bool stream_capturing(cudaStream_t st) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+}
+
+int scratch_acquire(lf_ctx* c, cudaStream_t st) {
+    if (c->scratch_pending && c->scratch_stream != st && !stream_capturing(st))
+        CK(cudaStreamWaitEvent(st, c->ev_scratch, 0));
+    return 0;
+}
+
+int scratch_release(lf_ctx* c, cudaStream_t st) {
+    if (stream_capturing(st)) return 0;            // graph replays run on the context's own stream, in order
+    CK(cudaEventRecord(c->ev_scratch, st));
+    c->scratch_stream = st; c->scratch_pending = true;
+    return 0;
+}
+
 int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_out, cudaStream_t st) {
     if (!c->have_sources || !c->have_grid) return fail("lf_lnprob: call lf_set_sources and lf_set_grid first");
     if (W <= 0) return 0;
     int n_src, n_quad;
     plan_rows(c, W, n_src, n_quad);
     if (ensure_scratch(c, W, n_src + n_quad)) return 1;
+    if (scratch_acquire(c, st)) return 1;
     KArgs a = c->ka;
     a.thetas = d_thetas; a.out = d_out; a.W = W; a.Wcap = c->Wcap;
     a.wp = c->d_wp; a.colA = c->d_colA; a.colB = c->d_colB;
@@ -1379,7 +1407,7 @@ int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_ou
     k_finish<<<(unsigned)((W + 31) / 32), 32 * FIN_GROUPS, 0, st>>>(a);
     c->launches += 3;
     CK(cudaGetLastError());
-    return 0;
+    return scratch_release(c, st);
 }
 
 extern "C" int lf_lnprob_batch_device(lf_ctx* c, const double* d_thetas, int64_t W, double* d_out, void* stream) {

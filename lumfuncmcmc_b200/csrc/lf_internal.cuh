@@ -181,6 +181,57 @@ __device__ __forceinline__ double u01(uint32_t x) { return __dmul_rn((double)x +
 
 
 // ------------------------------------------------------------------------------------------------
+// LambdaCDM distances, the arithmetic of lumfuncmcmc_b200/cosmology.py operation for operation (lf_setup.cu, lf_veff.cu)
+// ------------------------------------------------------------------------------------------------
+// E(z) with NumPy's order of operations and no fused multiply-adds (cosmology.py efunc)
+__device__ __forceinline__ double efunc_np(const lf_cosmology& c, double z) {
+    const double zp1 = __dadd_rn(1.0, z);
+    double t = __dadd_rn(__dmul_rn(c.Or0, zp1), c.Om0);
+    t = __dadd_rn(__dmul_rn(t, zp1), c.Ok0);
+    t = __dadd_rn(__dmul_rn(__dmul_rn(zp1, zp1), t), c.Ode0);
+    return sqrt(t);
+}
+
+// transverse comoving distance dm [Mpc] and D_C / d_H at redshift zi: cumulative 8-point Gauss-Legendre panels (cum[p] =
+// int_0^{p * panel} dz / E) + one 8-point closure.  Returns false for a redshift outside the panel table.
+__device__ __forceinline__ bool cosmo_dm(const lf_cosmology& c, const double* __restrict__ cum, long long ncum,
+                                         const double* __restrict__ glx, const double* __restrict__ glw, double zi,
+                                         double& dm, double& dc) {
+    const long long p = (long long)floor(__ddiv_rn(zi, c.panel));
+    if (!(zi >= 0.0) || p >= ncum) return false;
+    const double lo = __dmul_rn((double)p, c.panel);
+    const double half = __dmul_rn(0.5, __dsub_rn(zi, lo));
+    double acc = 0.0;
+    for (int q = 0; q < 8; ++q) {                                   // acc += w / E(lo + half * (1 + x)), in node order
+        const double node = __dadd_rn(lo, __dmul_rn(half, __dadd_rn(1.0, glx[q])));
+        acc = __dadd_rn(acc, __ddiv_rn(glw[q], efunc_np(c, node)));
+    }
+    dc = __dadd_rn(cum[p], __dmul_rn(half, acc));                   // D_C / d_H
+    dm = dc;
+    if (c.Ok0 > 0.0) { const double s = sqrt(c.Ok0); dm = __ddiv_rn(sinh(__dmul_rn(s, dc)), s); }
+    else if (c.Ok0 < 0.0) { const double s = sqrt(-c.Ok0); dm = __ddiv_rn(sin(__dmul_rn(s, dc)), s); }
+    dm = __dmul_rn(__ddiv_rn(299792.458, c.H0), dm);                // [Mpc]
+    return true;
+}
+
+// j = last knot <= xv for increasing knots xk[nk] and xk[0] <= xv <= xk[nk - 1] (numpy.interp's segment): candidate from
+// the mean spacing, exact comparisons decide; knots far from uniform fall back to a binary search
+__device__ __forceinline__ long long knot_segment(long long nk, const double* __restrict__ xk, double xv) {
+    const double x0 = xk[0], x1 = xk[nk - 1];
+    long long j = (long long)((xv - x0) / (x1 - x0) * (double)(nk - 1));
+    j = j < 0 ? 0 : (j > nk - 1 ? nk - 1 : j);
+    int steps = 0;
+    while (j > 0 && xk[j] > xv && steps < 8) { --j; ++steps; }
+    while (j < nk - 1 && xk[j + 1] <= xv && steps < 8) { ++j; ++steps; }
+    if (steps >= 8) {
+        long long lo = 0, hi = nk;                                  // invariant: xk[lo] <= xv, (hi == nk or xk[hi] > xv)
+        while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (xk[mid] <= xv) lo = mid; else hi = mid; }
+        j = lo;
+    }
+    return j;
+}
+
+// ------------------------------------------------------------------------------------------------
 // the context
 // ------------------------------------------------------------------------------------------------
 // peer-memory exchange (definitions used by lf_ctx; kernels further down)
@@ -193,8 +244,10 @@ struct PeerArgs {
     double* data[PEER_MAX];            // rank r's receive buffer: data[r][parity][sender][wcap]
     unsigned* flags[PEER_MAX];         // flags[r][parity][sender][nchunk_cap]
     const unsigned* seq;               // device counter of this rank: sequence number of the current exchange (starts at 1)
-    int* timed_out;
+    int* timed_out;                    // host-mapped, sticky: set when a wait expired
+    long long spin_limit;              // clock64 ticks a wait may last
 };
+#define PEER_SPIN_CLOCKS_DEFAULT 60000000000LL   /* ~30 s at 1.97 GHz: first-call module loads, re-allocations and host pauses fit */
 
 struct lf_ctx {
     lf_config cfg;
@@ -223,6 +276,14 @@ struct lf_ctx {
     long long vN = 0; double* v_lum = nullptr; double* v_phi = nullptr; double* v_edges = nullptr; int v_nbins = 0;
     unsigned long long* v_counts = nullptr; double* v_sums = nullptr; long long* v_outc = nullptr; double* v_outs = nullptr;
     int* v_mult = nullptr; short* v_bin = nullptr; int v_blocks = 0;
+    // sample kept resident across V_eff calls (lf_veff_set_sample) and its per-source volumes (lf_veff_volumes)
+    double* v_flux = nullptr; double* v_vol = nullptr; unsigned char* v_valid = nullptr;
+    // volume table of lf_veff_set_volume_table: cosmology + panel integrals, knots of the dV/dz interpolant, its cumulative integral
+    lf_cosmology v_cosmo; double* v_cum = nullptr; long long v_ncum = 0; double* v_gl = nullptr;
+    double* v_zk = nullptr; double* v_dVk = nullptr; double* v_cumV = nullptr; long long v_nk = 0;
+    bool v_have_sample = false, v_have_volumes = false; int v_K = 0; long long v_field_ind[LF_MAX_FIELDS + 1] = {};
+    // ordering of the shared per-call scratch across streams (see scratch_acquire)
+    cudaEvent_t ev_scratch = nullptr; cudaStream_t scratch_stream = nullptr; bool scratch_pending = false;
     // peer exchange
     unsigned char* peer_base = nullptr; unsigned* peer_seq = nullptr; int* peer_timeout = nullptr; int* peer_timeout_h = nullptr;
     size_t peer_data_bytes = 0; bool peer_connected = false; void* peer_opened[PEER_MAX] = {};
@@ -251,6 +312,12 @@ inline void dfree(T*& p) {
 // ------------------------------------------------------------------------------------------------
 // lf_engine.cu: enqueue one batched log-posterior evaluation (prologue, main kernels, finish) on `st`
 int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_out, cudaStream_t st);
+// lf_engine.cu: the per-call scratch (walker constants, partial rows, class lists, V_eff residency) is shared by every entry
+// point of a context.  A caller may drive lf_lnprob_batch_device on its own stream while the host API, the sampler and the
+// V_eff calls use the context's stream: scratch_acquire makes `st` wait for the last user on another stream,
+// scratch_release records where the next user has to wait.  (Skipped while `st` is being captured into a CUDA graph.)
+int scratch_acquire(lf_ctx* c, cudaStream_t st);
+int scratch_release(lf_ctx* c, cudaStream_t st);
 // lf_veff.cu: opt the V_eff kernels into their dynamic shared-memory sizes (called once per context)
 int veff_init(lf_ctx* c);
 // lf_peer.cu: enqueue the in-place sum over ranks of d_vec[W] (two launches); release peer mappings at destroy

@@ -29,12 +29,18 @@ __global__ void __launch_bounds__(PEER_CHUNK) k_allreduce_p2p(PeerArgs a, double
     // 2. raise my flag for this chunk on every rank
     if (threadIdx.x < a.world)
         st_release_sys(a.flags[threadIdx.x] + ((size_t)par * a.world + a.rank) * a.nchunk_cap + chunk, seq);
-    // 3. wait for every sender's flag on my own buffer (bounded spin: a dead peer must not hang the GPU)
+    // 3. wait for every sender's flag on my own buffer (bounded spin: a dead peer must not hang the GPU).  A wait that
+    //    expires -- or a time-out recorded by an EARLIER exchange (the flag is sticky) -- poisons this chunk's output
+    //    with NaN: a stale partial sum can never be mistaken for a log-posterior (the samplers reject NaN), and the
+    //    host raises on its next look at the flag.
+    __shared__ int s_expired;
+    if (threadIdx.x == 0) s_expired = *(volatile int*)a.timed_out;
+    __syncthreads();
     if (threadIdx.x < a.world) {
         const unsigned* f = a.flags[a.rank] + ((size_t)par * a.world + threadIdx.x) * a.nchunk_cap + chunk;
         const long long t0 = clock64();
         while ((int)(ld_acquire_sys(f) - seq) < 0) {
-            if (clock64() - t0 > 8000000000LL) { atomicExch(a.timed_out, 1); break; }
+            if (clock64() - t0 > a.spin_limit) { atomicExch(a.timed_out, 1); s_expired = 1; break; }
             __nanosleep(100);
         }
     }
@@ -43,7 +49,7 @@ __global__ void __launch_bounds__(PEER_CHUNK) k_allreduce_p2p(PeerArgs a, double
     if (w < W) {
         double s = 0.0;
         for (int r = 0; r < a.world; ++r) s += a.data[a.rank][((size_t)par * a.world + r) * (size_t)a.wcap + w];
-        vec[w] = s;
+        vec[w] = s_expired ? __longlong_as_double(0x7ff8000000000000LL) : s;
     }
 }
 __global__ void k_seq_advance(unsigned* seq) { *seq += 1u; }
@@ -74,6 +80,7 @@ extern "C" int lf_peer_buffer_create(lf_ctx* c, int32_t rank, int32_t world, int
     p.data[rank] = reinterpret_cast<double*>(c->peer_base);
     p.flags[rank] = reinterpret_cast<unsigned*>(c->peer_base + data_bytes);
     p.seq = c->peer_seq; p.timed_out = c->peer_timeout;
+    p.spin_limit = PEER_SPIN_CLOCKS_DEFAULT;
     c->peer_data_bytes = data_bytes;
     cudaIpcMemHandle_t h;
     CK(cudaIpcGetMemHandle(&h, c->peer_base));
@@ -91,6 +98,9 @@ extern "C" int lf_peer_buffer_connect(lf_ctx* c, const unsigned char* handles) {
         if (r == p.rank) continue;
         cudaIpcMemHandle_t h;
         memcpy(&h, handles + 64 * r, 64);
+        bool absent = true;                          // an all-zero row: no peer is mapped for rank r (tests of the time-out
+        for (int b = 0; b < 64; ++b) absent = absent && handles[64 * r + b] == 0;    // path); its stores fall into this rank's own buffer
+        if (absent) { p.data[r] = p.data[p.rank]; p.flags[r] = p.flags[p.rank]; continue; }
         void* base = nullptr;
         CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
         c->peer_opened[r] = base;
@@ -111,6 +121,9 @@ extern "C" int lf_allreduce_device(lf_ctx* c, double* d_vec, int64_t W, void* st
 }
 
 int peer_allreduce_launch(lf_ctx* c, double* d_vec, long long W, cudaStream_t st) {
+    // sticky: once a wait has expired every later exchange is refused until the caller acknowledges it (lf_peer_status)
+    if (c->peer_timeout_h && *(volatile int*)c->peer_timeout_h)
+        return fail("peer-memory all-reduce: an earlier exchange timed out waiting for another rank; results since then are NaN");
     k_allreduce_p2p<<<(unsigned)((W + PEER_CHUNK - 1) / PEER_CHUNK), PEER_CHUNK, 0, st>>>(c->peer, d_vec, W);
     k_seq_advance<<<1, 1, 0, st>>>(c->peer_seq);
     c->launches += 2;
@@ -131,8 +144,21 @@ extern "C" int lf_peer_status(lf_ctx* c, int32_t* timed_out) {
     if (!c || !timed_out) return fail("lf_peer_status: null argument");
     *timed_out = 0;
     if (!c->peer_timeout_h) return 0;
-    *timed_out = *(volatile int*)c->peer_timeout_h;        // meaningful after the stream that ran the exchange was synchronised
-    *c->peer_timeout_h = 0;
+    *timed_out = *(volatile int*)c->peer_timeout_h;        // sticky: stays set (and every later exchange is refused / NaN) until lf_peer_reset
+    return 0;
+}
+
+extern "C" int lf_peer_reset(lf_ctx* c) {
+    if (!c) return fail("lf_peer_reset: null context");
+    if (c->peer_timeout_h) *c->peer_timeout_h = 0;
+    return 0;
+}
+
+extern "C" int lf_peer_set_timeout(lf_ctx* c, double seconds) {
+    if (!c || !(seconds > 0.0)) return fail("lf_peer_set_timeout: need a context and seconds > 0");
+    int khz = 1965000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+    c->peer.spin_limit = (long long)(seconds * 1.0e3 * (double)khz);
     return 0;
 }
 

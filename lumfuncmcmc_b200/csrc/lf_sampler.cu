@@ -154,7 +154,16 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
         SCK(cudaGraphInstantiate(&exec, graph, 0));
         const long long per_step = c->launches - launches0;
         SCK(cudaEventRecord(c->ev0, st));
-        for (int64_t t = 0; t < nsteps; ++t) SCK(cudaGraphLaunch(exec, st));
+        for (int64_t t = 0; t < nsteps; ++t) {
+            // a peer time-out is sticky and poisons every later exchange with NaN (all proposals rejected): stop
+            // enqueueing as soon as the host-mapped flag shows it instead of replaying the update to the end
+            if (exchange && c->peer_timeout_h && *(volatile int*)c->peer_timeout_h) {
+                cudaStreamSynchronize(st);
+                fail("lf_sampler_run: the peer-memory exchange timed out waiting for another rank at update " + std::to_string((long long)t));
+                return cleanup();
+            }
+            SCK(cudaGraphLaunch(exec, st));
+        }
         SCK(cudaEventRecord(c->ev1, st));
         c->launches = launches0 + per_step * nsteps;
     }
@@ -165,6 +174,10 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
     if (lnprob_out) SCK(cudaMemcpyAsync(lnprob_out, ((step0 + nsteps) & 1) ? d_lpnext : d_lp, sizeof(double) * W, cudaMemcpyDeviceToHost, st));
     SCK(cudaStreamSynchronize(st));
     SCK(cudaGetLastError());
+    if (exchange && c->peer_timeout_h && *(volatile int*)c->peer_timeout_h) {
+        fail("lf_sampler_run: the peer-memory exchange timed out waiting for another rank; the chain is invalid from that update on");
+        return cleanup();
+    }
     if (nsteps > 0) { float ms = 0.f; SCK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->sampler_ms = ms; }
 #undef SCK
     rc = 0;

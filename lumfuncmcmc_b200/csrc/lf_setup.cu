@@ -5,36 +5,15 @@
 // ------------------------------------------------------------------------------------------------
 // set-up tables on the GPU: cosmology distances and NumPy-exact linear interpolation
 // ------------------------------------------------------------------------------------------------
-// E(z) with NumPy's order of operations and no fused multiply-adds (cosmology.py efunc)
-__device__ __forceinline__ double efunc_np(const lf_cosmology& c, double z) {
-    const double zp1 = __dadd_rn(1.0, z);
-    double t = __dadd_rn(__dmul_rn(c.Or0, zp1), c.Om0);
-    t = __dadd_rn(__dmul_rn(t, zp1), c.Ok0);
-    t = __dadd_rn(__dmul_rn(__dmul_rn(zp1, zp1), t), c.Ode0);
-    return sqrt(t);
-}
-
 __global__ void k_cosmo(lf_cosmology c, const double* __restrict__ cum, long long ncum, long long n,
                         const double* __restrict__ z, const double* __restrict__ glx, const double* __restrict__ glw,
                         double* __restrict__ DL, double* __restrict__ dV, int* __restrict__ bad) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const double zi = z[i];
-    const long long p = (long long)floor(__ddiv_rn(zi, c.panel));
-    if (!(zi >= 0.0) || p >= ncum) { atomicExch(bad, 1); return; }
-    const double lo = __dmul_rn((double)p, c.panel);
-    const double half = __dmul_rn(0.5, __dsub_rn(zi, lo));
-    double acc = 0.0;
-    for (int q = 0; q < 8; ++q) {                                   // acc += w / E(lo + half * (1 + x)), in node order
-        const double node = __dadd_rn(lo, __dmul_rn(half, __dadd_rn(1.0, glx[q])));
-        acc = __dadd_rn(acc, __ddiv_rn(glw[q], efunc_np(c, node)));
-    }
-    const double dc = __dadd_rn(cum[p], __dmul_rn(half, acc));      // D_C / d_H
-    double dm = dc;
-    if (c.Ok0 > 0.0) { const double s = sqrt(c.Ok0); dm = __ddiv_rn(sinh(__dmul_rn(s, dc)), s); }
-    else if (c.Ok0 < 0.0) { const double s = sqrt(-c.Ok0); dm = __ddiv_rn(sin(__dmul_rn(s, dc)), s); }
+    double dm, dc;
+    if (!cosmo_dm(c, cum, ncum, glx, glw, zi, dm, dc)) { atomicExch(bad, 1); return; }
     const double dH = __ddiv_rn(299792.458, c.H0);
-    dm = __dmul_rn(dH, dm);                                         // transverse comoving distance [Mpc]
     if (DL) DL[i] = __dmul_rn(__dadd_rn(1.0, zi), dm);
     if (dV) dV[i] = __ddiv_rn(__dmul_rn(__dmul_rn(dH, dm), dm), efunc_np(c, zi));
 }
@@ -47,16 +26,7 @@ __global__ void k_interp(long long nk, const double* __restrict__ xk, const doub
     const double xv = x[i];
     const double x0 = xk[0], x1 = xk[nk - 1];
     if (!(xv >= x0) || !(xv <= x1)) { atomicExch(bad, 1); y[i] = xv != xv ? xv : 0.0; return; }
-    long long j = (long long)((xv - x0) / (x1 - x0) * (double)(nk - 1));
-    j = j < 0 ? 0 : (j > nk - 1 ? nk - 1 : j);
-    int steps = 0;
-    while (j > 0 && xk[j] > xv && steps < 8) { --j; ++steps; }
-    while (j < nk - 1 && xk[j + 1] <= xv && steps < 8) { ++j; ++steps; }
-    if (steps >= 8) {                                               // knots far from uniform: plain binary search
-        long long lo = 0, hi = nk;                                  // invariant: xk[lo] <= xv, (hi == nk or xk[hi] > xv)
-        while (hi - lo > 1) { long long mid = (lo + hi) >> 1; if (xk[mid] <= xv) lo = mid; else hi = mid; }
-        j = lo;
-    }
+    const long long j = knot_segment(nk, xk, xv);
     double r;
     if (j == nk - 1) r = yk[j];
     else if (xk[j] == xv) r = yk[j];

@@ -410,44 +410,50 @@ static void veff_launch(const VeffPlan& p, const VeffArgs& a, cudaStream_t st) {
 // ------------------------------------------------------------------------------------------------
 // Veff host entry points
 // ------------------------------------------------------------------------------------------------
-extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const double* lum, const int64_t* field_ind,
-                           int32_t nfields, const double* flim, double alpha, double fcmin, double sum_omega,
-                           double vol_int, const double* vol_per_source, const uint8_t* valid,
-                           const double* edges, int32_t nbins, double* phi_out, int64_t* counts, double* sumphi) {
-    if (!c) return fail("lf_veff_bin: null context");
-    if (n <= 0 || !flux || !lum || !field_ind || !flim || !edges || !counts || !sumphi) return fail("lf_veff_bin: bad arguments");
-    if (nfields < 1 || nfields > LF_MAX_FIELDS) return fail("lf_veff_bin: nfields out of range");
-    if (nbins < 1 || nbins > VEFF_MAX_BINS) return fail("lf_veff_bin: nbins out of range");
-    if (field_ind[0] != 0 || field_ind[nfields] != n) return fail("lf_veff_bin: field_ind must run from 0 to n");
-    CK(cudaSetDevice(c->device));
-    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
-    dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
+// resident sample buffers: lum, phi, histogram row per source; (re)allocated only when the sample size changes
+static int veff_alloc_sample(lf_ctx* c, long long n) {
+    if (c->vN == n && c->v_lum && c->v_phi && c->v_bin) return 0;
+    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_bin); dfree(c->v_mult); dfree(c->v_flux); dfree(c->v_vol); dfree(c->v_valid);
+    c->v_have_sample = false; c->v_have_volumes = false; c->vN = 0;
     const size_t nb = sizeof(double) * (size_t)n;
-    double* d_flux = nullptr; double* d_vol = nullptr; unsigned char* d_valid = nullptr;
-    DevBufs call_bufs;                             // per-call inputs: released on every exit path
-    CK(call_bufs.alloc(&d_flux, nb));
     CK(cudaMalloc(&c->v_lum, nb));
     CK(cudaMalloc(&c->v_phi, nb));
-    CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
-    const VeffPlan plan = veff_plan(c, n, nbins);
-    const int blocks = plan.blocks;
-    c->v_blocks = blocks; c->v_nbins = nbins; c->vN = n;
-    CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)blocks * nbins));
-    CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)blocks * nbins));
-    CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
-    CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
     CK(cudaMalloc(&c->v_bin, sizeof(short) * (size_t)n));
-    CK(cudaMemcpyAsync(d_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+    c->vN = n;
+    return 0;
+}
+
+// per-histogram buffers: edges, block partials, results; (re)allocated only when the launch plan changes
+static int veff_alloc_bins(lf_ctx* c, const VeffPlan& plan, int nbins, const double* edges) {
+    if (c->v_nbins != nbins || c->v_blocks != plan.blocks || !c->v_edges) {
+        dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums); dfree(c->v_outc); dfree(c->v_outs);
+        CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
+        CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)plan.blocks * nbins));
+        CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)plan.blocks * nbins));
+        CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
+        CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
+        c->v_nbins = nbins; c->v_blocks = plan.blocks;
+    }
     CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
-    if (vol_per_source) {
-        CK(call_bufs.alloc(&d_vol, nb));
-        CK(cudaMemcpyAsync(d_vol, vol_per_source, nb, cudaMemcpyHostToDevice, c->stream));
-    }
-    if (valid) {
-        CK(call_bufs.alloc(&d_valid, (size_t)n));
-        CK(cudaMemcpyAsync(d_valid, valid, (size_t)n, cudaMemcpyHostToDevice, c->stream));
-    }
+    return 0;
+}
+
+static int veff_check_common(const char* who, const double* flim, const double* edges, const int64_t* counts, const double* sumphi,
+                             int nfields, int nbins) {
+    if (!flim || !edges || !counts || !sumphi) return fail(std::string(who) + ": bad arguments");
+    if (nfields < 1 || nfields > LF_MAX_FIELDS) return fail(std::string(who) + ": nfields out of range");
+    if (nbins < 1 || nbins > VEFF_MAX_BINS) return fail(std::string(who) + ": nbins out of range");
+    return 0;
+}
+
+// the weights + binning pass over device arrays (lum / phi / bin resident in the context), results to host buffers
+static int veff_weights_pass(lf_ctx* c, long long n, const double* d_flux, const double* d_vol, const unsigned char* d_valid,
+                             const long long* field_ind, int nfields, const double* flim, double alpha, double fcmin,
+                             double sum_omega, double vol_int, const double* edges, int nbins, double* phi_out,
+                             int64_t* counts, double* sumphi) {
+    const VeffPlan plan = veff_plan(c, n, nbins);
+    if (veff_alloc_bins(c, plan, nbins, edges)) return 1;
+    const int blocks = plan.blocks;
     VeffArgs a;
     memset(&a, 0, sizeof(a));
     a.n = n; a.flux = d_flux; a.lum = c->v_lum; a.vol = d_vol; a.valid = d_valid; a.phi = c->v_phi;
@@ -466,7 +472,7 @@ extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const doubl
     a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.vol_int = vol_int; a.modified = modified ? 1 : 0;
     a.inv_pref_vol = 1.0 / (a.pref * vol_int); a.tables = c->d_tables;
     a.edges = c->v_edges; a.nbins = nbins; a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = nullptr; a.bin = c->v_bin;
-    if (!vol_per_source && !valid) edges_fast_setup(edges, nbins, a);
+    if (!d_vol && !d_valid) edges_fast_setup(edges, nbins, a);
     CK(cudaEventRecord(c->ev0, c->stream));
     veff_launch<0>(plan, a, c->stream);
     k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
@@ -475,35 +481,112 @@ extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const doubl
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
-    if (phi_out) CK(cudaMemcpyAsync(phi_out, c->v_phi, nb, cudaMemcpyDeviceToHost, c->stream));
+    if (phi_out) CK(cudaMemcpyAsync(phi_out, c->v_phi, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms; }
+    return 0;
+}
+
+extern "C" int lf_veff_bin(lf_ctx* c, int64_t n, const double* flux, const double* lum, const int64_t* field_ind,
+                           int32_t nfields, const double* flim, double alpha, double fcmin, double sum_omega,
+                           double vol_int, const double* vol_per_source, const uint8_t* valid,
+                           const double* edges, int32_t nbins, double* phi_out, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_veff_bin: null context");
+    if (n <= 0 || !flux || !lum || !field_ind) return fail("lf_veff_bin: bad arguments");
+    if (veff_check_common("lf_veff_bin", flim, edges, counts, sumphi, nfields, nbins)) return 1;
+    if (field_ind[0] != 0 || field_ind[nfields] != n) return fail("lf_veff_bin: field_ind must run from 0 to n");
+    CK(cudaSetDevice(c->device));
+    if (scratch_acquire(c, c->stream)) return 1;
+    if (veff_alloc_sample(c, n)) return 1;
+    c->v_have_sample = false; c->v_have_volumes = false;     // the resident flux (if any) no longer belongs to this lum
+    dfree(c->v_flux);
+    const size_t nb = sizeof(double) * (size_t)n;
+    double* d_flux = nullptr; double* d_vol = nullptr; unsigned char* d_valid = nullptr;
+    DevBufs call_bufs;                             // per-call inputs: released on every exit path
+    CK(call_bufs.alloc(&d_flux, nb));
+    CK(cudaMemcpyAsync(d_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+    if (vol_per_source) {
+        CK(call_bufs.alloc(&d_vol, nb));
+        CK(cudaMemcpyAsync(d_vol, vol_per_source, nb, cudaMemcpyHostToDevice, c->stream));
+    }
+    if (valid) {
+        CK(call_bufs.alloc(&d_valid, (size_t)n));
+        CK(cudaMemcpyAsync(d_valid, valid, (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    }
+    long long fi[LF_MAX_FIELDS + 1];
+    for (int k = 0; k <= nfields; ++k) fi[k] = field_ind[k];
+    return veff_weights_pass(c, n, d_flux, d_vol, d_valid, fi, nfields, flim, alpha, fcmin, sum_omega, vol_int, edges, nbins,
+                             phi_out, counts, sumphi);
+}
+
+extern "C" int lf_veff_set_sample(lf_ctx* c, int64_t n, const double* flux, const double* lum, const int64_t* field_ind,
+                                  int32_t nfields) {
+    if (!c) return fail("lf_veff_set_sample: null context");
+    if (n <= 0 || !flux || !lum || !field_ind) return fail("lf_veff_set_sample: bad arguments");
+    if (nfields < 1 || nfields > LF_MAX_FIELDS) return fail("lf_veff_set_sample: nfields out of range");
+    if (field_ind[0] != 0 || field_ind[nfields] != n) return fail("lf_veff_set_sample: field_ind must run from 0 to n");
+    for (int k = 0; k < nfields; ++k)
+        if (field_ind[k + 1] < field_ind[k]) return fail("lf_veff_set_sample: field_ind must be non-decreasing");
+    CK(cudaSetDevice(c->device));
+    if (scratch_acquire(c, c->stream)) return 1;
+    if (veff_alloc_sample(c, n)) return 1;
+    const size_t nb = sizeof(double) * (size_t)n;
+    if (!c->v_flux) CK(cudaMalloc(&c->v_flux, nb));
+    CK(cudaMemcpyAsync(c->v_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->v_K = nfields;
+    for (int k = 0; k <= nfields; ++k) c->v_field_ind[k] = field_ind[k];
+    c->v_have_sample = true; c->v_have_volumes = false;
+    return 0;
+}
+
+extern "C" int lf_veff_bin_resident(lf_ctx* c, const double* flim, double alpha, double fcmin, double sum_omega, double vol_int,
+                                    int32_t use_device_volumes, const double* edges, int32_t nbins, double* phi_out,
+                                    int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_veff_bin_resident: null context");
+    if (!c->v_have_sample) return fail("lf_veff_bin_resident: call lf_veff_set_sample first");
+    if (veff_check_common("lf_veff_bin_resident", flim, edges, counts, sumphi, c->v_K, nbins)) return 1;
+    if (use_device_volumes && !c->v_have_volumes) return fail("lf_veff_bin_resident: call lf_veff_volumes first");
+    CK(cudaSetDevice(c->device));
+    if (scratch_acquire(c, c->stream)) return 1;
+    return veff_weights_pass(c, c->vN, c->v_flux, use_device_volumes ? c->v_vol : nullptr, use_device_volumes ? c->v_valid : nullptr,
+                             c->v_field_ind, c->v_K, flim, alpha, fcmin, sum_omega, vol_int, edges, nbins, phi_out, counts, sumphi);
+}
+
+extern "C" int lf_veff_get_phi(lf_ctx* c, double* phi_out) {
+    if (!c || !phi_out) return fail("lf_veff_get_phi: null argument");
+    if (!c->v_phi || c->vN <= 0) return fail("lf_veff_get_phi: no weights are resident");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(phi_out, c->v_phi, sizeof(double) * (size_t)c->vN, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
     return 0;
 }
 
 extern "C" int lf_bin_weights(lf_ctx* c, int64_t n, const double* lum, const double* phi, const double* edges,
                               int32_t nbins, int64_t* counts, double* sumphi) {
     if (!c) return fail("lf_bin_weights: null context");
-    if (n <= 0 || !lum || !phi || !edges || !counts || !sumphi) return fail("lf_bin_weights: bad arguments");
+    if (!edges || !counts || !sumphi) return fail("lf_bin_weights: bad arguments");
     if (nbins < 1 || nbins > VEFF_MAX_BINS) return fail("lf_bin_weights: nbins out of range");
+    // lum == NULL and phi == NULL: bin the sample and weights already resident (left by lf_veff_bin*), nothing is uploaded
+    const bool resident = !lum && !phi;
+    if (resident) {
+        if (!c->v_phi || !c->v_lum || c->vN <= 0) return fail("lf_bin_weights: no sample is resident");
+        n = c->vN;
+    } else if (n <= 0 || !lum || !phi) return fail("lf_bin_weights: bad arguments");
     CK(cudaSetDevice(c->device));
-    dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
-    dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
-    const size_t nb = sizeof(double) * (size_t)n;
-    CK(cudaMalloc(&c->v_lum, nb));
-    CK(cudaMalloc(&c->v_phi, nb));
-    CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
+    if (scratch_acquire(c, c->stream)) return 1;
+    if (!resident) {
+        if (veff_alloc_sample(c, n)) return 1;
+        if (c->v_have_sample) { c->v_have_sample = false; c->v_have_volumes = false; dfree(c->v_flux); }
+        const size_t nb = sizeof(double) * (size_t)n;
+        CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(c->v_phi, phi, nb, cudaMemcpyHostToDevice, c->stream));
+    }
     const VeffPlan plan = veff_plan(c, n, nbins);
+    if (veff_alloc_bins(c, plan, nbins, edges)) return 1;
     const int blocks = plan.blocks;
-    c->v_blocks = blocks; c->v_nbins = nbins; c->vN = n;
-    CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)blocks * nbins));
-    CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)blocks * nbins));
-    CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
-    CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
-    CK(cudaMalloc(&c->v_bin, sizeof(short) * (size_t)n));
-    CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->v_phi, phi, nb, cudaMemcpyHostToDevice, c->stream));
-    CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
     VeffArgs a;
     memset(&a, 0, sizeof(a));
     a.n = n; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = nbins;
@@ -519,6 +602,136 @@ extern "C" int lf_bin_weights(lf_ctx* c, int64_t n, const double* lum, const dou
     CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (cudaEventQuery(c->ev1) == cudaSuccess) { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// min_comp_frac > 0: per-source upper redshift limit and volume (reference lumfuncmcmc.py:521-524 ->
+// VmaxLumFunc.py:739-753 getMaxz = fsolve per source, VmaxLumFunc.py:235-257 lumfunc = QUADPACK per source)
+// ------------------------------------------------------------------------------------------------
+struct VolArgs {
+    long long n; const double* lum; int K; long long field_ind[LF_MAX_FIELDS + 1]; double fmin[LF_MAX_FIELDS];
+    lf_cosmology cosmo; const double* cum; long long ncum; const double* gl;
+    long long nk; const double* zk; const double* dVk; const double* cumV;
+    double zmin, zmax, DLmin, DLmax;
+    double* vol; unsigned char* valid; double* zmax_out;
+};
+
+// int_{zk[0]}^{z} of the piecewise-linear interpolant through (zk, dVk): cumulative trapezoids + the partial segment
+__device__ __forceinline__ double volume_to(const VolArgs& a, double z) {
+    const long long j = knot_segment(a.nk, a.zk, z);
+    if (j >= a.nk - 1) return a.cumV[a.nk - 1];
+    const double x0 = a.zk[j], y0 = a.dVk[j];
+    const double slope = (a.dVk[j + 1] - y0) / (a.zk[j + 1] - x0);
+    const double dz = z - x0;
+    return a.cumV[j] + dz * (y0 + 0.5 * slope * dz);
+}
+
+__global__ void __launch_bounds__(256) k_veff_volumes(VolArgs a) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    int k = 0;
+    while (k + 1 < a.K && i >= a.field_ind[k + 1]) ++k;
+    // luminosity distance [Mpc] at which 10^lum_i has dropped to the field's minimum flux (VmaxLumFunc.py:737, astropy's Mpc -> cm)
+    const double target = sqrt(exp10(a.lum[i]) / (FOURPI * a.fmin[k])) / 3.085677581491367e24;
+    double zm;
+    bool ok = true;
+    if (!(target > a.DLmin)) { ok = false; zm = a.zmin; }              // root <= zmin (or NaN): no volume, weight 0
+    else if (target >= a.DLmax) zm = a.zmax;                            // min(self.zmax, root)
+    else {
+        // D_L(z) = target by Newton from the secant through the interval's ends (D_L is smooth, increasing and close to
+        // linear over a survey's redshift range: 1e-2 -> 1e-4 -> 1e-8 -> 1e-16); iterates stay inside [zmin, zmax]
+        zm = a.zmin + (a.zmax - a.zmin) * (target - a.DLmin) / (a.DLmax - a.DLmin);
+        const double dH = 299792.458 / a.cosmo.H0;
+        for (int it = 0; it < 6; ++it) {
+            double dm, dc;
+            cosmo_dm(a.cosmo, a.cum, a.ncum, a.gl, a.gl + 8, zm, dm, dc);
+            double cf = 1.0;                                            // d(dm)/d(dc) / dH
+            if (a.cosmo.Ok0 > 0.0) cf = cosh(sqrt(a.cosmo.Ok0) * dc);
+            else if (a.cosmo.Ok0 < 0.0) cf = cos(sqrt(-a.cosmo.Ok0) * dc);
+            const double DL = (1.0 + zm) * dm;
+            const double dDL = dm + (1.0 + zm) * dH * cf / efunc_np(a.cosmo, zm);
+            zm -= (DL - target) / dDL;
+            zm = fmin(fmax(zm, a.zmin), a.zmax);
+        }
+        ok = zm > a.zmin;
+    }
+    a.vol[i] = ok ? volume_to(a, zm) - volume_to(a, a.zmin) : 1.0;
+    a.valid[i] = ok ? 1 : 0;
+    if (a.zmax_out) a.zmax_out[i] = zm;
+}
+
+extern "C" int lf_veff_set_volume_table(lf_ctx* c, const lf_cosmology* cosmo, const double* cum, int64_t ncum, int64_t nk,
+                                        const double* zk, const double* dVk) {
+    if (!c || !cosmo || !cum || !zk || !dVk) return fail("lf_veff_set_volume_table: null argument");
+    if (ncum < 1 || nk < 2) return fail("lf_veff_set_volume_table: need ncum >= 1 and nk >= 2");
+    if (!(cosmo->panel > 0.0) || !(cosmo->H0 > 0.0)) return fail("lf_veff_set_volume_table: need panel > 0 and H0 > 0");
+    for (int64_t j = 1; j < nk; ++j)
+        if (!(zk[j] > zk[j - 1])) return fail("lf_veff_set_volume_table: knots must be strictly increasing");
+    CK(cudaSetDevice(c->device));
+    if (scratch_acquire(c, c->stream)) return 1;
+    CK(cudaStreamSynchronize(c->stream));
+    dfree(c->v_cum); dfree(c->v_gl); dfree(c->v_zk); dfree(c->v_dVk); dfree(c->v_cumV);
+    c->v_nk = 0; c->v_have_volumes = false;
+    // cumulative trapezoids of the interpolant, sequential long-double sum (exact to the last bit that matters)
+    std::vector<double> cumV((size_t)nk);
+    long double acc = 0.0L;
+    cumV[0] = 0.0;
+    for (int64_t j = 1; j < nk; ++j) {
+        acc += 0.5L * ((long double)dVk[j] + (long double)dVk[j - 1]) * ((long double)zk[j] - (long double)zk[j - 1]);
+        cumV[(size_t)j] = (double)acc;
+    }
+    CK(cudaMalloc(&c->v_cum, sizeof(double) * ncum));
+    CK(cudaMalloc(&c->v_gl, sizeof(double) * 16));
+    CK(cudaMalloc(&c->v_zk, sizeof(double) * nk));
+    CK(cudaMalloc(&c->v_dVk, sizeof(double) * nk));
+    CK(cudaMalloc(&c->v_cumV, sizeof(double) * nk));
+    CK(cudaMemcpy(c->v_cum, cum, sizeof(double) * ncum, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->v_gl, cosmo->gl_x, sizeof(double) * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->v_gl + 8, cosmo->gl_w, sizeof(double) * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->v_zk, zk, sizeof(double) * nk, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->v_dVk, dVk, sizeof(double) * nk, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->v_cumV, cumV.data(), sizeof(double) * nk, cudaMemcpyHostToDevice));
+    c->v_cosmo = *cosmo; c->v_ncum = ncum; c->v_nk = nk;
+    return 0;
+}
+
+extern "C" int lf_veff_volumes(lf_ctx* c, double zmin, double zmax, double DL_zmin, double DL_zmax, const double* fmin,
+                               double* zmax_out, double* vol_out, uint8_t* valid_out) {
+    if (!c || !fmin) return fail("lf_veff_volumes: null argument");
+    if (!c->v_have_sample) return fail("lf_veff_volumes: call lf_veff_set_sample first");
+    if (c->v_nk < 2) return fail("lf_veff_volumes: call lf_veff_set_volume_table first");
+    if (!(zmax >= zmin) || !(DL_zmax >= DL_zmin) || !(DL_zmin > 0.0)) return fail("lf_veff_volumes: need zmin <= zmax and 0 < D_L(zmin) <= D_L(zmax)");
+    for (int k = 0; k < c->v_K; ++k)
+        if (!(fmin[k] > 0.0)) return fail("lf_veff_volumes: minimum fluxes must be positive");
+    CK(cudaSetDevice(c->device));
+    if (scratch_acquire(c, c->stream)) return 1;
+    const long long n = c->vN;
+    if (!c->v_vol) CK(cudaMalloc(&c->v_vol, sizeof(double) * (size_t)n));
+    if (!c->v_valid) CK(cudaMalloc(&c->v_valid, (size_t)n));
+    double* d_zm = nullptr;
+    DevBufs tmp;
+    if (zmax_out) CK(tmp.alloc(&d_zm, sizeof(double) * (size_t)n));
+    VolArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.lum = c->v_lum; a.K = c->v_K;
+    for (int k = 0; k <= c->v_K; ++k) a.field_ind[k] = c->v_field_ind[k];
+    for (int k = 0; k < c->v_K; ++k) a.fmin[k] = fmin[k];
+    a.cosmo = c->v_cosmo; a.cum = c->v_cum; a.ncum = c->v_ncum; a.gl = c->v_gl;
+    a.nk = c->v_nk; a.zk = c->v_zk; a.dVk = c->v_dVk; a.cumV = c->v_cumV;
+    a.zmin = zmin; a.zmax = zmax; a.DLmin = DL_zmin; a.DLmax = DL_zmax;
+    a.vol = c->v_vol; a.valid = c->v_valid; a.zmax_out = d_zm;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    k_veff_volumes<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(a);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1;
+    CK(cudaGetLastError());
+    if (zmax_out) CK(cudaMemcpyAsync(zmax_out, d_zm, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (vol_out) CK(cudaMemcpyAsync(vol_out, c->v_vol, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    if (valid_out) CK(cudaMemcpyAsync(valid_out, c->v_valid, (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms; }
+    c->v_have_volumes = true;
     return 0;
 }
 
@@ -540,6 +753,7 @@ extern "C" int lf_boot_bin_device(lf_ctx* c, uint64_t seed, int64_t replicate, i
     if (!counts || !sumphi) return fail("lf_boot_bin_device: bad arguments");
     if (c->vN >= (1LL << 32)) return fail("lf_boot_bin_device: more than 2^32 sources");
     CK(cudaSetDevice(c->device));
+    if (scratch_acquire(c, c->stream)) return 1;
     if (!c->v_mult) CK(cudaMalloc(&c->v_mult, sizeof(int) * (size_t)c->vN));
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->v_mult, 0, sizeof(int) * (size_t)c->vN, c->stream));
@@ -569,6 +783,7 @@ extern "C" int lf_boot_bin(lf_ctx* c, const int32_t* mult, int64_t* counts, doub
     if (!c->v_phi || c->vN <= 0) return fail("lf_boot_bin: call lf_veff_bin first");
     if (!mult || !counts || !sumphi) return fail("lf_boot_bin: bad arguments");
     CK(cudaSetDevice(c->device));
+    if (scratch_acquire(c, c->stream)) return 1;
     if (!c->v_mult) CK(cudaMalloc(&c->v_mult, sizeof(int) * (size_t)c->vN));
     CK(cudaMemcpyAsync(c->v_mult, mult, sizeof(int) * (size_t)c->vN, cudaMemcpyHostToDevice, c->stream));
     VeffArgs a;

@@ -49,6 +49,14 @@ def reduce_partials(partial, group=None):
     return partial
 
 
+def check_peer_geometry(gathered, world, wcap):
+    """``gathered[r] = (handle, rank, world, wcap)`` as every rank reported it; raises unless all agree with this rank."""
+    for r, g in enumerate(gathered):
+        if g[1] != r or g[2] != world or g[3] != wcap:
+            raise RuntimeError("peer buffers disagree: rank %d reports (rank=%d, world=%d, wcap=%d), expected (%d, %d, %d)"
+                               % (r, g[1], g[2], g[3], r, world, wcap))
+
+
 def walker_slice(W, rank, world):
     """Walkers [lo, hi) of a W-walker ensemble that rank r evaluates under walker sharding (contiguous, balanced)."""
     return shard_bounds(W, rank, world)
@@ -72,7 +80,9 @@ def gather_walker_results(local, W, group=None):
 
 class WalkerShardedLikelihood:
     """Small catalogues: every rank holds ALL sources and evaluates its slice of the walkers; the only
-    exchange is the all-gather of W/world results -- no sum over ranks, so results are bit-identical to one GPU."""
+    exchange is the all-gather of W/world results -- no sum over ranks.  Every walker's value is computed by one GPU
+    exactly as a single-GPU call on that slice would (the slab partition of the sources depends on the number of walkers
+    in the call, so the bits can differ from a full-ensemble call in the last place, ~1e-16 relative)."""
 
     def __init__(self, inp, kind, device=None, group=None, precision='f64'):
         import torch
@@ -84,6 +94,21 @@ class WalkerShardedLikelihood:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.engine = LikelihoodEngine(inp, kind, device=self.device, precision=precision)
         self.ndim = self.engine.ndim
+
+    def lnprob_device(self, d_thetas, d_out=None):
+        """Device-resident call on torch's current stream: this rank's slice of ``d_thetas`` (all W rows, identical on
+        every rank) -> kernels -> all-gather; returns the full (W,) vector on the device."""
+        t = self.torch
+        W = d_thetas.shape[0]
+        lo, hi = walker_slice(W, self.rank, self.world)
+        if self.world == 1:
+            return self.engine.lnprob_device(d_thetas, d_out)
+        local = self.engine.lnprob_device(d_thetas[lo:hi]) if hi > lo else t.zeros(0, dtype=t.float64, device=d_thetas.device)
+        full = gather_walker_results(local, W, self.group)
+        if d_out is not None:
+            d_out.copy_(full)
+            return d_out
+        return full
 
     def lnprob(self, thetas):
         t = self.torch
@@ -124,9 +149,13 @@ class ShardedLikelihood:
         self.wcap = int(wcap)
         if self.exchange == 'p2p':
             handle = self.engine.peer_buffer_create(self.rank, self.world, self.wcap)
-            handles = [None] * self.world
-            dist.all_gather_object(handles, handle, group=group)
-            self.engine.peer_buffer_connect(handles)
+            # the slot offsets inside every rank's buffer are computed from (world, wcap): a rank that created its buffer
+            # with other values would receive stores in the wrong place, so the geometry travels with the handle
+            mine = (handle, self.rank, self.world, self.wcap)
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, mine, group=group)
+            check_peer_geometry(gathered, self.world, self.wcap)
+            self.engine.peer_buffer_connect([g[0] for g in gathered])
             dist.barrier(group=group)
 
     def _ensure(self, W):
@@ -141,7 +170,10 @@ class ShardedLikelihood:
         self._cap = W
 
     def lnprob_device(self, d_thetas, d_out=None):
-        """Device-resident call on torch's current stream: kernels + all-reduce, asynchronous."""
+        """Device-resident call on torch's current stream: kernels + all-reduce, asynchronous.  A peer time-out of an
+        earlier call (sticky; its result and all later ones are NaN) raises here."""
+        if self.exchange == 'p2p' and self.engine.peer_timed_out():
+            raise RuntimeError("peer-memory all-reduce timed out waiting for another rank; results since then are NaN")
         d_out = self.engine.lnprob_device(d_thetas, d_out)
         if self.exchange == 'p2p':
             if d_out.shape[0] > self.wcap:

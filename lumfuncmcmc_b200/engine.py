@@ -45,6 +45,9 @@ def source_flux(inp):
 class _VeffOps:
     """1/V_eff weights, binned LF and bootstrap replicates on a context (``self._ctx`` / ``self.lib``)."""
 
+    _phi_gen = 0             # bumped whenever the weights resident on the device are replaced
+    _sample_owner = None     # whoever uploaded the resident sample (lfbase.LFBase._veff)
+
     def veff_bin(self, flux, lum, field_ind, flim, alpha, fcmin, sum_omega, vol_int, edges, vol_per_source=None,
                  valid=None, want_phi=True):
         """1/V_eff weights and the binned LF of the original sample (reference lumfuncmcmc.py:515-525,
@@ -56,12 +59,62 @@ class _VeffOps:
         val = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8)
         phi = np.empty(n, dtype=np.float64) if want_phi else None
         self._veff_nbins = nb
+        self._phi_gen += 1
+        self._sample_owner = None
         counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
         _lib.check(self.lib.lf_veff_bin(self._ctx, n, _ptr(flux), _ptr(lum), _ptr(fi), len(flim), _ptr(flim),
                                         float(alpha), float(fcmin) if fcmin else 0.0, float(sum_omega), float(vol_int),
                                         _ptr(vps), _ptr(val), _ptr(edges), nb, _ptr(phi), _ptr(counts), _ptr(sums)),
                    self.lib)
         return phi, counts, sums
+
+    # ---- sample resident across calls (VeffLF runs once per posterior summary on the same catalogue) ----
+    def veff_set_sample(self, flux, lum, field_ind):
+        """Upload flux (cgs), log-luminosity and the field offsets once (``lf_veff_set_sample``)."""
+        flux, lum = _f64(flux), _f64(lum)
+        fi = np.ascontiguousarray(field_ind, dtype=np.int64)
+        _lib.check(self.lib.lf_veff_set_sample(self._ctx, flux.shape[0], _ptr(flux), _ptr(lum), _ptr(fi), len(fi) - 1), self.lib)
+        self._veff_n = int(flux.shape[0])
+
+    def veff_bin_resident(self, flim, alpha, fcmin, sum_omega, vol_int, edges, device_volumes=False, want_phi=False):
+        """Weights + binned LF of the resident sample; the weights stay on the device (:meth:`veff_phi` fetches them).
+        Returns (phi or None, counts, sumphi)."""
+        flim, edges = _f64(flim), _f64(edges)
+        nb = edges.shape[0] - 1
+        phi = np.empty(self._veff_n, dtype=np.float64) if want_phi else None
+        self._veff_nbins = nb
+        self._phi_gen += 1
+        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
+        _lib.check(self.lib.lf_veff_bin_resident(self._ctx, _ptr(flim), float(alpha), float(fcmin) if fcmin else 0.0,
+                                                 float(sum_omega), float(vol_int), int(bool(device_volumes)), _ptr(edges), nb,
+                                                 _ptr(phi), _ptr(counts), _ptr(sums)), self.lib)
+        return phi, counts, sums
+
+    def veff_phi(self):
+        """The resident per-source weights as a host array (``lf_veff_get_phi``)."""
+        phi = np.empty(self._veff_n, dtype=np.float64)
+        _lib.check(self.lib.lf_veff_get_phi(self._ctx, _ptr(phi)), self.lib)
+        return phi
+
+    def veff_set_volume_table(self, cosmo, zk, dVk):
+        """Cosmology + knots of the dV/dz interpolant for :meth:`veff_volumes` (``lf_veff_set_volume_table``)."""
+        from .setup_gpu import cosmology_struct
+        zk, dVk = _f64(zk), _f64(dVk)
+        c, cum = cosmology_struct(cosmo, float(zk[-1]))
+        _lib.check(self.lib.lf_veff_set_volume_table(self._ctx, C.byref(c), _ptr(cum), cum.shape[0], zk.shape[0], _ptr(zk),
+                                                     _ptr(dVk)), self.lib)
+
+    def veff_volumes(self, zmin, zmax, DL_zmin, DL_zmax, fmin, want=False):
+        """Per-source upper redshift limit, volume and validity for min_comp_frac > 0 on the resident sample; the results
+        stay on the device for ``veff_bin_resident(device_volumes=True)``.  ``want=True`` also returns (zmax_i, vol_i, valid_i)."""
+        fmin = _f64(fmin)
+        n = self._veff_n
+        zm = np.empty(n) if want else None
+        vol = np.empty(n) if want else None
+        val = np.empty(n, dtype=np.uint8) if want else None
+        _lib.check(self.lib.lf_veff_volumes(self._ctx, float(zmin), float(zmax), float(DL_zmin), float(DL_zmax), _ptr(fmin),
+                                            _ptr(zm), _ptr(vol), _ptr(val)), self.lib)
+        return (zm, vol, val) if want else None
 
     def boot_bin(self, mult):
         """One bootstrap replicate on the sample left resident by :meth:`veff_bin`."""
@@ -88,11 +141,18 @@ class _VeffOps:
         return ms.value
 
     def bin_weights(self, lum, phi, edges):
-        """Counts and sum of caller-provided weights per half-open bin (reference VmaxLumFunc.py:345-350)."""
-        lum, phi, edges = _f64(lum), _f64(phi), _f64(edges)
+        """Counts and sum of caller-provided weights per half-open bin (reference VmaxLumFunc.py:345-350).
+        ``lum is None and phi is None``: bin the sample and weights already resident on the device."""
+        edges = _f64(edges)
         nb = edges.shape[0] - 1
         self._veff_nbins = nb
         counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
+        if lum is None and phi is None:
+            _lib.check(self.lib.lf_bin_weights(self._ctx, 0, None, None, _ptr(edges), nb, _ptr(counts), _ptr(sums)), self.lib)
+            return counts, sums
+        lum, phi = _f64(lum), _f64(phi)
+        self._phi_gen += 1
+        self._sample_owner = None
         _lib.check(self.lib.lf_bin_weights(self._ctx, lum.shape[0], _ptr(lum), _ptr(phi), _ptr(edges), nb,
                                            _ptr(counts), _ptr(sums)), self.lib)
         return counts, sums
@@ -320,9 +380,16 @@ class LikelihoodEngine(_VeffOps):
         return d_vec
 
     def peer_timed_out(self):
+        """True once a wait for another rank has expired (sticky until :meth:`peer_reset`; results since then are NaN)."""
         v = C.c_int32()
         _lib.check(self.lib.lf_peer_status(self._ctx, C.byref(v)), self.lib)
         return bool(v.value)
+
+    def peer_reset(self):
+        _lib.check(self.lib.lf_peer_reset(self._ctx), self.lib)
+
+    def peer_set_timeout(self, seconds):
+        _lib.check(self.lib.lf_peer_set_timeout(self._ctx, float(seconds)), self.lib)
 
     def last_call_info(self):
         counts = (C.c_int64 * 3)()

@@ -242,35 +242,78 @@ class LFBase:
                 self.table[-1][(i + start_value + j * n)] = v
 
     # ------------------------------------------------------------------ 1/V_eff luminosity function
+    _phifunc, _phi_engine, _phi_gen = None, None, -1
+
+    @property
+    def phifunc(self):
+        """Per-source 1/V_eff weights (reference attribute of the same name).  ``VeffLF`` leaves them on the GPU; they are
+        copied to the host the first time this attribute is read."""
+        if self._phifunc is None and self._phi_engine is not None:
+            if self._phi_engine._phi_gen != self._phi_gen:
+                raise RuntimeError("the 1/V_eff weights are no longer resident on the device (another sample was binned "
+                                   "on this engine); call VeffLF() again")
+            self._phifunc = self._phi_engine.veff_phi()
+        return self._phifunc
+
+    @phifunc.setter
+    def phifunc(self, value):
+        self._phifunc, self._phi_engine = value, None
+
+    def _veff_volumes_host(self, root_per_source):
+        """The reference's per-source loop (lumfuncmcmc.py:521-524): one fsolve (``V.getMaxz``) and one QUADPACK integral
+        per source.  Kept as the checked oracle of the device path (tests); O(N) Python, hours at 1e7 sources."""
+        n = len(self.flux)
+        vol, valid, zmaxs = np.ones(n), np.zeros(n, dtype=np.uint8), np.zeros(n)
+        for i in range(n):
+            zmaxval = min(self.zmax, V.getMaxz(10 ** self.lum[i], root_per_source[i]))
+            zmaxs[i] = zmaxval
+            if zmaxval > self.zmin:
+                vol[i] = quad(self.dVdzf, self.zmin, zmaxval)[0]
+                valid[i] = 1
+        return zmaxs, vol, valid
+
     def _veff(self, root_per_source):
         """Per-source 1/V_eff weights, binned LF and bootstrap errors on the GPU (reference lumfuncmcmc.py:515-525).
 
-        With min_comp_frac <= 0.001 every source integrates dV/dz over the whole [zmin, zmax]: one shared QUADPACK
-        integral of the interpolant, exactly the number the reference computes N times.  Otherwise each source's
-        upper limit is where its luminosity drops to the field's minimum flux (``V.getMaxz``) and its volume is a
-        QUADPACK integral to that limit, as in the reference."""
+        The catalogue (flux, lum) is uploaded once per engine and stays resident: VeffLF runs after every fit and again
+        for each posterior summary with new completeness parameters.  With min_comp_frac <= 0.001 every source integrates
+        dV/dz over the whole [zmin, zmax]: one shared QUADPACK integral of the interpolant, exactly the number the
+        reference computes N times.  Otherwise each source's upper limit is where its luminosity drops to the field's
+        minimum flux and its volume is the integral of dVdzf to that limit: the reference's per-source fsolve + QUADPACK
+        loop becomes one kernel (``lf_veff_volumes``: Newton on D_L, exact integral of the linear interpolant), equal to
+        the loop within its own solver tolerances (1.5e-8; :meth:`_veff_volumes_host` is the loop itself)."""
         sum_Omega = sum(self.Omega_0)
         n = len(self.flux)
-        vol, valid = None, None
-        if self.min_comp_frac <= 0.001:
-            vol_int = quad(self.dVdzf, self.zmin, self.zmax)[0] if self.zmax > self.zmin else 0.0
-            if not self.zmax > self.zmin:
-                valid = np.zeros(n, dtype=np.uint8)
-                vol_int = 1.0
-        else:
-            vol_int, vol, valid = 1.0, np.ones(n), np.zeros(n, dtype=np.uint8)
-            for i in range(n):
-                zmaxval = min(self.zmax, V.getMaxz(10 ** self.lum[i], root_per_source[i]))
-                if zmaxval > self.zmin:
-                    vol[i] = quad(self.dVdzf, self.zmin, zmaxval)[0]
-                    valid[i] = 1
-        edges = np.linspace(min(self.lum) * 1.001, max(self.lum), self.nbins + 1)
         eng = self._veff_engine()
-        self.phifunc, counts, _ = eng.veff_bin(self.flux, self.lum, self.field_ind, self.Flim, self.alpha, self.fcmin,
-                                               sum_Omega, vol_int, edges, vol_per_source=vol, valid=valid)
+        if getattr(self, '_veff_sample_on', None) is not eng or eng._sample_owner is not self:
+            eng.veff_set_sample(self.flux, self.lum, self.field_ind)
+            eng._sample_owner, self._veff_sample_on, self._veff_table_on = self, eng, None
+        lum_lo, lum_hi = np.min(self.lum), np.max(self.lum)
+        edges = np.linspace(lum_lo * 1.001, lum_hi, self.nbins + 1)
+        if self.min_comp_frac <= 0.001 and self.zmax > self.zmin:
+            vol_int = quad(self.dVdzf, self.zmin, self.zmax)[0]
+            _, counts, sums = eng.veff_bin_resident(self.Flim, self.alpha, self.fcmin, sum_Omega, vol_int, edges)
+        elif self.min_comp_frac <= 0.001:
+            # degenerate catalogue (one redshift): no source has a volume, every weight is 0 (lumfuncmcmc.py:522-523)
+            _, counts, sums = eng.veff_bin(self.flux, self.lum, self.field_ind, self.Flim, self.alpha, self.fcmin, sum_Omega,
+                                           1.0, edges, valid=np.zeros(n, dtype=np.uint8), want_phi=False)
+            self._veff_sample_on = None
+        else:
+            if self._veff_table_on is not eng:
+                eng.veff_set_volume_table(_cosmo, self.dVdzf.x, self.dVdzf.y)
+                self._veff_table_on = eng
+            fi = np.asarray(self.field_ind, dtype=np.int64)
+            root = np.asarray(root_per_source, dtype=np.float64)
+            fmin = np.array([root[fi[k]] if fi[k + 1] > fi[k] else 1.0 for k in range(self.nfields)])   # constant within a field
+            eng.veff_volumes(self.zmin, self.zmax, float(_cosmo.luminosity_distance(self.zmin)),
+                             float(_cosmo.luminosity_distance(self.zmax)), fmin)
+            _, counts, sums = eng.veff_bin_resident(self.Flim, self.alpha, self.fcmin, sum_Omega, 1.0, edges,
+                                                    device_volumes=True)
+        self._phifunc, self._phi_engine, self._phi_gen = None, eng, eng._phi_gen
         self.Lavg, self.lfbinorig, self.var, self.bincounts = V.getBootErrLog(
-            self.lum, self.phifunc, self.zmin, self.zmax, self.nboot, self.nbins, Fmin=1.0e-17 * np.max(self.Flim),
-            engine=eng, return_counts=True, rng=getattr(self, 'boot_rng', None) or os.environ.get('LF_BOOT_RNG', 'host'))
+            self.lum, None, self.zmin, self.zmax, self.nboot, self.nbins, Fmin=1.0e-17 * np.max(self.Flim),
+            engine=eng, return_counts=True, rng=getattr(self, 'boot_rng', None) or os.environ.get('LF_BOOT_RNG', 'host'),
+            Lrange=(lum_lo, lum_hi))
 
     def _veff_engine(self):
         if self._engines:

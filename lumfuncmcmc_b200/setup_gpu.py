@@ -59,6 +59,18 @@ def interp_linear(xk, yk, x, device=0):
     return y
 
 
+def cosmology_struct(cosmo, zmax):
+    """(``lf_cosmology`` struct, cumulative panel integrals covering [0, zmax]) of a :class:`..cosmology.LambdaCDM`."""
+    cosmo._extend(float(zmax))
+    cum = _f64(cosmo._cum)
+    c = _lib.LFCosmology()
+    c.H0, c.Om0, c.Ode0, c.Or0, c.Ok0, c.panel = cosmo.H0, cosmo.Om0, cosmo.Ode0, cosmo.Or0, cosmo.Ok0, cosmo._panel
+    glx, glw = np.polynomial.legendre.leggauss(8)
+    c.gl_x = (C.c_double * 8)(*glx)
+    c.gl_w = (C.c_double * 8)(*glw)
+    return c, cum
+
+
 def cosmo_distances(cosmo, z, device=0, want_dl=True, want_dv=True):
     """(D_L [Mpc], dV/dz/dOmega [Mpc^3/sr]) of a :class:`lumfuncmcmc_b200.cosmology.LambdaCDM` for an array z."""
     lib = _lib.load()
@@ -67,13 +79,7 @@ def cosmo_distances(cosmo, z, device=0, want_dl=True, want_dv=True):
     z = z.ravel()
     if z.size == 0:
         return (np.zeros(shape) if want_dl else None), (np.zeros(shape) if want_dv else None)
-    cosmo._extend(float(np.max(z)))
-    cum = _f64(cosmo._cum)
-    c = _lib.LFCosmology()
-    c.H0, c.Om0, c.Ode0, c.Or0, c.Ok0, c.panel = cosmo.H0, cosmo.Om0, cosmo.Ode0, cosmo.Or0, cosmo.Ok0, cosmo._panel
-    glx, glw = np.polynomial.legendre.leggauss(8)
-    c.gl_x = (C.c_double * 8)(*glx)
-    c.gl_w = (C.c_double * 8)(*glw)
+    c, cum = cosmology_struct(cosmo, float(np.max(z)))
     dl = np.empty_like(z) if want_dl else None
     dv = np.empty_like(z) if want_dv else None
     _lib.check(lib.lf_cosmo_distances(int(device), C.byref(c), _p(cum), cum.shape[0], z.size, _p(z), _p(dl), _p(dv)), lib)

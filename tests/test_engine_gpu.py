@@ -417,6 +417,50 @@ def test_peer_memory_allreduce_degenerates_to_identity_on_one_rank(golden):
     eng.close()
 
 
+def test_peer_exchange_timeout_poisons_the_result_and_is_sticky(golden):
+    """A rank that never arrives: the wait expires (bound set to 20 ms here), the exchange returns NaN -- never a stale
+    partial sum --, the flag stays set, later exchanges are refused until lf_peer_reset.  World = 2 with no peer mapped
+    for rank 1 (all-zero handle row): its flag is never raised."""
+    import torch
+    g = golden('free_k3_fixal')
+    eng = _engine(g, 'free')
+    handle = eng.peer_buffer_create(0, 2, 512)
+    eng.peer_buffer_connect([handle, bytes(64)])
+    eng.peer_set_timeout(0.02)
+    v = torch.arange(300, dtype=torch.float64, device='cuda') + 1.0
+    eng.allreduce_device(v)
+    torch.cuda.synchronize()
+    assert torch.isnan(v).all()
+    assert eng.peer_timed_out() and eng.peer_timed_out()          # sticky
+    with pytest.raises(Exception, match='timed out'):
+        eng.allreduce_device(v)
+    eng.peer_reset()
+    assert not eng.peer_timed_out()
+    eng.close()
+
+
+def test_lnprob_on_a_caller_stream_is_ordered_against_the_context_stream(golden):
+    """The per-call scratch is shared by every entry point of a context: a device call on the caller's stream followed
+    at once by host-API calls (context stream) and the reverse must give the same numbers as serial execution."""
+    import torch
+    g = golden('free_k5_n2000')
+    eng = _engine(g, 'free')
+    th = np.ascontiguousarray(g['thetas'])
+    want = eng.lnprob(th)
+    d_th = torch.from_numpy(th).cuda()
+    side = torch.cuda.Stream()
+    outs = []
+    for rep in range(20):
+        with torch.cuda.stream(side):
+            outs.append(eng.lnprob_device(d_th, stream=side))
+        got_host = eng.lnprob(th[::-1].copy())                    # context stream, right behind the side-stream call
+        assert np.array_equal(got_host, want[::-1], equal_nan=True)
+    torch.cuda.synchronize()
+    for o in outs:
+        assert np.array_equal(o.cpu().numpy(), want, equal_nan=True)
+    eng.close()
+
+
 def test_device_resampled_bootstrap_equals_host_replay_of_the_philox_stream():
     """rng='device': every replicate's multiplicities come from a Philox stream on the GPU; a host replay of the same
     stream gives the same integer counts, sums agree to 1e-12, and the variances are statistically those of the
