@@ -18,6 +18,20 @@ from .cosmology import cosmo
 
 SQARCSEC = (180. / np.pi * 3600.0) ** 2
 
+#: CUDA ordinal used for the O(N) cosmology passes of large catalogues when a GPU is present (bench / tests set it to the
+#: rank's device); below ``setup_gpu.GPU_MIN_POINTS`` points, or without a GPU, the host arithmetic of cosmology.py runs
+DEVICE = 0
+
+
+def _lumdist(z):
+    """D_L [Mpc]: ``cosmology.cosmo`` on the host, or the same arithmetic on the GPU (``lf_cosmo_distances``, equal to
+    ~2e-15) for large arrays -- synthetic data either way, and both the oracle and the engine consume what comes out."""
+    from .setup_gpu import GPU_MIN_POINTS, cosmo_distances, gpu_count
+    z = np.asarray(z, dtype=np.float64)
+    if z.size >= GPU_MIN_POINTS and gpu_count() > 0:
+        return cosmo_distances(cosmo, z, device=DEVICE, want_dv=False)[0]
+    return cosmo.luminosity_distance(z)
+
 
 def _fleming(f, f50, alpha, fcmin):
     n = alpha * np.log10(f / f50)
@@ -63,7 +77,7 @@ def make_catalogue(n_sources, seed=0, nfields=5, Lstar=42.5, phistar=-2.0, sch_a
     expected = np.array(expected)
     counts = np.floor(n_sources * expected / expected.sum()).astype(np.int64)
     counts[np.argmax(counts)] += n_sources - counts.sum()
-    z_l, f_l, fe_l = [], [], []
+    z_l, f_l, fe_l, dl_l = [], [], [], []
     for k in range(nfields):
         cdf = np.cumsum(dens[k].ravel())
         cdf /= cdf[-1]
@@ -72,19 +86,26 @@ def make_catalogue(n_sources, seed=0, nfields=5, Lstar=42.5, phistar=-2.0, sch_a
         iz, il = np.divmod(cell, nl)
         z = zmin + (zmax - zmin) * (iz + rng.random(counts[k])) / nz
         logL = Lc + (Lh - Lc) * (il + rng.random(counts[k])) / nl
-        flux = 10.0 ** logL / (4.0 * np.pi * (3.086e24 * cosmo.luminosity_distance(z)) ** 2) / 1.0e-17
+        dl = _lumdist(z)
+        flux = 10.0 ** logL / (4.0 * np.pi * (3.086e24 * dl) ** 2) / 1.0e-17
+        dl_l.append(dl)
         z_l.append(z)
         f_l.append(flux)
         fe_l.append(flux_err_frac * flux)
     field_ind = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     return dict(z=z_l, flux=f_l, flux_e=fe_l, field_ind=field_ind,
                 field_names=np.array(['F%d' % k for k in range(nfields)]),
-                Flim=Flim, alpha=alpha, Omega_0=Omega_0, fcmin=fcmin, expected_total=float(expected.sum()),
+                Flim=Flim, alpha=alpha, Omega_0=Omega_0, fcmin=fcmin, expected_total=float(expected.sum()), _DL=dl_l,
                 truth=dict(Lstar=Lstar, phistar=phistar, sch_al=sch_al, evolve=evolve))
 
 
-def direct_inputs(cat, nknots=4096, size_ln=101, Lh=46.0, z_pivots=(1.20, 1.53, 1.86), tabulated=False):
+def direct_inputs(cat, nknots=4096, size_ln=101, Lh=46.0, z_pivots=(1.20, 1.53, 1.86), tabulated=False, zrange=None,
+                  lum_floor=None):
     """Engine inputs straight from a catalogue (no class constructor).
+
+    ``zrange=(zmin, zmax)`` and ``lum_floor`` (a value, or a callable mapping this catalogue's own minimum to the one to
+    use) pin the quadrature grid instead of deriving it from this catalogue's extremes: the shards of ONE catalogue held
+    by several ranks must integrate over the same grid.
 
     Mirrors the reference's set-up arithmetic: knots ``zint = linspace(.95 zmin, 1.05 zmax, nknots)``
     (lumfuncmcmc.py:183, with a fixed knot count instead of N), ``lum`` from the exact D_L (:186, :259),
@@ -97,15 +118,18 @@ def direct_inputs(cat, nknots=4096, size_ln=101, Lh=46.0, z_pivots=(1.20, 1.53, 
     flux = 1.0e-17 * np.concatenate(cat['flux'])
     K = len(cat['Flim'])
     fi = np.asarray(cat['field_ind'], dtype=np.int64)
-    zmin, zmax = float(z.min()), float(z.max())
+    zmin, zmax = (float(z.min()), float(z.max())) if zrange is None else (float(zrange[0]), float(zrange[1]))
     zint = np.linspace(0.95 * zmin, 1.05 * zmax, nknots)
     DLarr = cosmo.luminosity_distance(zint)
     dVdzarr = cosmo.differential_comoving_volume(zint)
     DLf, dVdzf = interp1d(zint, DLarr), interp1d(zint, dVdzarr)
-    DL = cosmo.luminosity_distance(z)
+    DL = np.concatenate(cat['_DL']) if '_DL' in cat else _lumdist(z)       # the exact D_L of every source (:186)
     lum = np.log10(4.0 * np.pi * (DL * 3.086e24) ** 2 * flux)
     zarr = np.linspace(zmin, zmax, size_ln)
-    col = np.linspace(lum.min(), Lh, size_ln)
+    floor = lum.min() if len(lum) else Lh - 6.0
+    if lum_floor is not None:
+        floor = float(lum_floor(floor)) if callable(lum_floor) else float(lum_floor)
+    col = np.linspace(floor, Lh, size_ln)
     grid = np.repeat(col[:, None], size_ln, axis=1)
     inp = dict(lum=lum, z=z, zint=zint, DLarr=DLarr, dVdzarr=dVdzarr, field_ind=fi,
                Omega_0=np.asarray(cat['Omega_0'], dtype=np.float64), Flim=np.asarray(cat['Flim'], dtype=np.float64),
