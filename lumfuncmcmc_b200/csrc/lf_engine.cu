@@ -1193,8 +1193,17 @@ extern "C" int lf_set_grid(lf_ctx* c, const double* logL, const double* zarr, co
         CK(cudaMalloc(&c->d_qpf, sizeof(QuadPointFree) * (size_t)NQ));
         CK(cudaMemcpy(c->d_qpf, pts.data(), sizeof(QuadPointFree) * (size_t)NQ, cudaMemcpyHostToDevice));
     } else {
-        std::vector<QuadPoint> pts((size_t)NQ);
-        for (int k = 0; k < K; ++k)
+        // The reference hands every field the SAME luminosity grid (lumfuncmcmc.py:232 appends one array object for all
+        // fields), and the FIXED / Z integrand depends on the field only through integ_part: when the K
+        // grids are bit-identical the K weight planes are summed once here and the walkers integrate S^2 points instead
+        // of K S^2.  (sum_k trapz(trapz(phi integ_k)) == trapz(trapz(phi sum_k integ_k)) up to the order of additions.)
+        bool merged = K > 1;
+        for (int k = 1; k < K && merged; ++k) merged = memcmp(logL + (size_t)k * SS, logL, sizeof(double) * (size_t)SS) == 0;
+        const int Kq = merged ? 1 : K;
+        const long long NQe = SS * Kq;
+        c->NQ = NQe; a.NQ = NQe;
+        std::vector<QuadPoint> pts((size_t)NQe);
+        for (int k = 0; k < Kq; ++k)
             for (int i = 0; i < S; ++i)
                 for (int j = 0; j < S; ++j) {
                     double x = at(logL, k, j, i);
@@ -1205,11 +1214,17 @@ extern "C" int lf_set_grid(lf_ctx* c, const double* logL, const double* zarr, co
                     QuadPoint& p = pts[((size_t)k * S + i) * S + j];
                     p.x = x;
                     p.Lx = pow(10.0, x);
-                    p.wt = wl * wz[i] * at(integ_part, k, j, i);
+                    if (merged) {
+                        long double sum = 0.0L;
+                        for (int kk = 0; kk < K; ++kk) sum += (long double)at(integ_part, kk, j, i);
+                        p.wt = wl * wz[i] * (double)sum;
+                    } else {
+                        p.wt = wl * wz[i] * at(integ_part, k, j, i);
+                    }
                     p.pad = 0.0;
                 }
-        CK(cudaMalloc(&c->d_qp, sizeof(QuadPoint) * (size_t)NQ));
-        CK(cudaMemcpy(c->d_qp, pts.data(), sizeof(QuadPoint) * (size_t)NQ, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&c->d_qp, sizeof(QuadPoint) * (size_t)NQe));
+        CK(cudaMemcpy(c->d_qp, pts.data(), sizeof(QuadPoint) * (size_t)NQe, cudaMemcpyHostToDevice));
     }
     CK(cudaMalloc(&c->d_zarr, sizeof(double) * S));
     CK(cudaMemcpy(c->d_zarr, zarr, sizeof(double) * S, cudaMemcpyHostToDevice));
