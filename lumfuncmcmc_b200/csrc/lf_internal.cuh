@@ -278,6 +278,9 @@ struct lf_ctx {
     int* v_mult = nullptr; short* v_bin = nullptr; int v_blocks = 0;
     // sample kept resident across V_eff calls (lf_veff_set_sample) and its per-source volumes (lf_veff_volumes)
     double* v_flux = nullptr; double* v_vol = nullptr; unsigned char* v_valid = nullptr;
+    double* v_u = nullptr;                         // log10(flux / VRES_F0), computed once per sample
+    bool v_rows_valid = false; std::vector<double> v_edges_host;     // edges the resident rows / counts were computed for
+    unsigned long long* v_rowcounts = nullptr; int v_rowcounts_n = 0; unsigned* v_ticket = nullptr;
     // volume table of lf_veff_set_volume_table: cosmology + panel integrals, knots of the dV/dz interpolant, its cumulative integral
     lf_cosmology v_cosmo; double* v_cum = nullptr; long long v_ncum = 0; double* v_gl = nullptr;
     double* v_zk = nullptr; double* v_dVk = nullptr; double* v_cumV = nullptr; long long v_nk = 0;

@@ -348,6 +348,217 @@ __global__ void __launch_bounds__(32 * VP_WARPS) k_veff_priv(VeffArgs a) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// resident sample: what does not depend on the completeness parameters is computed ONCE
+// ------------------------------------------------------------------------------------------------
+// VeffLF is called again and again on the same catalogue with new (F50_k, alpha) (lumfuncmcmc.py:541, :567, :650).  Two
+// per-source quantities never change between those calls and are kept on the device (lf_veff_set_sample):
+//   u_i   = log10(f_i / VRES_F0)          -> n_i = alpha (u_i - log10(F50_k / VRES_F0)) is one fma instead of a logarithm;
+//           the reference point sits inside the prior range of F50, so |u| < 1 where the completeness turns over and the
+//           rounding of u (~1e-16 absolute) is what the reference's own log10(f / F50) carries
+//   row_i = histogram row of lum_i        (re-done only when the edges change) together with the integer bin counts,
+//           which do not depend on the weights at all (VmaxLumFunc.py:346-349 counts every source in the bin)
+// The weights pass then streams 26 B per source (u, f, row in; phi out) and executes 45 FP64 + ~45 other instructions per
+// source (61 + 93 in k_veff_priv<0>, which recomputes the logarithm, searches the bin and counts on every call).
+#define VRES_F0 3.0e-17
+__global__ void k_veff_prepare(long long n, const double* __restrict__ flux, double* __restrict__ u) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) u[i] = log10(flux[i] / VRES_F0);
+}
+
+// rows + integer counts for one set of edges (exact comparisons against the caller's edges, VmaxLumFunc.py:346-348)
+__global__ void __launch_bounds__(256) k_veff_rows(long long n, const double* __restrict__ lum, const double* __restrict__ edges,
+                                                   int nbins, short* __restrict__ row, unsigned long long* __restrict__ counts) {
+    extern __shared__ unsigned char smem_raw[];
+    double* s_edges = reinterpret_cast<double*>(smem_raw);
+    unsigned* s_cnt = reinterpret_cast<unsigned*>(s_edges + nbins + 1);
+    for (int i = threadIdx.x; i <= nbins; i += blockDim.x) s_edges[i] = edges[i];
+    for (int i = threadIdx.x; i < nbins; i += blockDim.x) s_cnt[i] = 0u;
+    __syncthreads();
+    const double e0 = s_edges[0], enb = s_edges[nbins];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double L = lum[i];
+        int r = L < e0 ? 0 : nbins + 1;                                   // below / above (or NaN): no bin
+        const int j = bin_of(L, s_edges, nbins);
+        if (j >= 0) { r = j + 1; atomicAdd(&s_cnt[j], 1u); }
+        else if (!(L >= enb)) r = 0;
+        row[i] = (short)r;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < nbins; j += blockDim.x)
+        if (s_cnt[j]) atomicAdd(&counts[j], (unsigned long long)s_cnt[j]);
+}
+
+struct VresArgs {
+    long long n;
+    const double* flux; const double* u; const short* row; const double* vol; const unsigned char* valid;
+    double* phi;
+    int K; long long field_ind[LF_MAX_FIELDS + 1];
+    double nconst[LF_MAX_FIELDS], inv_ftau[LF_MAX_FIELDS], F50[LF_MAX_FIELDS], ftau[LF_MAX_FIELDS];
+    double alpha, pref, inv_pref_vol; int modified, nbins;
+    const Tables* tables;
+    double* sumphi;                      // [gridDim.x][nbins] block partials
+    double* out_s;                       // [nbins] final sums, written by the last block to finish
+    unsigned* ticket;
+};
+
+// 1 / fleming for n = alpha log10(f / F50) already formed; otherwise the arithmetic of inv_fleming_stream
+template <bool MODIFIED>
+__device__ __forceinline__ double inv_fleming_from_n(double num, double f, double inv_ftau, const double* s_exp,
+                                                     const double2* s_logm, bool& bad) {
+    const double y = fma(num, num, 1.0);
+    const double r0 = rsqrt_seed(y);
+    const double e = fma(-(y * r0), r0, 1.0);
+    const double pe = fma(0.375, e, 0.5) * e;
+    const double nr = num * r0;
+    const double fc = fma(0.5, fma(nr, pe, nr), 0.5);
+    int lowest = __double2hiint(fc);                                        // fc > 1e-6
+    double t = log_stream(fc, s_logm);                                      // ln fc <= 0
+    if (MODIFIED) {
+        const double x = f * inv_ftau;
+        const int hx = __double2hiint(x);
+        lowest = min(lowest, hx);                                           // x > 1e-6
+        const double xm = hx < 0x40859000 ? x : 690.0;                      // beyond 690 the decay factor is 1 anyway
+        t *= rcp_stream(exp_stream(-xm, s_exp) - 1.0);                      // -ln(fc) / (1 - e^-x) >= 0
+    } else {
+        t = -t;
+    }
+    const bool ok = (lowest > 0x3eb0c6f7) & ((unsigned)__double2hiint(t) < 0x40859000u);   // and 0 <= t < 690
+    bad = !ok;
+    return exp_stream(ok ? t : 0.0, s_exp);
+}
+
+#define VR_WARPS 8
+#define VR_UNROLL 4
+template <bool MODIFIED, bool PERSRC>
+__global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
+    constexpr int U = VR_UNROLL;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int nb = a.nbins, nrow = nb + 2;
+    double2* s_logm = reinterpret_cast<double2*>(smem_raw);
+    double* s_exp = reinterpret_cast<double*>(s_logm + STREAM_LOG_N);
+    double* s_sum = s_exp + EXP_TAB_N;                                      // [VR_WARPS][nrow][VP_COLS]
+    __shared__ int s_fb[LF_MAX_FIELDS + 1];
+    __shared__ double s_fk[LF_MAX_FIELDS][4];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < VR_WARPS * nrow * VP_COLS; i += blockDim.x) s_sum[i] = 0.0;
+    load_stream_tables(a.tables, s_exp, s_logm);
+    constexpr int STRIDE = 32 * VR_WARPS, TRIP = STRIDE * U;
+    const long long per_block = ((a.n + gridDim.x - 1) / gridDim.x + TRIP - 1) / TRIP * TRIP;
+    const long long start = (long long)blockIdx.x * per_block;
+    const int len = (int)(a.n - start < per_block ? (a.n - start > 0 ? a.n - start : 0) : per_block);
+    if (threadIdx.x < a.K) {
+        const long long b = a.field_ind[threadIdx.x + 1] - start;
+        s_fb[threadIdx.x] = threadIdx.x == a.K - 1 ? 0x7fffffff : (int)(b < 0 ? 0 : (b > len ? len : b));
+        s_fk[threadIdx.x][0] = a.nconst[threadIdx.x]; s_fk[threadIdx.x][1] = a.inv_ftau[threadIdx.x];
+        s_fk[threadIdx.x][2] = a.F50[threadIdx.x]; s_fk[threadIdx.x][3] = a.ftau[threadIdx.x];
+    }
+    __syncthreads();
+    int sum_off = warp * nrow * VP_COLS + (lane & (VP_COLS - 1));
+    asm volatile("" : "+r"(sum_off));
+    double* my_sum = s_sum + sum_off;
+    const int turn = lane >> 4;
+    const double* __restrict__ p_flux = a.flux + start;
+    const double* __restrict__ p_u = a.u + start;
+    const short* __restrict__ p_row = a.row + start;
+    const double* __restrict__ p_vol = PERSRC ? a.vol + start : nullptr;
+    const unsigned char* __restrict__ p_valid = PERSRC ? a.valid + start : nullptr;
+    double* __restrict__ p_phi = a.phi + start;
+    const double alpha = a.alpha;
+    int kU = 0;
+    for (int t0 = 0; t0 < len; t0 += TRIP) {
+        double phi[U], f[U], uu[U];
+        int row[U];
+        const int base = t0 + threadIdx.x;
+        while (t0 >= s_fb[kU]) ++kU;                                        // block-uniform; s_fb[K - 1] = INT_MAX
+        const bool whole = t0 + TRIP <= len && t0 + TRIP <= s_fb[kU];      // complete trip inside one field
+        if (whole) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                f[u] = __ldcs(p_flux + base + u * STRIDE);
+                uu[u] = __ldcs(p_u + base + u * STRIDE);
+                row[u] = (int)__ldcs(p_row + base + u * STRIDE);
+            }
+            const double nc = s_fk[kU][0], iftau = s_fk[kU][1];
+            unsigned badmask = 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                bool bad;
+                phi[u] = inv_fleming_from_n<MODIFIED>(fma(alpha, uu[u], nc), f[u], iftau, s_exp, s_logm, bad);
+                badmask |= bad ? 1u << u : 0u;
+            }
+            if (badmask) {                                                   // rare: outside the fast range
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (badmask >> u & 1u) phi[u] = inv_fleming_literal(f[u], s_fk[kU][2], alpha, s_fk[kU][3], MODIFIED);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (PERSRC) {
+                    const double vol = __ldcs(p_vol + base + u * STRIDE);
+                    const bool ok = p_valid[base + u * STRIDE] != 0;
+                    phi[u] = ok ? phi[u] * (1.0 / (a.pref * vol)) : 0.0;     // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
+                } else {
+                    phi[u] *= a.inv_pref_vol;
+                }
+                __stcs(p_phi + base + u * STRIDE, phi[u]);
+            }
+        } else {
+            // partial trip or a field boundary inside: per-source bounds and field
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int off = base + u * STRIDE;
+                const bool in = off < len;
+                const double fl = in ? __ldcs(p_flux + off) : 1.0;
+                const double ul = in ? __ldcs(p_u + off) : 0.0;
+                row[u] = in ? (int)__ldcs(p_row + off) : 0;
+                int k = kU;
+                while (off >= s_fb[k]) ++k;
+                bool bad;
+                double icomp = inv_fleming_from_n<MODIFIED>(fma(alpha, ul, s_fk[k][0]), fl, s_fk[k][1], s_exp, s_logm, bad);
+                if (bad) icomp = inv_fleming_literal(fl, s_fk[k][2], alpha, s_fk[k][3], MODIFIED);
+                double ipv = a.inv_pref_vol;
+                bool ok = in;
+                if (PERSRC && in) { ipv = 1.0 / (a.pref * __ldcs(p_vol + off)); ok = p_valid[off] != 0; }
+                phi[u] = ok ? icomp * ipv : 0.0;
+                if (in) __stcs(p_phi + off, phi[u]);
+            }
+        }
+        // sums in the thread's private column, lanes l and l + 16 in two turns (plain read-modify-writes, deterministic)
+#pragma unroll
+        for (int tn = 0; tn < 2; ++tn) {
+            if (turn == tn) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) my_sum[row[u] * VP_COLS] += phi[u];
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    for (int jb = warp; jb < nb; jb += VR_WARPS) {
+        double s = 0.0;
+        for (int wv = lane >> 4; wv < VR_WARPS; wv += 2) s += s_sum[(wv * nrow + jb + 1) * VP_COLS + (lane & (VP_COLS - 1))];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) a.sumphi[(long long)blockIdx.x * nb + jb] = s;
+    }
+    // the last block to arrive adds the block partials in block order (one warp per bin, fixed shuffle tree): the result
+    // does not depend on which block that is, and no second launch is needed
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    for (int jb = warp; jb < nb; jb += VR_WARPS) {
+        double s = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&a.sumphi[(long long)b * nb + jb]);
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) a.out_s[jb] = s;
+    }
+    if (threadIdx.x == 0) *a.ticket = 0u;
+}
+
 // one warp per bin: lanes stride over the block partials, fixed shuffle tree (deterministic)
 __global__ void k_veff_reduce(int nblocks, int nbins, const unsigned long long* __restrict__ counts,
                               const double* __restrict__ sumphi, long long* __restrict__ out_c, double* __restrict__ out_s) {
@@ -414,6 +625,7 @@ static void veff_launch(const VeffPlan& p, const VeffArgs& a, cudaStream_t st) {
 static int veff_alloc_sample(lf_ctx* c, long long n) {
     if (c->vN == n && c->v_lum && c->v_phi && c->v_bin) return 0;
     dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_bin); dfree(c->v_mult); dfree(c->v_flux); dfree(c->v_vol); dfree(c->v_valid);
+    dfree(c->v_u); c->v_rows_valid = false;
     c->v_have_sample = false; c->v_have_volumes = false; c->vN = 0;
     const size_t nb = sizeof(double) * (size_t)n;
     CK(cudaMalloc(&c->v_lum, nb));
@@ -423,17 +635,26 @@ static int veff_alloc_sample(lf_ctx* c, long long n) {
     return 0;
 }
 
-// per-histogram buffers: edges, block partials, results; (re)allocated only when the launch plan changes
-static int veff_alloc_bins(lf_ctx* c, const VeffPlan& plan, int nbins, const double* edges) {
-    if (c->v_nbins != nbins || c->v_blocks != plan.blocks || !c->v_edges) {
-        dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums); dfree(c->v_outc); dfree(c->v_outs);
+// per-histogram buffers: edges, block partials, results; (re)allocated only when the histogram or the grid size changes
+static int veff_alloc_partials(lf_ctx* c, int blocks, int nbins) {
+    if (c->v_nbins != nbins || !c->v_edges) {
+        dfree(c->v_edges); dfree(c->v_outc); dfree(c->v_outs);
         CK(cudaMalloc(&c->v_edges, sizeof(double) * (nbins + 1)));
-        CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)plan.blocks * nbins));
-        CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)plan.blocks * nbins));
         CK(cudaMalloc(&c->v_outc, sizeof(long long) * nbins));
         CK(cudaMalloc(&c->v_outs, sizeof(double) * nbins));
-        c->v_nbins = nbins; c->v_blocks = plan.blocks;
+        c->v_rows_valid = false;
     }
+    if (c->v_nbins != nbins || c->v_blocks != blocks || !c->v_counts) {
+        CK(cudaStreamSynchronize(c->stream));
+        dfree(c->v_counts); dfree(c->v_sums);
+        CK(cudaMalloc(&c->v_counts, sizeof(unsigned long long) * (size_t)blocks * nbins));
+        CK(cudaMalloc(&c->v_sums, sizeof(double) * (size_t)blocks * nbins));
+    }
+    c->v_nbins = nbins; c->v_blocks = blocks;
+    return 0;
+}
+static int veff_alloc_bins(lf_ctx* c, const VeffPlan& plan, int nbins, const double* edges) {
+    if (veff_alloc_partials(c, plan.blocks, nbins)) return 1;
     CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
     return 0;
 }
@@ -447,10 +668,86 @@ static int veff_check_common(const char* who, const double* flim, const double* 
 }
 
 // the weights + binning pass over device arrays (lum / phi / bin resident in the context), results to host buffers
+static size_t vres_smem(int nbins) {
+    return sizeof(double2) * STREAM_LOG_N + sizeof(double) * EXP_TAB_N + sizeof(double) * (size_t)VR_WARPS * (nbins + 2) * VP_COLS;
+}
+
+// resident route: rows + counts cached per edge set, weights pass on (u, f, row) with the block partials reduced in-kernel
+static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned char* d_valid, const double* flim, double alpha,
+                              double fcmin, double sum_omega, double vol_int, const double* edges, int nbins, double* phi_out,
+                              int64_t* counts, double* sumphi) {
+    const long long n = c->vN;
+    const int K = c->v_K;
+    // (re)bin only when the edges changed
+    bool same_edges = c->v_rows_valid && (int)c->v_edges_host.size() == nbins + 1 &&
+                      memcmp(c->v_edges_host.data(), edges, sizeof(double) * (nbins + 1)) == 0;
+    const int blocks = (int)std::max<long long>(1, std::min<long long>((long long)c->sm_count * 3, (n + 32 * VR_WARPS * VR_UNROLL - 1) / (32 * VR_WARPS * VR_UNROLL)));
+    const bool same_nbins = c->v_nbins == nbins;
+    if (veff_alloc_partials(c, blocks, nbins)) return 1;
+    same_edges = same_edges && same_nbins && c->v_rows_valid;
+    if (!c->v_ticket) { CK(cudaMalloc(&c->v_ticket, sizeof(unsigned))); CK(cudaMemsetAsync(c->v_ticket, 0, sizeof(unsigned), c->stream)); }
+    if (!c->v_rowcounts || c->v_rowcounts_n < nbins) {
+        dfree(c->v_rowcounts);
+        CK(cudaMalloc(&c->v_rowcounts, sizeof(unsigned long long) * nbins));
+        c->v_rowcounts_n = nbins;
+        c->v_rows_valid = false;
+    }
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (!same_edges || !c->v_rows_valid) {
+        CK(cudaMemcpyAsync(c->v_edges, edges, sizeof(double) * (nbins + 1), cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemsetAsync(c->v_rowcounts, 0, sizeof(unsigned long long) * nbins, c->stream));
+        const int rb = (int)std::min<long long>((long long)c->sm_count * 8, (n + 255) / 256);
+        k_veff_rows<<<rb, 256, sizeof(double) * (nbins + 1) + sizeof(unsigned) * nbins, c->stream>>>(n, c->v_lum, c->v_edges, nbins,
+                                                                                                   c->v_bin, c->v_rowcounts);
+        c->launches += 1;
+        c->v_edges_host.assign(edges, edges + nbins + 1);
+        c->v_rows_valid = true;
+    }
+    VresArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = n; a.flux = c->v_flux; a.u = c->v_u; a.row = c->v_bin; a.vol = d_vol; a.valid = d_valid; a.phi = c->v_phi;
+    a.K = K;
+    for (int k = 0; k <= K; ++k) a.field_ind[k] = c->v_field_ind[k];
+    const bool modified = fcmin != 0.0;
+    const double aa = (2.0 * fcmin - 1.0) * (2.0 * fcmin - 1.0);
+    for (int k = 0; k < K; ++k) {
+        a.F50[k] = 1.0e-17 * flim[k];
+        const double b = -1.0 * pow(fabs(aa / (1.0 - aa)) * pow(alpha, -2.0), 0.5);        // inverse_fleming (VmaxLumFunc.py:164-167)
+        a.ftau[k] = a.F50[k] * pow(10.0, b);
+        a.inv_ftau[k] = 1.0 / a.ftau[k];
+        a.nconst[k] = (double)(-(long double)alpha * log10l((long double)a.F50[k] / (long double)VRES_F0));
+    }
+    a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.modified = modified ? 1 : 0;
+    a.inv_pref_vol = 1.0 / (a.pref * vol_int); a.tables = c->d_tables; a.nbins = nbins;
+    a.sumphi = c->v_sums; a.out_s = c->v_outs; a.ticket = c->v_ticket;
+    const size_t smem = vres_smem(nbins);
+    const bool persrc = d_vol != nullptr;
+    if (modified) {
+        if (persrc) k_veff_res<true, true><<<blocks, 32 * VR_WARPS, smem, c->stream>>>(a);
+        else k_veff_res<true, false><<<blocks, 32 * VR_WARPS, smem, c->stream>>>(a);
+    } else {
+        if (persrc) k_veff_res<false, true><<<blocks, 32 * VR_WARPS, smem, c->stream>>>(a);
+        else k_veff_res<false, false><<<blocks, 32 * VR_WARPS, smem, c->stream>>>(a);
+    }
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 1;
+    CK(cudaGetLastError());
+    static_assert(sizeof(unsigned long long) == sizeof(int64_t), "count width");
+    CK(cudaMemcpyAsync(counts, c->v_rowcounts, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    if (phi_out) CK(cudaMemcpyAsync(phi_out, c->v_phi, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    { float ms = 0.f; CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1)); c->last_ms = ms; }
+    return 0;
+}
+
 static int veff_weights_pass(lf_ctx* c, long long n, const double* d_flux, const double* d_vol, const unsigned char* d_valid,
                              const long long* field_ind, int nfields, const double* flim, double alpha, double fcmin,
                              double sum_omega, double vol_int, const double* edges, int nbins, double* phi_out,
                              int64_t* counts, double* sumphi) {
+    if (d_flux == c->v_flux && c->v_have_sample && c->v_u && vres_smem(nbins) <= 72 * 1024 && (d_vol == nullptr) == (d_valid == nullptr))
+        return veff_resident_pass(c, d_vol, d_valid, flim, alpha, fcmin, sum_omega, vol_int, edges, nbins, phi_out, counts, sumphi);
+    c->v_rows_valid = false;                       // the general kernel rewrites the rows for ITS edges
     const VeffPlan plan = veff_plan(c, n, nbins);
     if (veff_alloc_bins(c, plan, nbins, edges)) return 1;
     const int blocks = plan.blocks;
@@ -535,7 +832,12 @@ extern "C" int lf_veff_set_sample(lf_ctx* c, int64_t n, const double* flux, cons
     if (!c->v_flux) CK(cudaMalloc(&c->v_flux, nb));
     CK(cudaMemcpyAsync(c->v_flux, flux, nb, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
+    if (!c->v_u) CK(cudaMalloc(&c->v_u, nb));
+    k_veff_prepare<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(n, c->v_flux, c->v_u);
+    c->launches += 1;
+    CK(cudaGetLastError());
     CK(cudaStreamSynchronize(c->stream));
+    c->v_rows_valid = false;
     c->v_K = nfields;
     for (int k = 0; k <= nfields; ++k) c->v_field_ind[k] = field_ind[k];
     c->v_have_sample = true; c->v_have_volumes = false;
@@ -584,6 +886,9 @@ extern "C" int lf_bin_weights(lf_ctx* c, int64_t n, const double* lum, const dou
         CK(cudaMemcpyAsync(c->v_lum, lum, nb, cudaMemcpyHostToDevice, c->stream));
         CK(cudaMemcpyAsync(c->v_phi, phi, nb, cudaMemcpyHostToDevice, c->stream));
     }
+    if (!(c->v_rows_valid && (int)c->v_edges_host.size() == nbins + 1 &&
+          memcmp(c->v_edges_host.data(), edges, sizeof(double) * (nbins + 1)) == 0))
+        c->v_rows_valid = false;                   // this pass rewrites the rows for other edges
     const VeffPlan plan = veff_plan(c, n, nbins);
     if (veff_alloc_bins(c, plan, nbins, edges)) return 1;
     const int blocks = plan.blocks;
@@ -764,8 +1069,11 @@ extern "C" int lf_boot_bin_device(lf_ctx* c, uint64_t seed, int64_t replicate, i
     memset(&a, 0, sizeof(a));
     a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
     a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult; a.bin = c->v_bin;
-    const int nbins = c->v_nbins, blocks = c->v_blocks;
+    const int nbins = c->v_nbins;
     const VeffPlan plan = veff_plan(c, c->vN, nbins);
+    if (veff_alloc_partials(c, plan.blocks, nbins)) return 1;
+    const int blocks = plan.blocks;
+    a.counts = c->v_counts; a.sumphi = c->v_sums;
     veff_launch<1>(plan, a, c->stream);
     k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -790,8 +1098,11 @@ extern "C" int lf_boot_bin(lf_ctx* c, const int32_t* mult, int64_t* counts, doub
     memset(&a, 0, sizeof(a));
     a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
     a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult; a.bin = c->v_bin;
-    const int nbins = c->v_nbins, blocks = c->v_blocks;
+    const int nbins = c->v_nbins;
     const VeffPlan plan = veff_plan(c, c->vN, nbins);
+    if (veff_alloc_partials(c, plan.blocks, nbins)) return 1;
+    const int blocks = plan.blocks;
+    a.counts = c->v_counts; a.sumphi = c->v_sums;
     CK(cudaEventRecord(c->ev0, c->stream));
     veff_launch<1>(plan, a, c->stream);
     k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
@@ -813,6 +1124,10 @@ int veff_init(lf_ctx* c) {
         CK(cudaFuncSetAttribute(k_veff<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, atom_smem));
         CK(cudaFuncSetAttribute(k_veff<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, atom_smem));
     }
+    CK(cudaFuncSetAttribute(k_veff_res<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CK(cudaFuncSetAttribute(k_veff_res<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CK(cudaFuncSetAttribute(k_veff_res<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CK(cudaFuncSetAttribute(k_veff_res<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CK(cudaFuncSetAttribute(k_veff_priv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
     CK(cudaFuncSetAttribute(k_veff_priv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
     CK(cudaFuncSetAttribute(k_veff_priv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));

@@ -135,15 +135,33 @@ def test_resident_sample_equals_host_buffer_path_and_weights_are_fetched_lazily(
     for flim, alpha in ((cat['Flim'], cat['alpha']), ([2.0, 3.0, 2.5, 4.0], 4.2), (cat['Flim'], cat['alpha'])):
         none, cnt_b, sum_b = b.veff_bin_resident(flim, alpha, cat['fcmin'], so, 3.0e10, edges)   # repeated calls, same sample
         assert none is None
-    assert np.array_equal(cnt_a, cnt_b) and np.array_equal(sum_a, sum_b)
-    assert np.array_equal(b.veff_phi(), phi_a)                                    # bit-identical weights, fetched on demand
+    assert np.array_equal(cnt_a, cnt_b)
+    np.testing.assert_allclose(sum_b, sum_a, rtol=1e-12)
+    # the resident route forms n = alpha (u - log10(F50 / F0)) from the stored u = log10(f / F0) instead of taking the
+    # logarithm of f / F50 on every call: same weights to the rounding of that logarithm
+    np.testing.assert_allclose(b.veff_phi(), phi_a, rtol=1e-13)
+    flims_arr = np.repeat(np.asarray(cat['Flim'], dtype=np.float64), np.diff(fi))
+    ref = lf_oracle.veff_weights(flux, flims_arr, cat['alpha'], cat['fcmin'], so, 3.0e10, 0.0)
+    np.testing.assert_allclose(b.veff_phi(), ref, rtol=1e-13)
     cnt_c, sum_c = b.bin_weights(None, None, edges)                               # re-binning the resident weights
     assert np.array_equal(cnt_c, cnt_a)
     np.testing.assert_allclose(sum_c, sum_a, rtol=1e-13)
     mult = np.bincount(np.random.RandomState(3).randint(n, size=n), minlength=n)
     ca, sa = a.boot_bin(mult)
     cb, sb = b.boot_bin(mult)
-    assert np.array_equal(ca, cb) and np.array_equal(sa, sb)
+    assert np.array_equal(ca, cb)
+    np.testing.assert_allclose(sb, sa, rtol=1e-12)
+    # other edges, other number of bins: the cached rows and counts are rebuilt
+    edges2 = np.linspace(lum.min() * 1.001, lum.max(), 26)
+    _, cnt2, sum2 = b.veff_bin_resident(cat['Flim'], cat['alpha'], cat['fcmin'], so, 3.0e10, edges2)
+    idx = np.searchsorted(edges2, lum, side='right') - 1
+    keep = (idx >= 0) & (idx < 25)
+    assert np.array_equal(cnt2, np.bincount(idx[keep], minlength=25)[:25])
+    np.testing.assert_allclose(sum2, np.bincount(idx[keep], weights=ref[keep], minlength=25)[:25], rtol=1e-12)
+    _, cnt3, sum3 = b.veff_bin_resident(cat['Flim'], cat['alpha'], 0.0, so, 3.0e10, edges2)        # plain Fleming curve
+    ref3 = lf_oracle.veff_weights(flux, flims_arr, cat['alpha'], 0.0, so, 3.0e10, 0.0)
+    np.testing.assert_allclose(b.veff_phi(), ref3, rtol=1e-13)
+    assert np.array_equal(cnt3, cnt2)
     a.close()
     b.close()
 
