@@ -181,6 +181,16 @@ int lf_boot_bin(lf_ctx* ctx, const int32_t* mult, int64_t* counts, double* sumph
  * multiplicities for that).  Integer counts do not depend on the order of the atomics, so a replicate is reproducible. */
 int lf_boot_bin_device(lf_ctx* ctx, uint64_t seed, int64_t replicate, int64_t* counts, double* sumphi);
 
+/* The reference's resampling stream itself, generated on the device: VmaxLumFunc.py:353 draws np.random.randint(n, size=n)
+ * from NumPy's legacy global MT19937 generator (per sample: 32-bit outputs masked with the smallest 2^k - 1 >= n - 1 until one
+ * is <= n - 1).  lf_boot_mt_set_state takes that generator's state (np.random.get_state(): key[624], pos), lf_boot_bin_mt
+ * performs ONE replicate -- n accepted draws -> multiplicities -> binning, all on the device -- and leaves the state where
+ * NumPy's would be; lf_boot_mt_get_state returns it so the host generator can be re-synchronised (np.random.set_state).
+ * Replicates are bit-identical to lf_boot_bin with host-drawn multiplicities, without n host draws per replicate. */
+int lf_boot_mt_set_state(lf_ctx* ctx, const uint32_t* key, int32_t pos);
+int lf_boot_mt_get_state(lf_ctx* ctx, uint32_t* key_out, int32_t* pos_out);
+int lf_boot_bin_mt(lf_ctx* ctx, int64_t* counts, double* sumphi);
+
 /* Register-only FP64 FMA micro-benchmark on the context's device: sustained DFMA thread-instructions / s. */
 int lf_fp64_peak(lf_ctx* ctx, int32_t iters, double* dfma_per_s, double* ms);
 
@@ -226,6 +236,14 @@ int lf_cosmo_distances(int32_t device, const lf_cosmology* cosmo, const double* 
  * scipy.interpolate.interp1d(kind='linear') evaluates (lumfuncmcmc.py:196-197).  x outside [xk[0], xk[nk-1]] is an
  * error (interp1d raises). */
 int lf_interp_linear(int32_t device, int64_t nk, const double* xk, const double* yk, int64_t n, const double* x, double* y);
+
+/* Per-source tabulated Omega, the array lumfuncmcmc.py:235 builds with Omega(lum, z, DLf, Omega_0_arr, 1e-17 Flims_arr, alpha,
+ * fcmin) (lumfuncmcmc.py:47-70 -> V.fleming): om_out[i] = omega0_int[k] / sqarcsec * fleming(10^lum_i / (4 pi (3.086e24 DLf(z_i))^2);
+ * 1e-17 flim[k], alpha, fcmin), k = field of source i, DLf = numpy.interp through the knots (zk, DLk).  Reference order of
+ * operations with libdevice pow / log10 / exp / sqrt: within ~1e-15 of NumPy's values (not bit-identical). */
+int lf_omega_sources(int32_t device, int64_t n, const double* lum, const double* z, const int64_t* field_ind,
+                     int32_t nfields, const int64_t* omega0_int, const double* flim, double alpha, double fcmin,
+                     int64_t nk, const double* zk, const double* DLk, double* om_out);
 
 /* Device-resident affine-invariant ensemble sampler: replaces emcee.EnsembleSampler(...).run_mcmc(pos, nsteps)
  * (lumfuncmcmc.py:489-491, lumfuncmcmc_z.py:444-446) for a context on one GPU.  Goodman & Weare stretch move with

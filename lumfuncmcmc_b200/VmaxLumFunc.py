@@ -97,7 +97,7 @@ def veff_weights_gpu(flux, lum, field_ind, Flim, alpha, fcmin, sum_omega, vol_in
 
 
 def getBootErrLog(L, phi, minz, maxz, nboot=100, nbin=25, Fmin=1.0e-20, Larr=None, correct_low=False, device=0,
-                  engine=None, return_counts=False, rng='host', seed=None, Lrange=None):
+                  engine=None, return_counts=False, rng='auto', seed=None, Lrange=None):
     """Binned luminosity function dn/dlogL with bootstrap variances (reference VmaxLumFunc.py:304-364).
 
     Bin edges ``linspace(min(L)*1.001, max(L), nbin+1)`` unless ``Larr`` is given; bins are half-open
@@ -105,6 +105,12 @@ def getBootErrLog(L, phi, minz, maxz, nboot=100, nbin=25, Fmin=1.0e-20, Larr=Non
     reference does (:353), so a seeded run resamples the same sources.  The index draw happens on the host (it is
     the reference's RNG); the gather + binning of every replicate is one GPU pass over per-source multiplicities.
     ``correct_low`` (partial-bin correction, never enabled by the MCMC classes) is not supported.
+
+    ``rng='mt19937'`` draws the SAME stream on the GPU: NumPy's global MT19937 state is handed to the device
+    (``lf_boot_mt_set_state``), every replicate's indices are generated there exactly as ``np.random.randint(N, size=N)``
+    would (masked rejection sampling of 32-bit outputs), and the host generator is re-synchronised afterwards -- bit-identical
+    replicates and generator state, without N host draws and an N-element upload per replicate.  ``rng='auto'`` (default)
+    takes that route from 1e5 sources up and the host draw below; the results do not depend on the choice.
 
     ``rng='device'`` (additive option) resamples on the GPU instead: a Philox stream keyed by ``seed`` (default: one draw
     from NumPy's global stream) generates every replicate's indices and multiplicities on the device -- statistically
@@ -135,17 +141,28 @@ def getBootErrLog(L, phi, minz, maxz, nboot=100, nbin=25, Fmin=1.0e-20, Larr=Non
     lfbinorig = np.where(counts > 0, sums / dL, 0.0)
     lfbin = np.zeros((nboot, nb))
     n = len(L)
-    if rng not in ('host', 'device'):
-        raise ValueError("rng must be 'host' or 'device'")
+    if rng not in ('auto', 'host', 'mt19937', 'device'):
+        raise ValueError("rng must be 'auto', 'host', 'mt19937' or 'device'")
+    mt_ok = 2 <= n < 2 ** 32 and np.random.get_state()[0] == 'MT19937'
+    if rng == 'auto':
+        rng = 'mt19937' if (n >= 100000 and mt_ok) else 'host'
+    if rng == 'mt19937':
+        if not mt_ok:
+            raise ValueError("rng='mt19937' needs 2 <= N < 2**32 sources and NumPy's legacy MT19937 global generator")
+        eng.boot_mt_set_state(np.random.get_state())
     if rng == 'device' and seed is None:
         seed = int(np.random.randint(0, 2 ** 31 - 1)) | (int(np.random.randint(0, 2 ** 31 - 1)) << 32)
     for k in range(nboot):
         if rng == 'device':
             bc, bs = eng.boot_bin_device(seed, k)
+        elif rng == 'mt19937':
+            bc, bs = eng.boot_bin_mt()
         else:
             boot = np.random.randint(n, size=n)
             bc, bs = eng.boot_bin(np.bincount(boot, minlength=n))
         lfbin[k] = np.where(bc > 0, bs / dL, 0.0)
+    if rng == 'mt19937':
+        np.random.set_state(eng.boot_mt_get_state())       # the host generator continues where the reference's would
     binavg = np.average(lfbin, axis=0)
     var = 1. / (nboot - 1) * np.sum((lfbin - binavg) ** 2, axis=0)
     var[var <= 0.0] = min(var[var > 0.0])

@@ -542,17 +542,28 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) a.sumphi[(long long)blockIdx.x * nb + jb] = s;
     }
-    // the last block to arrive adds the block partials in block order (one warp per bin, fixed shuffle tree): the result
-    // does not depend on which block that is, and no second launch is needed
+    // the last block to arrive adds the block partials in a fixed order (lane l of the bin's warp takes blocks l, l + 32, ...,
+    // all of its loads in flight at once, then a fixed shuffle tree): the result does not depend on which block that is,
+    // and no second launch is needed
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
     __syncthreads();
     if (!s_last) return;
     __threadfence();
+    constexpr int RMAX = 16;                                                // covers grids of up to 512 blocks per pass
     for (int jb = warp; jb < nb; jb += VR_WARPS) {
         double s = 0.0;
-        for (int b = lane; b < (int)gridDim.x; b += 32) s += __ldcg(&a.sumphi[(long long)b * nb + jb]);
+        for (int b0 = 0; b0 < (int)gridDim.x; b0 += 32 * RMAX) {
+            double v[RMAX];
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) {
+                const int b = b0 + r * 32 + lane;
+                v[r] = b < (int)gridDim.x ? __ldcg(&a.sumphi[(long long)b * nb + jb]) : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < RMAX; ++r) s += v[r];
+        }
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) a.out_s[jb] = s;
     }
@@ -565,7 +576,19 @@ __global__ void k_veff_reduce(int nblocks, int nbins, const unsigned long long* 
     const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (j >= nbins) return;
     double s = 0.0; unsigned long long c = 0ULL;
-    for (int b = lane; b < nblocks; b += 32) { s += sumphi[(long long)b * nbins + j]; c += counts[(long long)b * nbins + j]; }
+    constexpr int RMAX = 8;                                                 // loads of a pass are all in flight before the adds
+    for (int b0 = 0; b0 < nblocks; b0 += 32 * RMAX) {
+        double v[RMAX]; unsigned long long w[RMAX];
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) {
+            const int b = b0 + r * 32 + lane;
+            const bool in = b < nblocks;
+            v[r] = in ? sumphi[(long long)b * nbins + j] : 0.0;
+            w[r] = in ? counts[(long long)b * nbins + j] : 0ULL;
+        }
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) { s += v[r]; c += w[r]; }
+    }
     for (int o = 16; o > 0; o >>= 1) {
         s += __shfl_xor_sync(0xffffffffu, s, o);
         c += __shfl_xor_sync(0xffffffffu, c, o);
@@ -1069,6 +1092,145 @@ extern "C" int lf_boot_bin_device(lf_ctx* c, uint64_t seed, int64_t replicate, i
     memset(&a, 0, sizeof(a));
     a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
     a.counts = c->v_counts; a.sumphi = c->v_sums; a.mult = c->v_mult; a.bin = c->v_bin;
+    const int nbins = c->v_nbins;
+    const VeffPlan plan = veff_plan(c, c->vN, nbins);
+    if (veff_alloc_partials(c, plan.blocks, nbins)) return 1;
+    const int blocks = plan.blocks;
+    a.counts = c->v_counts; a.sumphi = c->v_sums;
+    veff_launch<1>(plan, a, c->stream);
+    k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->launches += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    { float ms = 0.f; if (cudaEventElapsedTime(&ms, c->ev0, c->ev1) == cudaSuccess) c->last_ms = ms; }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bootstrap resampling with NumPy's legacy MT19937 stream generated ON the device
+// ------------------------------------------------------------------------------------------------
+// The reference resamples with np.random.randint(n, size=n) on NumPy's global RandomState (VmaxLumFunc.py:353): for
+// n - 1 < 2^32 that is, per sample, "draw 32-bit MT19937 outputs, AND them with the smallest all-ones mask >= n - 1, until
+// one is <= n - 1" (numpy/random/src/distributions/distributions.c: random_bounded_uint64_fill ->
+// buffered_bounded_masked_uint32).  One CTA reproduces exactly that stream: the 624-word state is regenerated in three
+// parallel phases (words [0, 227) depend on the old state only, [227, 454) on those, [454, 624) on the second group),
+// every thread tempers one word, accepted values increment the multiplicity of their source (integer atomics: order does
+// not matter), and the replicate ends right after its n-th accepted output -- the state and position left behind are what
+// NumPy's would be, so the host generator can be re-synchronised afterwards (lf_boot_mt_get_state).
+#define MT_N 624
+#define MT_M 397
+#define MT_THREADS 640
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b) {
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+__global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g_state, int* __restrict__ g_pos, long long n,
+                                                       uint32_t rng, uint32_t mask, int* __restrict__ mult) {
+    __shared__ uint32_t mt[2][MT_N];
+    __shared__ int s_warp_cnt[MT_THREADS / 32];
+    __shared__ int s_newpos;
+    const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
+    int cur = 0;
+    if (j < MT_N) mt[0][j] = g_state[j];
+    int pos = *g_pos;                                   // next unused output of the current state block (624: none left)
+    long long acc = 0;                                  // samples accepted so far
+    __syncthreads();
+    for (;;) {
+        if (pos >= MT_N) {                              // regenerate the state block (block-uniform)
+            const uint32_t* o = mt[cur];
+            uint32_t* w = mt[cur ^ 1];
+            if (j < MT_N - MT_M) w[j] = o[j + MT_M] ^ mt_twist(o[j], o[j + 1]);
+            __syncthreads();
+            if (j >= MT_N - MT_M && j < 2 * (MT_N - MT_M)) w[j] = w[j - (MT_N - MT_M)] ^ mt_twist(o[j], o[j + 1]);
+            __syncthreads();
+            if (j >= 2 * (MT_N - MT_M) && j < MT_N - 1) w[j] = w[j - (MT_N - MT_M)] ^ mt_twist(o[j], o[j + 1]);
+            if (j == MT_N - 1) w[j] = w[MT_M - 1] ^ mt_twist(o[j], w[0]);
+            __syncthreads();
+            cur ^= 1;
+            pos = 0;
+        }
+        // outputs pos .. 623 of this block, one per thread, in stream order
+        bool ok = false;
+        uint32_t v = 0u;
+        if (j >= pos && j < MT_N) {
+            v = mt_temper(mt[cur][j]) & mask;
+            ok = v <= rng;
+        }
+        const int cnt = __syncthreads_count(ok);
+        if (acc + cnt < n) {                            // the replicate needs all of them (and more)
+            if (ok) atomicAdd(&mult[v], 1);
+            acc += cnt;
+            pos = MT_N;
+            continue;
+        }
+        // the n-th accepted output lies in this block: rank the accepted outputs in stream order
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int before = __popc(bal & ((1u << lane) - 1u));
+        for (int wv = 0; wv < warp; ++wv) before += s_warp_cnt[wv];
+        const long long my_index = acc + before;        // 0-based index of this thread's sample, if accepted
+        if (ok && my_index < n) atomicAdd(&mult[v], 1);
+        if (ok && my_index == n - 1) s_newpos = j + 1;  // everything after it belongs to whoever draws next
+        __syncthreads();
+        pos = s_newpos;
+        break;
+    }
+    if (j < MT_N) g_state[j] = mt[cur][j];
+    if (j == 0) *g_pos = pos;
+}
+
+extern "C" int lf_boot_mt_set_state(lf_ctx* c, const uint32_t* key, int32_t pos) {
+    if (!c || !key) return fail("lf_boot_mt_set_state: null argument");
+    if (pos < 0 || pos > MT_N) return fail("lf_boot_mt_set_state: pos must be in [0, 624]");
+    CK(cudaSetDevice(c->device));
+    if (!c->v_mt_state) CK(cudaMalloc(&c->v_mt_state, sizeof(uint32_t) * MT_N + sizeof(int)));
+    CK(cudaMemcpyAsync(c->v_mt_state, key, sizeof(uint32_t) * MT_N, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->v_mt_state + MT_N, &pos, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lf_boot_mt_get_state(lf_ctx* c, uint32_t* key_out, int32_t* pos_out) {
+    if (!c || !key_out || !pos_out) return fail("lf_boot_mt_get_state: null argument");
+    if (!c->v_mt_state) return fail("lf_boot_mt_get_state: call lf_boot_mt_set_state first");
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(key_out, c->v_mt_state, sizeof(uint32_t) * MT_N, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(pos_out, c->v_mt_state + MT_N, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int lf_boot_bin_mt(lf_ctx* c, int64_t* counts, double* sumphi) {
+    if (!c) return fail("lf_boot_bin_mt: null context");
+    if (!c->v_phi || c->vN <= 0) return fail("lf_boot_bin_mt: call lf_veff_bin or lf_bin_weights first");
+    if (!c->v_mt_state) return fail("lf_boot_bin_mt: call lf_boot_mt_set_state first");
+    if (!counts || !sumphi) return fail("lf_boot_bin_mt: bad arguments");
+    if (c->vN < 2 || c->vN > (1LL << 32) - 1) return fail("lf_boot_bin_mt: needs 2 <= n < 2^32 sources");
+    CK(cudaSetDevice(c->device));
+    if (scratch_acquire(c, c->stream)) return 1;
+    if (!c->v_mult) CK(cudaMalloc(&c->v_mult, sizeof(int) * (size_t)c->vN));
+    const uint32_t rng = (uint32_t)(c->vN - 1);
+    uint32_t mask = rng;                                // gen_mask: smallest 2^k - 1 >= rng
+    mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    CK(cudaEventRecord(c->ev0, c->stream));
+    CK(cudaMemsetAsync(c->v_mult, 0, sizeof(int) * (size_t)c->vN, c->stream));
+    k_mt_draw<<<1, MT_THREADS, 0, c->stream>>>(c->v_mt_state, reinterpret_cast<int*>(c->v_mt_state + MT_N), c->vN, rng, mask, c->v_mult);
+    VeffArgs a;
+    memset(&a, 0, sizeof(a));
+    a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
+    a.mult = c->v_mult; a.bin = c->v_bin;
     const int nbins = c->v_nbins;
     const VeffPlan plan = veff_plan(c, c->vN, nbins);
     if (veff_alloc_partials(c, plan.blocks, nbins)) return 1;

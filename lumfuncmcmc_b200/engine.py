@@ -124,6 +124,28 @@ class _VeffOps:
         _lib.check(self.lib.lf_boot_bin(self._ctx, _ptr(mult), _ptr(counts), _ptr(sums)), self.lib)
         return counts, sums
 
+    def boot_mt_set_state(self, state):
+        """Hand NumPy's legacy generator state (``np.random.get_state()``) to the device MT19937 stream."""
+        if state[0] != 'MT19937':
+            raise ValueError("the device stream reproduces NumPy's legacy MT19937 generator only")
+        key = np.ascontiguousarray(state[1], dtype=np.uint32)
+        _lib.check(self.lib.lf_boot_mt_set_state(self._ctx, _ptr(key), int(state[2])), self.lib)
+        self._mt_tail = tuple(state[3:])
+
+    def boot_mt_get_state(self):
+        """The generator state after the replicates drawn on the device, in ``np.random.set_state`` form."""
+        key = np.empty(624, dtype=np.uint32)
+        pos = C.c_int32()
+        _lib.check(self.lib.lf_boot_mt_get_state(self._ctx, _ptr(key), C.byref(pos)), self.lib)
+        return ('MT19937', key, int(pos.value)) + self._mt_tail
+
+    def boot_bin_mt(self):
+        """One bootstrap replicate whose indices are NumPy's ``np.random.randint(n, size=n)`` stream, drawn on the device."""
+        nb = self._nbins_resident()
+        counts, sums = np.zeros(nb, dtype=np.int64), np.zeros(nb, dtype=np.float64)
+        _lib.check(self.lib.lf_boot_bin_mt(self._ctx, _ptr(counts), _ptr(sums)), self.lib)
+        return counts, sums
+
     def boot_bin_device(self, seed, replicate):
         """One bootstrap replicate resampled ON the device (Philox stream keyed by ``seed``; counter = draw, replicate)."""
         nb = self._nbins_resident()

@@ -42,7 +42,7 @@ class LFBase:
     # ------------------------------------------------------------------ set-up tables
     def _concat_inputs(self, z, flux, flux_e, lum, lum_e):
         self.z = np.concatenate(z)
-        self.zmin, self.zmax = min(self.z), max(self.z)
+        self.zmin, self.zmax = np.min(self.z), np.max(self.z)          # = min(self.z), max(self.z) without the Python-level loop
         self._flux_in, self._flux_e_in, self._lum_in, self._lum_e_in = flux, flux_e, lum, lum_e
 
     def defineFlimOmArr(self):
@@ -139,8 +139,17 @@ class LFBase:
                 self.logLi[:, i] = np.linspace(lo[i], self.Lh, S)
             self.integ_part.append(self.volume_part * self.Omegaf[k].ev(self.logLi, self.zarr_rep))
         self.logL = [self.logLi] * self.nfields
-        self.Om_arr = Omega(self.lum, self.z, self.DLf, self.Omega_0_arr, 1.0e-17 * self.Flims_arr, self.alpha,
-                            self.fcmin)
+        if len(self.lum) >= GPU_MIN_POINTS and gpu_count() > 0:
+            # the O(N) pass of the set-up chain on the GPU: same formula and order of operations, libdevice transcendentals
+            # (within ~1e-15 of NumPy's; the engine input either way)
+            from .setup_gpu import omega_sources
+            om0_field = [int(self.Omega_0_arr[self.field_ind[k]]) if self.field_ind[k + 1] > self.field_ind[k] else 0
+                         for k in range(self.nfields)]
+            self.Om_arr = omega_sources(self.lum, self.z, self.field_ind, om0_field, self.Flim, self.alpha, self.fcmin, self.DLf,
+                                        device=getattr(self, 'device', 0))
+        else:
+            self.Om_arr = Omega(self.lum, self.z, self.DLf, self.Omega_0_arr, 1.0e-17 * self.Flims_arr, self.alpha,
+                                self.fcmin)
 
     def setup_logging(self):
         self.log = logging.getLogger(self.logger_name)
@@ -312,7 +321,7 @@ class LFBase:
         self._phifunc, self._phi_engine, self._phi_gen = None, eng, eng._phi_gen
         self.Lavg, self.lfbinorig, self.var, self.bincounts = V.getBootErrLog(
             self.lum, None, self.zmin, self.zmax, self.nboot, self.nbins, Fmin=1.0e-17 * np.max(self.Flim),
-            engine=eng, return_counts=True, rng=getattr(self, 'boot_rng', None) or os.environ.get('LF_BOOT_RNG', 'host'),
+            engine=eng, return_counts=True, rng=getattr(self, 'boot_rng', None) or os.environ.get('LF_BOOT_RNG', 'auto'),
             Lrange=(lum_lo, lum_hi))
 
     def _veff_engine(self):

@@ -86,6 +86,25 @@ def cosmo_distances(cosmo, z, device=0, want_dl=True, want_dv=True):
     return (dl.reshape(shape) if want_dl else None), (dv.reshape(shape) if want_dv else None)
 
 
+def omega_sources(lum, z, field_ind, omega0_int, flim, alpha, fcmin, DLf, device=0):
+    """Per-source tabulated Omega on the GPU (``lf_omega_sources``): what the reference evaluates with
+    ``Omega(lum, z, DLf, Omega_0_arr, 1e-17 * Flims_arr, alpha, fcmin)`` (lumfuncmcmc.py:235)."""
+    lib = _lib.load()
+    lum, z = _f64(lum), _f64(z)
+    fi = np.ascontiguousarray(field_ind, dtype=np.int64)
+    om0 = np.ascontiguousarray(omega0_int, dtype=np.int64)
+    flim = _f64(flim)
+    out = np.empty_like(lum)
+    rc = lib.lf_omega_sources(int(device), lum.shape[0], _p(lum), _p(z), _p(fi), len(flim), _p(om0), _p(flim), float(alpha),
+                              float(fcmin) if fcmin else 0.0, DLf.x.shape[0], _p(DLf.x), _p(DLf.y), _p(out))
+    if rc:
+        msg = lib.lf_last_error().decode()
+        if 'outside the interpolation range' in msg:
+            raise ValueError("A value in x_new is outside the interpolation range.")
+        raise _lib.EngineError(msg)
+    return out
+
+
 class LinearTable:
     """Linear interpolant with ``interp1d``'s call semantics (bounds error, array in / array out) and NumPy's
     arithmetic; ``.x`` / ``.y`` are the knots."""

@@ -185,3 +185,66 @@ def test_class_veff_minimum_completeness_runs_on_the_device(golden):
     assert np.array_equal(m.bincounts, g['counts'])
     np.testing.assert_allclose(m.lfbinorig, g['lfbinorig'], rtol=1e-6)
     m.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n', [400, 65537, 1000000])
+def test_device_mt19937_bootstrap_is_numpys_stream(n):
+    """Replicates drawn on the device from NumPy's legacy MT19937 stream (reference VmaxLumFunc.py:353) are bit-identical to
+    the host-drawn ones, and the host generator ends where the reference's would."""
+    from lumfuncmcmc_b200 import VmaxLumFunc as V
+    from lumfuncmcmc_b200.engine import VeffEngine
+    rs = np.random.RandomState(n)
+    L = rs.uniform(41.0, 44.0, n)
+    phi = 10 ** rs.uniform(-6, -2, n)
+    eng = VeffEngine(device=0)
+    out, after, nxt = {}, {}, {}
+    for rng in ('host', 'mt19937'):
+        np.random.seed(20260 + n)
+        np.random.rand(int(n) % 700 + 3)                          # start somewhere inside a state block
+        out[rng] = V.getBootErrLog(L, phi, 1.2, 1.9, nboot=7, nbin=12, engine=eng, return_counts=True, rng=rng)
+        after[rng] = np.random.get_state()
+        nxt[rng] = np.random.randint(10 ** 6, size=8)
+    for a, b in zip(out['host'], out['mt19937']):
+        assert np.array_equal(a, b)
+    assert after['host'][2] == after['mt19937'][2] and np.array_equal(after['host'][1], after['mt19937'][1])
+    assert np.array_equal(nxt['host'], nxt['mt19937'])
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_golden_bootstrap_variance_with_the_device_stream(golden):
+    """veff_k3_n400: the variances the unmodified reference produced, from the stream generated on the device."""
+    from lumfuncmcmc_b200 import VmaxLumFunc as V
+    from lumfuncmcmc_b200.engine import VeffEngine
+    g = golden('veff_k3_n400')
+    eng = VeffEngine(device=0)
+    np.random.seed(int(g['seed']))
+    Lavg, lfb, var = V.getBootErrLog(g['lum'], g['phifunc'], float(g['zmin']), float(g['zmax']), nboot=int(g['nboot']),
+                                     nbin=int(g['nbins']), engine=eng, rng='mt19937')
+    np.testing.assert_array_equal(Lavg, g['Lavg'])
+    np.testing.assert_allclose(lfb, g['lfbinorig'], rtol=1e-12)
+    np.testing.assert_allclose(var, g['var'], rtol=1e-9)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_per_source_omega_on_the_device_matches_numpy():
+    from lumfuncmcmc_b200 import synth
+    from lumfuncmcmc_b200.cosmology import cosmo
+    from lumfuncmcmc_b200.lfbase import Omega
+    from lumfuncmcmc_b200.setup_gpu import LinearTable, omega_sources
+    n = 250000
+    cat = synth.make_catalogue(n, seed=9, nfields=4)
+    z = np.concatenate(cat['z'])
+    flux = 1.0e-17 * np.concatenate(cat['flux'])
+    lum = np.log10(4.0 * np.pi * (cosmo.luminosity_distance(z) * 3.086e24) ** 2 * flux)
+    fi = np.asarray(cat['field_ind'], dtype=np.int64)
+    zint = np.linspace(0.95 * z.min(), 1.05 * z.max(), 5000)
+    DLf = LinearTable(zint, cosmo.luminosity_distance(zint))
+    om0 = np.asarray(cat['Omega_0']).astype(int)
+    for fcmin in (cat['fcmin'], 0.0):
+        got = omega_sources(lum, z, fi, om0, cat['Flim'], cat['alpha'], fcmin, DLf)
+        want = Omega(lum, z, lambda zz: np.interp(zz, zint, DLf.y), np.repeat(om0, np.diff(fi)),
+                     1.0e-17 * np.repeat(np.asarray(cat['Flim'], dtype=np.float64), np.diff(fi)), cat['alpha'], fcmin)
+        np.testing.assert_allclose(got, want, rtol=2e-14)
