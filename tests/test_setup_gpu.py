@@ -51,8 +51,8 @@ def test_large_catalogue_setup_uses_the_gpu_and_equals_the_host_tables(monkeypat
                            Omega_0=list(cat['Omega_0']), Flim_lims=configLF.Flim_lims, alpha_lims=configLF.alpha_lims,
                            sch_al=configLF.sch_al, Lstar=configLF.Lstar, phistar=configLF.phistar, fcmin=cat['fcmin'],
                            min_comp_frac=0.0, field_names=cat['field_names'], field_ind=cat['field_ind'])
-    calls = {'cosmo': 0, 'interp': 0}
-    real_c, real_i = setup_gpu.cosmo_distances, setup_gpu.interp_linear
+    calls = {'cosmo': 0, 'interp': 0, 'omega': 0}
+    real_c, real_i, real_o = setup_gpu.cosmo_distances, setup_gpu.interp_linear, setup_gpu.omega_sources
 
     def count_c(*a, **k):
         calls['cosmo'] += 1
@@ -61,18 +61,26 @@ def test_large_catalogue_setup_uses_the_gpu_and_equals_the_host_tables(monkeypat
     def count_i(*a, **k):
         calls['interp'] += 1
         return real_i(*a, **k)
+    def count_o(*a, **k):
+        calls['omega'] += 1
+        return real_o(*a, **k)
     import lumfuncmcmc_b200.lfbase as lfbase
     monkeypatch.setattr(lfbase, 'cosmo_distances', count_c)
     monkeypatch.setattr(setup_gpu, 'interp_linear', count_i)
+    monkeypatch.setattr(setup_gpu, 'omega_sources', count_o)
     g = build()
-    assert calls['cosmo'] == 2 and calls['interp'] >= 1
+    # the three O(N) passes of the constructor: D_L per source, the N-knot tables, the per-source tabulated Omega (which
+    # interpolates D_L inside the kernel)
+    assert calls['cosmo'] == 2 and calls['omega'] == 1
     monkeypatch.setattr(lfbase, 'gpu_count', lambda: 0)
     monkeypatch.setattr(setup_gpu, 'gpu_count', lambda: 0)
     h = build()
     np.testing.assert_allclose(g.DLf.y, h.DLf.y, rtol=2e-15, atol=0)
     np.testing.assert_allclose(g.dVdzf.y, h.dVdzf.y, rtol=4e-15, atol=0)
     np.testing.assert_allclose(g.lum, h.lum, rtol=1e-15, atol=0)
-    np.testing.assert_allclose(g.Om_arr, h.Om_arr, rtol=1e-12, atol=0)
+    # device set-up path: same formulas and order of operations with libdevice sin / sqrt / pow / log10 / exp instead of
+    # NumPy's -- pinned here at 2e-15 (distances), 4e-15 (dV/dz), 1e-15 (lum) and 1e-13 (Omega per source)
+    np.testing.assert_allclose(g.Om_arr, h.Om_arr, rtol=1e-13, atol=0)
     th = synth.draw_thetas(g.engine_inputs(), 'free', 8, seed=3, mode='near', scale=0.02)
     a, b = g.lnprob(th), h.lnprob(th)
     assert np.max(np.abs(a - b) / np.abs(b)) < 1e-12
