@@ -1335,8 +1335,9 @@ static int ensure_scratch(lf_ctx* c, long long W, int rows) {
 // choose slab counts so that one class fills the machine with a few waves of warp items
 static void plan_rows(const lf_ctx* c, long long W, int& n_src, int& n_quad) {
     const long long n_wg = (W + 31) / 32;
-    const long long target_items = (long long)c->sm_count * 16 * 24;   // ~24-32 items per resident warp
-    long long rows = std::min<long long>(4096, std::max<long long>(1, target_items / n_wg));
+    static const int items_per_slot = []() { const char* e = getenv("LF_PLAN_ITEMS"); const int v = e ? atoi(e) : 0; return v > 0 ? v : 24; }();
+    const long long target_items = (long long)c->sm_count * 16 * items_per_slot;   // ~24-32 items per resident warp (LF_PLAN_ITEMS: tuning)
+    long long rows = std::min<long long>(items_per_slot > 24 ? 16384 : 4096, std::max<long long>(1, target_items / n_wg));
     const int model = c->cfg.model;
     // relative cost of a quadrature point vs a source term
     double src_cost = model == LF_MODEL_FREE ? 1.0 : (model == LF_MODEL_Z ? 0.5 : 0.0);

@@ -397,9 +397,7 @@ struct VresArgs {
     double nconst[LF_MAX_FIELDS], inv_ftau[LF_MAX_FIELDS], F50[LF_MAX_FIELDS], ftau[LF_MAX_FIELDS];
     double alpha, pref, inv_pref_vol; int modified, nbins;
     const Tables* tables;
-    double* sumphi;                      // [gridDim.x][nbins] block partials
-    double* out_s;                       // [nbins] final sums, written by the last block to finish
-    unsigned* ticket;
+    double* sumphi;                      // [gridDim.x][nbins] block partials (summed per bin by k_veff_sumreduce)
 };
 
 // 1 / fleming for n = alpha log10(f / F50) already formed; otherwise the arithmetic of inv_fleming_stream
@@ -433,6 +431,7 @@ __device__ __forceinline__ double inv_fleming_from_n(double num, double f, doubl
 template <bool MODIFIED, bool PERSRC>
 __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
     constexpr int U = VR_UNROLL;
+    asm volatile("griddepcontrol.launch_dependents;");                      // k_veff_sumreduce may become resident and wait
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int nb = a.nbins, nrow = nb + 2;
     double2* s_logm = reinterpret_cast<double2*>(smem_raw);
@@ -440,7 +439,6 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
     double* s_sum = s_exp + EXP_TAB_N;                                      // [VR_WARPS][nrow][VP_COLS]
     __shared__ int s_fb[LF_MAX_FIELDS + 1];
     __shared__ double s_fk[LF_MAX_FIELDS][4];
-    __shared__ bool s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int i = threadIdx.x; i < VR_WARPS * nrow * VP_COLS; i += blockDim.x) s_sum[i] = 0.0;
     load_stream_tables(a.tables, s_exp, s_logm);
@@ -542,32 +540,33 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0) a.sumphi[(long long)blockIdx.x * nb + jb] = s;
     }
-    // the last block to arrive adds the block partials in a fixed order (lane l of the bin's warp takes blocks l, l + 32, ...,
-    // all of its loads in flight at once, then a fixed shuffle tree): the result does not depend on which block that is,
-    // and no second launch is needed
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(a.ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    constexpr int RMAX = 16;                                                // covers grids of up to 512 blocks per pass
-    for (int jb = warp; jb < nb; jb += VR_WARPS) {
-        double s = 0.0;
-        for (int b0 = 0; b0 < (int)gridDim.x; b0 += 32 * RMAX) {
-            double v[RMAX];
+}
+
+// block partials -> per-bin sums, one block per bin: every thread's loads are in flight at once (a serial chain of L2 round
+// trips here costs more than the streaming pass at 1e6 sources), then a fixed tree -- deterministic.  Launched programmatically
+// dependent on the weights kernel, so its launch latency hides behind that kernel's tail.
+#define VRS_THREADS 128
+__global__ void __launch_bounds__(VRS_THREADS) k_veff_sumreduce(int nblocks, int nbins, const double* __restrict__ sumphi,
+                                                               double* __restrict__ out_s) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    __shared__ double s_w[VRS_THREADS / 32];
+    const int j = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int RMAX = 4;                                                 // 512 blocks per pass
+    double s = 0.0;
+    for (int b0 = 0; b0 < nblocks; b0 += VRS_THREADS * RMAX) {
+        double v[RMAX];
 #pragma unroll
-            for (int r = 0; r < RMAX; ++r) {
-                const int b = b0 + r * 32 + lane;
-                v[r] = b < (int)gridDim.x ? __ldcg(&a.sumphi[(long long)b * nb + jb]) : 0.0;
-            }
-#pragma unroll
-            for (int r = 0; r < RMAX; ++r) s += v[r];
+        for (int r = 0; r < RMAX; ++r) {
+            const int b = b0 + r * VRS_THREADS + threadIdx.x;
+            v[r] = b < nblocks ? __ldcg(&sumphi[(long long)b * nbins + j]) : 0.0;
         }
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) a.out_s[jb] = s;
+#pragma unroll
+        for (int r = 0; r < RMAX; ++r) s += v[r];
     }
-    if (threadIdx.x == 0) *a.ticket = 0u;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_w[warp] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) out_s[j] = (s_w[0] + s_w[1]) + (s_w[2] + s_w[3]);
 }
 
 // one warp per bin: lanes stride over the block partials, fixed shuffle tree (deterministic)
@@ -708,7 +707,6 @@ static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned cha
     const bool same_nbins = c->v_nbins == nbins;
     if (veff_alloc_partials(c, blocks, nbins)) return 1;
     same_edges = same_edges && same_nbins && c->v_rows_valid;
-    if (!c->v_ticket) { CK(cudaMalloc(&c->v_ticket, sizeof(unsigned))); CK(cudaMemsetAsync(c->v_ticket, 0, sizeof(unsigned), c->stream)); }
     if (!c->v_rowcounts || c->v_rowcounts_n < nbins) {
         dfree(c->v_rowcounts);
         CK(cudaMalloc(&c->v_rowcounts, sizeof(unsigned long long) * nbins));
@@ -742,7 +740,7 @@ static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned cha
     }
     a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.modified = modified ? 1 : 0;
     a.inv_pref_vol = 1.0 / (a.pref * vol_int); a.tables = c->d_tables; a.nbins = nbins;
-    a.sumphi = c->v_sums; a.out_s = c->v_outs; a.ticket = c->v_ticket;
+    a.sumphi = c->v_sums;
     const size_t smem = vres_smem(nbins);
     const bool persrc = d_vol != nullptr;
     if (modified) {
@@ -752,8 +750,18 @@ static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned cha
         if (persrc) k_veff_res<false, true><<<blocks, 32 * VR_WARPS, smem, c->stream>>>(a);
         else k_veff_res<false, false><<<blocks, 32 * VR_WARPS, smem, c->stream>>>(a);
     }
+    {
+        cudaLaunchConfig_t lc;
+        memset(&lc, 0, sizeof(lc));
+        lc.gridDim = dim3(nbins); lc.blockDim = dim3(VRS_THREADS); lc.dynamicSmemBytes = 0; lc.stream = c->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = attr; lc.numAttrs = 1;
+        CK(cudaLaunchKernelEx(&lc, k_veff_sumreduce, blocks, nbins, (const double*)c->v_sums, c->v_outs));
+    }
     CK(cudaEventRecord(c->ev1, c->stream));
-    c->launches += 1;
+    c->launches += 2;
     CK(cudaGetLastError());
     static_assert(sizeof(unsigned long long) == sizeof(int64_t), "count width");
     CK(cudaMemcpyAsync(counts, c->v_rowcounts, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
