@@ -542,9 +542,179 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
     }
 }
 
+// ---- the same pass with the inputs staged by the TMA engine ----
+// ncu of k_veff_res (N = 1e7): no unit above 46 %, 36 % of the stall samples are warps waiting for their own global loads --
+// the trip is load -> long dependent FP64 chain -> histogram, and the loads of the next trip are not in flight while the
+// arithmetic runs.  Here one thread per block hands the next trips to the copy engine instead (cp.async.bulk, 1-D,
+// completion on an mbarrier: 8 KB of u, 8 KB of f, 2 KB of rows per trip into a two-stage ring in shared memory), so 18 KB
+// per block are always in flight whatever the warps are doing, and no registers are spent on prefetching.
+#ifndef LF_VRT_COLS
+#define LF_VRT_COLS 16                       /* private sum columns per warp and histogram row (32 / COLS lanes take turns) */
+#endif
+#define VRT_STAGES 2
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded: a copy that never completes (a bug, not a run-time condition) traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    for (int spin = 0; spin < (1 << 20); ++spin)
+        if (mbar_try_wait(bar, parity)) return;
+    __trap();
+}
+
+template <bool MODIFIED>
+__global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res_tma(VresArgs a) {
+    constexpr int U = VR_UNROLL, COLS = LF_VRT_COLS, TURNS = 32 / COLS;
+    constexpr int STRIDE = 32 * VR_WARPS, TRIP = STRIDE * U;
+    constexpr unsigned STAGE_BYTES = TRIP * (8 + 8 + 2);
+    asm volatile("griddepcontrol.launch_dependents;");                      // k_veff_sumreduce may become resident and wait
+    extern __shared__ __align__(16) unsigned char smem_raw[];          // bulk copies need 16-byte aligned destinations
+    __shared__ __align__(8) unsigned long long s_bar[VRT_STAGES];
+    __shared__ int s_fb[LF_MAX_FIELDS + 1];
+    __shared__ double s_fk[LF_MAX_FIELDS][4];
+    const int nb = a.nbins, nrow = nb + 2;
+    // stage sg: [TRIP f64 flux][TRIP f64 u][TRIP i16 row] at smem_raw + sg * STAGE_BYTES
+    double2* s_logm = reinterpret_cast<double2*>(smem_raw + (size_t)VRT_STAGES * STAGE_BYTES);
+    double* s_exp = reinterpret_cast<double*>(s_logm + STREAM_LOG_N);
+    double* s_sum = s_exp + EXP_TAB_N;                                      // [VR_WARPS][nrow][COLS]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long per_block = ((a.n + gridDim.x - 1) / gridDim.x + TRIP - 1) / TRIP * TRIP;
+    const long long start = (long long)blockIdx.x * per_block;
+    const int len = (int)(a.n - start < per_block ? (a.n - start > 0 ? a.n - start : 0) : per_block);
+    const int nfull = len / TRIP;
+    const double* __restrict__ p_flux = a.flux + start;
+    const double* __restrict__ p_u = a.u + start;
+    const short* __restrict__ p_row = a.row + start;
+    double* __restrict__ p_phi = a.phi + start;
+    auto issue = [&](int sg, int trip) {                                     // one thread: arm the barrier, start the three copies
+        mbar_expect_tx(&s_bar[sg], STAGE_BYTES);
+        unsigned char* base = smem_raw + (size_t)sg * STAGE_BYTES;
+        bulk_g2s(base, p_flux + (size_t)trip * TRIP, TRIP * 8, &s_bar[sg]);
+        bulk_g2s(base + TRIP * 8, p_u + (size_t)trip * TRIP, TRIP * 8, &s_bar[sg]);
+        bulk_g2s(base + TRIP * 16, p_row + (size_t)trip * TRIP, TRIP * 2, &s_bar[sg]);
+    };
+    if (threadIdx.x == 0) {
+        for (int sg = 0; sg < VRT_STAGES; ++sg) mbar_init(&s_bar[sg], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int sg = 0; sg < VRT_STAGES; ++sg)
+            if (sg < nfull) issue(sg, sg);                                   // the copies run under the table fill and the zeroing
+    }
+    for (int i = threadIdx.x; i < VR_WARPS * nrow * COLS; i += blockDim.x) s_sum[i] = 0.0;
+    load_stream_tables(a.tables, s_exp, s_logm);
+    if (threadIdx.x < a.K) {
+        const long long b = a.field_ind[threadIdx.x + 1] - start;
+        s_fb[threadIdx.x] = threadIdx.x == a.K - 1 ? 0x7fffffff : (int)(b < 0 ? 0 : (b > len ? len : b));
+        s_fk[threadIdx.x][0] = a.nconst[threadIdx.x]; s_fk[threadIdx.x][1] = a.inv_ftau[threadIdx.x];
+        s_fk[threadIdx.x][2] = a.F50[threadIdx.x]; s_fk[threadIdx.x][3] = a.ftau[threadIdx.x];
+    }
+    __syncthreads();
+    int sum_off = warp * nrow * COLS + (lane & (COLS - 1));
+    asm volatile("" : "+r"(sum_off));
+    double* my_sum = s_sum + sum_off;
+    const int turn = lane / COLS;
+    const double alpha = a.alpha;
+    int kU = 0;
+    // one trip: U sources per thread; FULL trips come from the shared-memory stage, the last partial one from global memory
+    auto trip_body = [&](int t0, const double* fsrc, const double* usrc, const short* rsrc, bool full) {
+        double phi[U];
+        int row[U];
+        const int base = t0 + threadIdx.x;
+        while (t0 >= s_fb[kU]) ++kU;                                        // block-uniform; s_fb[K - 1] = INT_MAX
+        if (full && t0 + TRIP <= s_fb[kU]) {                                // complete trip inside one field
+            double f[U], uu[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                f[u] = fsrc[threadIdx.x + u * STRIDE];
+                uu[u] = usrc[threadIdx.x + u * STRIDE];
+                row[u] = (int)rsrc[threadIdx.x + u * STRIDE];
+            }
+            const double nc = s_fk[kU][0], iftau = s_fk[kU][1];
+            unsigned badmask = 0u;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                bool bad;
+                phi[u] = inv_fleming_from_n<MODIFIED>(fma(alpha, uu[u], nc), f[u], iftau, s_exp, s_logm, bad);
+                badmask |= bad ? 1u << u : 0u;
+            }
+            if (badmask) {                                                   // rare: outside the fast range
+#pragma unroll
+                for (int u = 0; u < U; ++u)
+                    if (badmask >> u & 1u) phi[u] = inv_fleming_literal(f[u], s_fk[kU][2], alpha, s_fk[kU][3], MODIFIED);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                phi[u] *= a.inv_pref_vol;                                    // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
+                __stcs(p_phi + base + u * STRIDE, phi[u]);
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int off = base + u * STRIDE, so = threadIdx.x + u * STRIDE;
+                const bool in = off < len;
+                const double fl = in ? fsrc[so] : 1.0;
+                const double ul = in ? usrc[so] : 0.0;
+                row[u] = in ? (int)rsrc[so] : 0;
+                int k = kU;
+                while (off >= s_fb[k]) ++k;
+                bool bad;
+                double icomp = inv_fleming_from_n<MODIFIED>(fma(alpha, ul, s_fk[k][0]), fl, s_fk[k][1], s_exp, s_logm, bad);
+                if (bad) icomp = inv_fleming_literal(fl, s_fk[k][2], alpha, s_fk[k][3], MODIFIED);
+                phi[u] = in ? icomp * a.inv_pref_vol : 0.0;
+                if (in) __stcs(p_phi + off, phi[u]);
+            }
+        }
+        // sums in the thread's private column, the lanes that share it take turns (plain read-modify-writes, deterministic)
+#pragma unroll
+        for (int tn = 0; tn < TURNS; ++tn) {
+            if (turn == tn) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) my_sum[row[u] * COLS] += phi[u];
+            }
+            __syncwarp();
+        }
+    };
+    for (int t = 0; t < nfull; ++t) {
+        const int sg = t % VRT_STAGES;
+        mbar_wait(&s_bar[sg], (unsigned)((t / VRT_STAGES) & 1));
+        const unsigned char* stage = smem_raw + (size_t)sg * STAGE_BYTES;
+        trip_body(t * TRIP, reinterpret_cast<const double*>(stage), reinterpret_cast<const double*>(stage + TRIP * 8),
+                  reinterpret_cast<const short*>(stage + TRIP * 16), true);
+        __syncthreads();                                                    // every thread has read its part of the stage
+        if (threadIdx.x == 0 && t + VRT_STAGES < nfull) issue(sg, t + VRT_STAGES);
+    }
+    if (nfull * TRIP < len)                                                  // the chunk's last, partial trip: straight from global memory
+        trip_body(nfull * TRIP, p_flux + (size_t)nfull * TRIP, p_u + (size_t)nfull * TRIP, p_row + (size_t)nfull * TRIP, false);
+    __syncthreads();
+    for (int jb = warp; jb < nb; jb += VR_WARPS) {
+        double s = 0.0;
+        for (int wv = lane / COLS; wv < VR_WARPS; wv += TURNS) s += s_sum[(wv * nrow + jb + 1) * COLS + (lane & (COLS - 1))];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) a.sumphi[(long long)blockIdx.x * nb + jb] = s;
+    }
+}
+
 // block partials -> per-bin sums, one block per bin: every thread's loads are in flight at once (a serial chain of L2 round
 // trips here costs more than the streaming pass at 1e6 sources), then a fixed tree -- deterministic.  Launched programmatically
 // dependent on the weights kernel, so its launch latency hides behind that kernel's tail.
+#define VRT_SMEM_MAX (110 * 1024)
 #define VRS_THREADS 128
 __global__ void __launch_bounds__(VRS_THREADS) k_veff_sumreduce(int nblocks, int nbins, const double* __restrict__ sumphi,
                                                                double* __restrict__ out_s) {
@@ -693,6 +863,10 @@ static int veff_check_common(const char* who, const double* flim, const double* 
 static size_t vres_smem(int nbins) {
     return sizeof(double2) * STREAM_LOG_N + sizeof(double) * EXP_TAB_N + sizeof(double) * (size_t)VR_WARPS * (nbins + 2) * VP_COLS;
 }
+static size_t vres_tma_smem(int nbins) {
+    return (size_t)VRT_STAGES * (32 * VR_WARPS * VR_UNROLL) * 18 + sizeof(double2) * STREAM_LOG_N + sizeof(double) * EXP_TAB_N +
+           sizeof(double) * (size_t)VR_WARPS * (nbins + 2) * LF_VRT_COLS;
+}
 
 // resident route: rows + counts cached per edge set, weights pass on (u, f, row) with the block partials reduced in-kernel
 static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned char* d_valid, const double* flim, double alpha,
@@ -743,7 +917,13 @@ static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned cha
     a.sumphi = c->v_sums;
     const size_t smem = vres_smem(nbins);
     const bool persrc = d_vol != nullptr;
-    if (modified) {
+    static const bool use_tma = []() { const char* e = getenv("LF_VEFF_TMA"); return !(e && e[0] == '0'); }();
+    if (!persrc && use_tma && vres_tma_smem(nbins) <= VRT_SMEM_MAX) {
+        // inputs staged by the copy engine (bulk async copies + mbarrier ring)
+        const size_t smt = vres_tma_smem(nbins);
+        if (modified) k_veff_res_tma<true><<<blocks, 32 * VR_WARPS, smt, c->stream>>>(a);
+        else k_veff_res_tma<false><<<blocks, 32 * VR_WARPS, smt, c->stream>>>(a);
+    } else if (modified) {
         if (persrc) k_veff_res<true, true><<<blocks, 32 * VR_WARPS, smem, c->stream>>>(a);
         else k_veff_res<true, false><<<blocks, 32 * VR_WARPS, smem, c->stream>>>(a);
     } else {
@@ -1298,6 +1478,8 @@ int veff_init(lf_ctx* c) {
     CK(cudaFuncSetAttribute(k_veff_res<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CK(cudaFuncSetAttribute(k_veff_res<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
     CK(cudaFuncSetAttribute(k_veff_res<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CK(cudaFuncSetAttribute(k_veff_res_tma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, VRT_SMEM_MAX));
+    CK(cudaFuncSetAttribute(k_veff_res_tma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, VRT_SMEM_MAX));
     CK(cudaFuncSetAttribute(k_veff_priv<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
     CK(cudaFuncSetAttribute(k_veff_priv<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));
     CK(cudaFuncSetAttribute(k_veff_priv<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)VP_SMEM_MAX));

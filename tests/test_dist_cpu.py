@@ -4,6 +4,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -91,3 +92,15 @@ def test_walker_sharding_gathers_the_full_vector_on_every_rank():
         want[0] = -np.inf
         for r in range(world):
             assert np.array_equal(ret[r][W], want)
+
+
+def test_peer_geometry_mismatch_is_refused():
+    """Every rank's peer buffer must be created with the same (world, wcap): the slot offsets are computed from them."""
+    from lumfuncmcmc_b200.dist import check_peer_geometry
+    ok = [(b'h0', 0, 2, 4096), (b'h1', 1, 2, 4096)]
+    check_peer_geometry(ok, 2, 4096)
+    for bad in ([(b'h0', 0, 2, 4096), (b'h1', 1, 2, 2048)],        # other capacity
+                [(b'h0', 0, 2, 4096), (b'h1', 1, 4, 4096)],        # other world
+                [(b'h0', 0, 2, 4096), (b'h1', 0, 2, 4096)]):       # duplicate rank
+        with pytest.raises(RuntimeError, match='disagree'):
+            check_peer_geometry(bad, 2, 4096)
