@@ -715,6 +715,7 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res_tma(VresArgs a) {
 // trips here costs more than the streaming pass at 1e6 sources), then a fixed tree -- deterministic.  Launched programmatically
 // dependent on the weights kernel, so its launch latency hides behind that kernel's tail.
 #define VRT_SMEM_MAX (110 * 1024)
+#define VRT_MIN_SOURCES 4000000              /* below this the two-stage ring's set-up costs more than it hides (measured) */
 #define VRS_THREADS 128
 __global__ void __launch_bounds__(VRS_THREADS) k_veff_sumreduce(int nblocks, int nbins, const double* __restrict__ sumphi,
                                                                double* __restrict__ out_s) {
@@ -918,7 +919,7 @@ static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned cha
     const size_t smem = vres_smem(nbins);
     const bool persrc = d_vol != nullptr;
     static const bool use_tma = []() { const char* e = getenv("LF_VEFF_TMA"); return !(e && e[0] == '0'); }();
-    if (!persrc && use_tma && vres_tma_smem(nbins) <= VRT_SMEM_MAX) {
+    if (!persrc && use_tma && n >= VRT_MIN_SOURCES && vres_tma_smem(nbins) <= VRT_SMEM_MAX) {
         // inputs staged by the copy engine (bulk async copies + mbarrier ring)
         const size_t smt = vres_tma_smem(nbins);
         if (modified) k_veff_res_tma<true><<<blocks, 32 * VR_WARPS, smt, c->stream>>>(a);

@@ -331,10 +331,17 @@ def test_full_size_catalogue_properties_and_oracle_spot_check():
     eng = _engine(inp, 'free')
     whole = eng.lnprob(th)
     assert eng.last_call_info()['fast'] >= 60
-    # (1) the reference algorithm on three walkers (3e7 terms of NumPy work)
-    ref = lf_oracle.lnprob_batch(inp, 'free', th[[0, 31, 59]])
-    _assert_parity(whole[[0, 31, 59]], ref)
+    # (1) the reference algorithm on ten walkers, two of them prior draws (1e8 terms of NumPy work)
+    sel = [0, 7, 15, 23, 31, 39, 47, 59, 60, 63]
+    ref = lf_oracle.lnprob_batch(inp, 'free', th[sel])
+    _assert_parity(whole[sel], ref)
     eng.close()
+    # (1b) the optional FP32 loop at the same size: 1e-5 against the FP64 engine on every walker, and against the oracle
+    e32 = _engine(inp, 'free', precision='f32')
+    got32 = e32.lnprob(th)
+    _assert_parity(got32, whole, rtol=1e-5)
+    _assert_parity(got32[sel], ref, rtol=1e-5)
+    e32.close()
     # (2) additivity over three unequal source shards, each integrating a third of the walkers
     parts = []
     for r, (a, b) in enumerate([(0.0, 0.21), (0.21, 0.64), (0.64, 1.0)]):
@@ -353,6 +360,30 @@ def test_full_size_catalogue_properties_and_oracle_spot_check():
     e = _engine(p, 'free')
     _assert_parity(e.lnprob(th), whole, rtol=1e-13)
     e.close()
+
+
+def test_config3_size_z_model_against_oracle():
+    """BASELINE.json configs[2] at its own size: redshift-evolving model, 1e6 sources x 512 walkers; the oracle on twelve of
+    them (prior draws included), the -inf sets of the whole ensemble against the literal kernels."""
+    n = 1_000_000
+    cat = synth.make_catalogue(n, seed=78, evolve=(0.3, -0.2))
+    inp = synth.direct_inputs(cat, nknots=4096, size_ln=201, tabulated=True)
+    th = np.concatenate([synth.draw_thetas(inp, 'z', 480, seed=5, mode='near', scale=0.02),
+                         synth.draw_thetas(inp, 'z', 32, seed=6, mode='prior')])
+    eng = _engine(inp, 'z')
+    got = eng.lnprob(th)
+    assert eng.last_call_info()['fast'] >= 480
+    sel = [0, 100, 200, 300, 400, 479, 480, 485, 490, 495, 505, 511]
+    ref = lf_oracle.lnprob_batch(inp, 'z', th[sel])
+    _assert_parity(got[sel], ref)
+    eng.close()
+    lit = _engine(inp, 'z', force_literal=True)
+    sub = np.r_[0:16, 480:512]
+    _assert_parity(lit.lnprob(th[sub]), got[sub], rtol=1e-10)
+    lit.close()
+    e32 = _engine(inp, 'z', precision='f32')
+    _assert_parity(e32.lnprob(th), got, rtol=1e-5)
+    e32.close()
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -13,10 +13,21 @@ from lumfuncmcmc_b200.engine import LikelihoodEngine, VeffEngine   # noqa: E402
 quick = len(sys.argv) > 1
 
 
+# FP64-pipe instructions per (walker, source) term and per (walker, quadrature point) of the fast kernels (SASS counts,
+# tools/sass_loop_mix.py): the quadrature is real work that "terms/s" does not count -- at 1e5 sources it is the larger half
+FP64_TERM = {'free': 23, 'z': 9, 'fixed': 0}
+FP64_POINT = {'free': 36, 'z': 12, 'fixed': 12}
+PEAK = {}
+
+
 def run(kind, n, walkers, prec='f64'):
     cat = synth.make_catalogue(n, seed=1, evolve=(0.3, -0.2) if kind == 'z' else None)
     inp = synth.direct_inputs(cat, nknots=4096, size_ln=101 if kind == 'free' else 201, tabulated=(kind != 'free'))
     eng = LikelihoodEngine(inp, kind, precision=prec)
+    if 'dfma' not in PEAK:
+        PEAK['dfma'] = max(eng.fp64_peak(100000)[0] for _ in range(3))
+    S = len(inp['zarr'])
+    npoints = (len(inp['Flim']) if kind == 'free' else 1) * S * S          # FIXED / Z: identical field grids are merged
     for W in walkers:
         th = synth.draw_thetas(inp, kind, W, seed=3, mode='near', scale=0.02)
         for _ in range(3):
@@ -28,13 +39,16 @@ def run(kind, n, walkers, prec='f64'):
             ws.append(time.perf_counter() - t0)
             ts.append(eng.last_kernel_ms() * 1e-3)
         k, w = min(ts), min(ws)
-        print("| %-5s | %s | %8.0e | %5d | %9.3f | %9.3f | %10.3e | %10.3e |" % (kind, prec, n, W, k * 1e3, w * 1e3, n * W / k, n * W / w),
+        frac_terms = n * W * FP64_TERM[kind] / k / PEAK['dfma']
+        frac_all = (n * W * FP64_TERM[kind] + npoints * W * FP64_POINT[kind]) / k / PEAK['dfma']
+        fr = "%.2f / %.2f" % (frac_terms, frac_all) if prec == 'f64' else "-"
+        print("| %-5s | %s | %8.0e | %5d | %9.3f | %9.3f | %10.3e | %10.3e | %s |" % (kind, prec, n, W, k * 1e3, w * 1e3, n * W / k, n * W / w, fr),
               flush=True)
     eng.close()
 
 
-print("| model | loop arithmetic | sources | walkers | kernel ms | host-call ms | terms/s (kernels) | terms/s (host API) |")
-print("|---|---|---|---|---|---|---|---|")
+print("| model | loop arithmetic | sources | walkers | kernel ms | host-call ms | terms/s (kernels) | terms/s (host API) | fraction of the measured DFMA rate: terms only / terms + quadrature |")
+print("|---|---|---|---|---|---|---|---|---|")
 sizes = [100000, 1000000] if quick else [100000, 1000000, 10000000]
 for n in sizes:
     run('free', n, [64, 256, 1024, 4096])
