@@ -575,6 +575,7 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned 
 }
 // bounded: a copy that never completes (a bug, not a run-time condition) traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+#pragma unroll 1
     for (int spin = 0; spin < (1 << 20); ++spin)
         if (mbar_try_wait(bar, parity)) return;
     __trap();
