@@ -327,7 +327,8 @@ static __constant__ double KS[16] = {
     1.0 / 24.0, 1.0 / 6.0,                           // 9-10  expm1
     0.0,
     0.43429448190325182765,                          // 12    log10(e)
-    0.0, 0.0, 0.0};
+    -256.0 * LOG2E,                                  // 13    exp(-x) range reduction
+    0.0, 0.0};
 
 __device__ __forceinline__ void load_stream_tables(const Tables* __restrict__ t, double* s_exp, double2* s_logm) {
     for (int i = threadIdx.x; i < EXP_TAB_N; i += blockDim.x) s_exp[i] = t->exp2_frac[i];
@@ -341,7 +342,9 @@ __device__ __forceinline__ void load_stream_tables(const Tables* __restrict__ t,
 // instructions; the exponent becomes a double by pairing it with the high word of 2^52 (no I2F)
 __device__ __forceinline__ double log_stream(double v, const double2* s_logm) {
     const int hi = __double2hiint(v);
-    const double m = __hiloint2double((hi & 0x000fffff) | 0x3fe00000, __double2loint(v));   // v = 2^e m, m in [1/2, 1)
+    int mh;                                                                 // (hi & 0xfffff) | 0x3fe00000 as ONE LOP3 (constants in registers)
+    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(mh) : "r"(hi), "r"(0x000fffff), "r"(0x3fe00000));
+    const double m = __hiloint2double(mh, __double2loint(v));               // v = 2^e m, m in [1/2, 1)
     const double2 tb = *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(s_logm) +
                                                          (((unsigned)hi >> (20 - LOG_MANT_BITS - 4)) & ((STREAM_LOG_N - 1) << 4)));
     const double eps = fma(m, tb.x, -1.0);                                  // |eps| <= 2^-9
@@ -366,6 +369,26 @@ __device__ __forceinline__ double exp_stream(double x, const double* s_exp) {
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
     p = p * r;                                                              // expm1(r), truncation r^5/120 < 4e-17
+    return fma(Ts, p, Ts);
+}
+
+// exp(+x) (NEG = false) or exp(-x) (NEG = true) with the sign folded into the constants (no negation instruction) and the
+// power of two clamped at 2^-1000 instead of the argument: for arguments below -693 the result is a finite ~1e-301 (0
+// against 1 for the decay factor 1 - exp(-x), the only caller that can get there), so no compare-and-select is needed.
+// Same arithmetic and accuracy as exp_stream on its range.
+template <bool NEG>
+__device__ __forceinline__ double exp_stream_signed(double x, const double* s_exp) {
+    const double t = fma(x, NEG ? KS[13] : KS[5], KS[6]);
+    const int k = max(__double2loint(t), -1000 * EXP_TAB_N);
+    const double kf = t - KS[6];
+    double r = NEG ? fma(kf, KS[7], -x) : fma(kf, KS[7], x);
+    r = fma(kf, KS[8], r);                                                  // |r| <= ln2/512
+    const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (((unsigned)k << 3) & ((EXP_TAB_N - 1) << 3)));
+    const double Ts = __hiloint2double(__double2hiint(T) + (int)(((unsigned)k << (20 - EXP_TAB_BITS)) & 0xfff00000u), __double2loint(T));
+    double p = fma(r, KS[9], KS[10]);
+    p = fma(r, p, 0.5);
+    p = fma(r, p, 1.0);
+    p = p * r;
     return fma(Ts, p, Ts);
 }
 

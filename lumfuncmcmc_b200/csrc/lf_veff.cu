@@ -395,14 +395,16 @@ struct VresArgs {
     double* phi;
     int K; long long field_ind[LF_MAX_FIELDS + 1];
     double nconst[LF_MAX_FIELDS], inv_ftau[LF_MAX_FIELDS], F50[LF_MAX_FIELDS], ftau[LF_MAX_FIELDS];
-    double alpha, pref, inv_pref_vol; int modified, nbins;
+    double alpha, pref, inv_pref_vol, ln_inv_pref_vol; int modified, nbins;
     const Tables* tables;
     double* sumphi;                      // [gridDim.x][nbins] block partials (summed per bin by k_veff_sumreduce)
 };
 
-// 1 / fleming for n = alpha log10(f / F50) already formed; otherwise the arithmetic of inv_fleming_stream
+// exp(lnscale) / fleming for n = alpha log10(f / F50) already formed; otherwise the arithmetic of inv_fleming_stream.  The
+// caller's constant factor 1 / (pref vol) rides in the exponent (lnscale = its logarithm; one fma instead of a multiply per
+// source, 2e-15 relative).  Lanes flagged `bad` return garbage that the caller replaces by the literal evaluation.
 template <bool MODIFIED>
-__device__ __forceinline__ double inv_fleming_from_n(double num, double f, double inv_ftau, const double* s_exp,
+__device__ __forceinline__ double inv_fleming_from_n(double num, double f, double inv_ftau, double lnscale, const double* s_exp,
                                                      const double2* s_logm, bool& bad) {
     const double y = fma(num, num, 1.0);
     const double r0 = rsqrt_seed(y);
@@ -414,16 +416,14 @@ __device__ __forceinline__ double inv_fleming_from_n(double num, double f, doubl
     double t = log_stream(fc, s_logm);                                      // ln fc <= 0
     if (MODIFIED) {
         const double x = f * inv_ftau;
-        const int hx = __double2hiint(x);
-        lowest = min(lowest, hx);                                           // x > 1e-6
-        const double xm = hx < 0x40859000 ? x : 690.0;                      // beyond 690 the decay factor is 1 anyway
-        t *= rcp_stream(exp_stream(-xm, s_exp) - 1.0);                      // -ln(fc) / (1 - e^-x) >= 0
+        lowest = min(lowest, __double2hiint(x));                            // x > 1e-6
+        t = fma(t, rcp_stream(exp_stream_signed<true>(x, s_exp) - 1.0), lnscale);    // -ln(fc) / (1 - e^-x) + lnscale
     } else {
-        t = -t;
+        t = lnscale - t;
     }
-    const bool ok = (lowest > 0x3eb0c6f7) & ((unsigned)__double2hiint(t) < 0x40859000u);   // and 0 <= t < 690
-    bad = !ok;
-    return exp_stream(ok ? t : 0.0, s_exp);
+    // fc, x > 1e-6 and the exponent inside (-690, 690): compares on high words (|t| < 690 <=> hi(|t|) < hi(690))
+    bad = !((lowest > 0x3eb0c6f7) & ((unsigned)(__double2hiint(t) & 0x7fffffff) < 0x40859000u));
+    return exp_stream_signed<false>(t, s_exp);
 }
 
 #define VR_WARPS 8
@@ -483,13 +483,14 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 bool bad;
-                phi[u] = inv_fleming_from_n<MODIFIED>(fma(alpha, uu[u], nc), f[u], iftau, s_exp, s_logm, bad);
+                phi[u] = inv_fleming_from_n<MODIFIED>(fma(alpha, uu[u], nc), f[u], iftau, PERSRC ? 0.0 : a.ln_inv_pref_vol, s_exp, s_logm, bad);
                 badmask |= bad ? 1u << u : 0u;
             }
             if (badmask) {                                                   // rare: outside the fast range
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    if (badmask >> u & 1u) phi[u] = inv_fleming_literal(f[u], s_fk[kU][2], alpha, s_fk[kU][3], MODIFIED);
+                    if (badmask >> u & 1u)
+                        phi[u] = inv_fleming_literal(f[u], s_fk[kU][2], alpha, s_fk[kU][3], MODIFIED) * (PERSRC ? 1.0 : a.inv_pref_vol);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -497,8 +498,6 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
                     const double vol = __ldcs(p_vol + base + u * STRIDE);
                     const bool ok = p_valid[base + u * STRIDE] != 0;
                     phi[u] = ok ? phi[u] * (1.0 / (a.pref * vol)) : 0.0;     // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
-                } else {
-                    phi[u] *= a.inv_pref_vol;
                 }
                 __stcs(p_phi + base + u * STRIDE, phi[u]);
             }
@@ -514,7 +513,7 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
                 int k = kU;
                 while (off >= s_fb[k]) ++k;
                 bool bad;
-                double icomp = inv_fleming_from_n<MODIFIED>(fma(alpha, ul, s_fk[k][0]), fl, s_fk[k][1], s_exp, s_logm, bad);
+                double icomp = inv_fleming_from_n<MODIFIED>(fma(alpha, ul, s_fk[k][0]), fl, s_fk[k][1], 0.0, s_exp, s_logm, bad);
                 if (bad) icomp = inv_fleming_literal(fl, s_fk[k][2], alpha, s_fk[k][3], MODIFIED);
                 double ipv = a.inv_pref_vol;
                 bool ok = in;
@@ -549,7 +548,7 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res(VresArgs a) {
 // completion on an mbarrier: 8 KB of u, 8 KB of f, 2 KB of rows per trip into a two-stage ring in shared memory), so 18 KB
 // per block are always in flight whatever the warps are doing, and no registers are spent on prefetching.
 #ifndef LF_VRT_COLS
-#define LF_VRT_COLS 16                       /* private sum columns per warp and histogram row (32 / COLS lanes take turns) */
+#define LF_VRT_COLS 8                        /* private sum columns per warp and histogram row (32 / COLS lanes take turns) */
 #endif
 #define VRT_STAGES 2
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -652,19 +651,17 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res_tma(VresArgs a) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 bool bad;
-                phi[u] = inv_fleming_from_n<MODIFIED>(fma(alpha, uu[u], nc), f[u], iftau, s_exp, s_logm, bad);
+                // 1 / (pref vol comp): lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
+                phi[u] = inv_fleming_from_n<MODIFIED>(fma(alpha, uu[u], nc), f[u], iftau, a.ln_inv_pref_vol, s_exp, s_logm, bad);
                 badmask |= bad ? 1u << u : 0u;
             }
             if (badmask) {                                                   // rare: outside the fast range
 #pragma unroll
                 for (int u = 0; u < U; ++u)
-                    if (badmask >> u & 1u) phi[u] = inv_fleming_literal(f[u], s_fk[kU][2], alpha, s_fk[kU][3], MODIFIED);
+                    if (badmask >> u & 1u) phi[u] = inv_fleming_literal(f[u], s_fk[kU][2], alpha, s_fk[kU][3], MODIFIED) * a.inv_pref_vol;
             }
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                phi[u] *= a.inv_pref_vol;                                    // lumfuncmcmc.py:524, VmaxLumFunc.py:256-257
-                __stcs(p_phi + base + u * STRIDE, phi[u]);
-            }
+            for (int u = 0; u < U; ++u) __stcs(p_phi + base + u * STRIDE, phi[u]);
         } else {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -676,7 +673,7 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res_tma(VresArgs a) {
                 int k = kU;
                 while (off >= s_fb[k]) ++k;
                 bool bad;
-                double icomp = inv_fleming_from_n<MODIFIED>(fma(alpha, ul, s_fk[k][0]), fl, s_fk[k][1], s_exp, s_logm, bad);
+                double icomp = inv_fleming_from_n<MODIFIED>(fma(alpha, ul, s_fk[k][0]), fl, s_fk[k][1], 0.0, s_exp, s_logm, bad);
                 if (bad) icomp = inv_fleming_literal(fl, s_fk[k][2], alpha, s_fk[k][3], MODIFIED);
                 phi[u] = in ? icomp * a.inv_pref_vol : 0.0;
                 if (in) __stcs(p_phi + off, phi[u]);
@@ -716,7 +713,7 @@ __global__ void __launch_bounds__(32 * VR_WARPS) k_veff_res_tma(VresArgs a) {
 // trips here costs more than the streaming pass at 1e6 sources), then a fixed tree -- deterministic.  Launched programmatically
 // dependent on the weights kernel, so its launch latency hides behind that kernel's tail.
 #define VRT_SMEM_MAX (110 * 1024)
-#define VRT_MIN_SOURCES 4000000              /* below this the two-stage ring's set-up costs more than it hides (measured) */
+#define VRT_MIN_SOURCES 0                    /* the staged kernel is at least as fast as the direct one from 1e6 sources down (measured) */
 #define VRS_THREADS 128
 __global__ void __launch_bounds__(VRS_THREADS) k_veff_sumreduce(int nblocks, int nbins, const double* __restrict__ sumphi,
                                                                double* __restrict__ out_s) {
@@ -916,6 +913,7 @@ static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned cha
     }
     a.alpha = alpha; a.pref = sum_omega / SQARCSEC; a.modified = modified ? 1 : 0;
     a.inv_pref_vol = 1.0 / (a.pref * vol_int); a.tables = c->d_tables; a.nbins = nbins;
+    a.ln_inv_pref_vol = (double)(-logl((long double)a.pref * (long double)vol_int));
     a.sumphi = c->v_sums;
     const size_t smem = vres_smem(nbins);
     const bool persrc = d_vol != nullptr;
