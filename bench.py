@@ -445,8 +445,27 @@ def veff_block(eng, inp, n):
     for _ in range(3):
         cb, _ = eng.boot_bin(mult)
         best_b = min(best_b, eng.last_kernel_ms())
-    want_b = np.bincount(idx[(idx >= 0) & (idx < nb)], weights=mult[(idx >= 0) & (idx < nb)], minlength=nb)[:nb]
+    inb = (idx >= 0) & (idx < nb)
+    want_b = np.bincount(idx[inb], weights=mult[inb], minlength=nb)[:nb]
     boot_equal = bool(np.array_equal(cb, want_b.astype(np.int64)))
+    # the same resampling with NumPy's MT19937 stream generated ON the device (VmaxLumFunc.py:353): the first replicate must
+    # equal the host-drawn one bin for bin; then the cost of a replicate without the host draw and the 4 N-byte upload
+    rs = np.random.RandomState(5)
+    eng.boot_mt_set_state(rs.get_state())
+    t0 = time.perf_counter()
+    cm, _ = eng.boot_bin_mt()
+    mult_h = np.bincount(rs.randint(n, size=n), minlength=n)
+    want_m = np.bincount(idx[inb], weights=mult_h[inb], minlength=nb)[:nb].astype(np.int64)
+    mt_equal = bool(np.array_equal(cm, want_m))
+    t0 = time.perf_counter()
+    for _ in range(3):
+        eng.boot_bin_mt()
+    mt_ms = (time.perf_counter() - t0) / 3 * 1e3
+    st_dev, st_host = eng.boot_mt_get_state(), None
+    for _ in range(3):
+        rs.randint(n, size=n)
+    st_host = rs.get_state()
+    mt_state_equal = bool(st_dev[2] == st_host[2] and np.array_equal(st_dev[1], st_host[1]))
     return {"workload": "1/V_eff weights + binning, %d sources, %d bins, sample resident on the device; one bootstrap replicate" % (n, nb),
             "weights_ms": best_w, "weights_gbs": 26.0 * n / (best_w * 1e-3) / 1e9,
             "replicate_ms": best_b, "replicate_gbs": 14.0 * n / (best_b * 1e-3) / 1e9,
@@ -454,7 +473,12 @@ def veff_block(eng, inp, n):
             "e2e_ms_resident_call": best_call, "sample_upload_ms_once": t_upload * 1e3,
             "e2e_note": "host wall clock of lf_veff_bin_resident (kernels + D2H of 50 counts and sums + sync); the per-source "
                         "weights stay on the device and are downloaded only when phifunc is read",
-            "counts_match_numpy_per_bin": per_bin_equal, "bootstrap_counts_match_numpy_per_bin": boot_equal}
+            "mt19937_replicate_ms": mt_ms,
+            "mt19937_note": "one bootstrap replicate with np.random.randint(N, size=N)'s own stream drawn on the device (lf_boot_bin_mt), "
+                            "host wall clock; counts bit-equal to the host-drawn replicate and generator state equal after 4 replicates: %s / %s"
+                            % (mt_equal, mt_state_equal),
+            "counts_match_numpy_per_bin": per_bin_equal,
+            "bootstrap_counts_match_numpy_per_bin": bool(boot_equal and mt_equal and mt_state_equal)}
 
 
 def main():
