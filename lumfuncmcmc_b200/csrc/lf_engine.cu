@@ -1006,7 +1006,7 @@ extern "C" void lf_destroy(lf_ctx* c) {
     dfree(c->d_cls); dfree(c->d_list_fast); dfree(c->d_list_lit); dfree(c->d_list_fastq); dfree(c->d_list_litq); dfree(c->d_thetas); dfree(c->d_out);
     dfree(c->v_lum); dfree(c->v_phi); dfree(c->v_edges); dfree(c->v_counts); dfree(c->v_sums);
     dfree(c->v_outc); dfree(c->v_outs); dfree(c->v_mult); dfree(c->v_bin);
-    dfree(c->v_flux); dfree(c->v_vol); dfree(c->v_valid); dfree(c->v_u); dfree(c->v_rowcounts); dfree(c->v_ticket); dfree(c->v_mt_state);
+    dfree(c->v_flux); dfree(c->v_vol); dfree(c->v_valid); dfree(c->v_u); dfree(c->v_rowcounts); dfree(c->v_ticket); dfree(c->v_mt_state); dfree(c->v_mt_vals);
     dfree(c->v_cum); dfree(c->v_gl); dfree(c->v_zk); dfree(c->v_dVk); dfree(c->v_cumV);
     if (c->ev_scratch) cudaEventDestroy(c->ev_scratch);
     peer_release(c);

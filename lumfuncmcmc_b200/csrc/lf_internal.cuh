@@ -278,6 +278,7 @@ struct lf_ctx {
     int* v_mult = nullptr; short* v_bin = nullptr; int v_blocks = 0;
     // sample kept resident across V_eff calls (lf_veff_set_sample) and its per-source volumes (lf_veff_volumes)
     double* v_flux = nullptr; double* v_vol = nullptr; unsigned char* v_valid = nullptr;
+    uint32_t* v_mt_vals = nullptr; long long v_mt_cap = 0;      // candidate values of one replicate (+ the count of words used)
     uint32_t* v_mt_state = nullptr;                // MT19937 key[624] + position (device bootstrap with NumPy's stream)
     double* v_u = nullptr;                         // log10(flux / VRES_F0), computed once per sample
     bool v_rows_valid = false; std::vector<double> v_edges_host;     // edges the resident rows / counts were computed for

@@ -1323,8 +1323,13 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     return y;
 }
 
+// The generating CTA only WRITES the accepted-or-not values (coalesced, one word per output; MT_REJECT for a rejected one)
+// and counts; k_mt_scatter, a full grid, turns them into multiplicities afterwards.  (Issuing the ~370 random global atomics
+// per state block from the one generating SM made the draw five times slower than the state recurrence itself.)
+#define MT_REJECT 0xffffffffu
 __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g_state, int* __restrict__ g_pos, long long n,
-                                                       uint32_t rng, uint32_t mask, int* __restrict__ mult) {
+                                                       uint32_t rng, uint32_t mask, uint32_t* __restrict__ vals, long long cap,
+                                                       long long* __restrict__ g_used, int* __restrict__ mult) {
     __shared__ uint32_t mt[2][MT_N];
     __shared__ int s_warp_cnt[MT_THREADS / 32];
     __shared__ int s_newpos;
@@ -1333,6 +1338,7 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g
     if (j < MT_N) mt[0][j] = g_state[j];
     int pos = *g_pos;                                   // next unused output of the current state block (624: none left)
     long long acc = 0;                                  // samples accepted so far
+    long long used = 0;                                 // words written to vals
     __syncthreads();
     for (;;) {
         if (pos >= MT_N) {                              // regenerate the state block (block-uniform)
@@ -1356,8 +1362,11 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g
             ok = v <= rng;
         }
         const int cnt = __syncthreads_count(ok);
+        const bool buffered = used + MT_N <= cap;       // room for a whole block of outputs (else: direct atomics, rare)
         if (acc + cnt < n) {                            // the replicate needs all of them (and more)
-            if (ok) atomicAdd(&mult[v], 1);
+            if (buffered) { if (j < MT_N) vals[used + j] = ok ? v : MT_REJECT; }
+            else if (ok) atomicAdd(&mult[v], 1);
+            if (buffered) used += MT_N;
             acc += cnt;
             pos = MT_N;
             continue;
@@ -1376,7 +1385,16 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g
         break;
     }
     if (j < MT_N) g_state[j] = mt[cur][j];
-    if (j == 0) *g_pos = pos;
+    if (j == 0) { *g_pos = pos; *g_used = used; }
+}
+
+__global__ void __launch_bounds__(256) k_mt_scatter(const uint32_t* __restrict__ vals, const long long* __restrict__ g_used,
+                                                    int* __restrict__ mult) {
+    const long long used = *g_used;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < used; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t v = vals[i];
+        if (v != MT_REJECT) atomicAdd(&mult[v], 1);
+    }
 }
 
 extern "C" int lf_boot_mt_set_state(lf_ctx* c, const uint32_t* key, int32_t pos) {
@@ -1412,9 +1430,20 @@ extern "C" int lf_boot_bin_mt(lf_ctx* c, int64_t* counts, double* sumphi) {
     const uint32_t rng = (uint32_t)(c->vN - 1);
     uint32_t mask = rng;                                // gen_mask: smallest 2^k - 1 >= rng
     mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+    // candidate buffer: the mask accepts at least every second output, so 2 n words + a few sigma + one state block hold a
+    // replicate; whatever does not fit is scattered directly by the generating CTA
+    const long long cap = 2 * c->vN + 16 * (long long)sqrt(2.0 * (double)c->vN) + 4 * MT_N;
+    if (!c->v_mt_vals || c->v_mt_cap < cap) {
+        dfree(c->v_mt_vals);
+        CK(cudaMalloc(&c->v_mt_vals, sizeof(uint32_t) * ((size_t)cap + 2) + sizeof(long long)));
+        c->v_mt_cap = cap;
+    }
+    long long* d_used = reinterpret_cast<long long*>(c->v_mt_vals + ((size_t)cap + 1) / 2 * 2);
     CK(cudaEventRecord(c->ev0, c->stream));
     CK(cudaMemsetAsync(c->v_mult, 0, sizeof(int) * (size_t)c->vN, c->stream));
-    k_mt_draw<<<1, MT_THREADS, 0, c->stream>>>(c->v_mt_state, reinterpret_cast<int*>(c->v_mt_state + MT_N), c->vN, rng, mask, c->v_mult);
+    k_mt_draw<<<1, MT_THREADS, 0, c->stream>>>(c->v_mt_state, reinterpret_cast<int*>(c->v_mt_state + MT_N), c->vN, rng, mask,
+                                                c->v_mt_vals, cap, d_used, c->v_mult);
+    k_mt_scatter<<<c->sm_count * 8, 256, 0, c->stream>>>(c->v_mt_vals, d_used, c->v_mult);
     VeffArgs a;
     memset(&a, 0, sizeof(a));
     a.n = c->vN; a.lum = c->v_lum; a.phi = c->v_phi; a.edges = c->v_edges; a.nbins = c->v_nbins;
@@ -1427,7 +1456,7 @@ extern "C" int lf_boot_bin_mt(lf_ctx* c, int64_t* counts, double* sumphi) {
     veff_launch<1>(plan, a, c->stream);
     k_veff_reduce<<<(nbins + 3) / 4, 128, 0, c->stream>>>(blocks, nbins, c->v_counts, c->v_sums, c->v_outc, c->v_outs);
     CK(cudaEventRecord(c->ev1, c->stream));
-    c->launches += 3;
+    c->launches += 4;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(counts, c->v_outc, sizeof(long long) * nbins, cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(sumphi, c->v_outs, sizeof(double) * nbins, cudaMemcpyDeviceToHost, c->stream));

@@ -13,6 +13,6 @@ python tools/veff_one.py 1e7 > gpurun_out/r2_vone_tma.log 2>&1 &&
   ncu --set full --clock-control none --import-source on -k regex:k_veff_res_tma -s 1 -c 1 -o gpurun_out/r2_vres_tma_1e7 \
       python tools/veff_one.py 1e7 > /dev/null 2>&1
 python bench.py --kind z --nsources 1e6 --walkers 512 --no-extras --no-cpu-baseline --steps 3 --warmup 3 > gpurun_out/r2_zplain.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k 'regex:k_main<\(bool\)0' -s 3 -c 1 -o gpurun_out/r2_kmain_z_1e6x512 \
+  ncu --set full --clock-control none --import-source on -k regex:k_main -s 6 -c 1 -o gpurun_out/r2_kmain_z_1e6x512 \
       python bench.py --kind z --nsources 1e6 --walkers 512 --no-extras --no-cpu-baseline --steps 3 --warmup 3 > /dev/null 2>&1
 ls -la gpurun_out/*.ncu-rep
