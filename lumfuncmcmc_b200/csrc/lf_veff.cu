@@ -1305,12 +1305,12 @@ extern "C" int lf_boot_bin_device(lf_ctx* c, uint64_t seed, int64_t replicate, i
 // one is <= n - 1" (numpy/random/src/distributions/distributions.c: random_bounded_uint64_fill ->
 // buffered_bounded_masked_uint32).  One CTA reproduces exactly that stream: the 624-word state is regenerated in three
 // parallel phases (words [0, 227) depend on the old state only, [227, 454) on those, [454, 624) on the second group),
-// every thread tempers one word, accepted values increment the multiplicity of their source (integer atomics: order does
+// the words are tempered and tested, accepted values increment the multiplicity of their source (integer atomics: order does
 // not matter), and the replicate ends right after its n-th accepted output -- the state and position left behind are what
 // NumPy's would be, so the host generator can be re-synchronised afterwards (lf_boot_mt_get_state).
 #define MT_N 624
 #define MT_M 397
-#define MT_THREADS 640
+#define MT_THREADS 256
 __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b) {
     const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
     return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
@@ -1327,15 +1327,19 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 // and counts; k_mt_scatter, a full grid, turns them into multiplicities afterwards.  (Issuing the ~370 random global atomics
 // per state block from the one generating SM made the draw five times slower than the state recurrence itself.)
 #define MT_REJECT 0xffffffffu
+// 227 working threads (8 warps: cheap barriers): thread j owns words j, j + 227 and j + 454 of the state block -- one per
+// phase of the regeneration -- and tempers / tests / stores the same three words.  Per block of 624 outputs: three barriers
+// for the recurrence and one counting barrier.
 __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g_state, int* __restrict__ g_pos, long long n,
                                                        uint32_t rng, uint32_t mask, uint32_t* __restrict__ vals, long long cap,
                                                        long long* __restrict__ g_used, int* __restrict__ mult) {
+    constexpr int L = MT_N - MT_M;                      // 227: words that can be regenerated in parallel
     __shared__ uint32_t mt[2][MT_N];
-    __shared__ int s_warp_cnt[MT_THREADS / 32];
+    __shared__ int s_cnt[3][MT_THREADS / 32];
     __shared__ int s_newpos;
     const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
     int cur = 0;
-    if (j < MT_N) mt[0][j] = g_state[j];
+    for (int i = j; i < MT_N; i += MT_THREADS) mt[0][i] = g_state[i];
     int pos = *g_pos;                                   // next unused output of the current state block (624: none left)
     long long acc = 0;                                  // samples accepted so far
     long long used = 0;                                 // words written to vals
@@ -1344,47 +1348,73 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g
         if (pos >= MT_N) {                              // regenerate the state block (block-uniform)
             const uint32_t* o = mt[cur];
             uint32_t* w = mt[cur ^ 1];
-            if (j < MT_N - MT_M) w[j] = o[j + MT_M] ^ mt_twist(o[j], o[j + 1]);
+            if (j < L) w[j] = o[j + MT_M] ^ mt_twist(o[j], o[j + 1]);
             __syncthreads();
-            if (j >= MT_N - MT_M && j < 2 * (MT_N - MT_M)) w[j] = w[j - (MT_N - MT_M)] ^ mt_twist(o[j], o[j + 1]);
+            if (j < L) w[j + L] = w[j] ^ mt_twist(o[j + L], o[j + L + 1]);
             __syncthreads();
-            if (j >= 2 * (MT_N - MT_M) && j < MT_N - 1) w[j] = w[j - (MT_N - MT_M)] ^ mt_twist(o[j], o[j + 1]);
-            if (j == MT_N - 1) w[j] = w[MT_M - 1] ^ mt_twist(o[j], w[0]);
+            if (j + 2 * L < MT_N - 1) w[j + 2 * L] = w[j + L] ^ mt_twist(o[j + 2 * L], o[j + 2 * L + 1]);
+            else if (j + 2 * L == MT_N - 1) w[MT_N - 1] = w[MT_M - 1] ^ mt_twist(o[MT_N - 1], w[0]);
             __syncthreads();
             cur ^= 1;
             pos = 0;
         }
-        // outputs pos .. 623 of this block, one per thread, in stream order
-        bool ok = false;
-        uint32_t v = 0u;
-        if (j >= pos && j < MT_N) {
-            v = mt_temper(mt[cur][j]) & mask;
-            ok = v <= rng;
+        // outputs pos .. 623 of this block: thread j looks at words j, j + 227, j + 454
+        uint32_t v[3];
+        bool ok[3];
+        int mine = 0;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int idx = j + t * L;
+            ok[t] = false; v[t] = 0u;
+            if (j < L && idx >= pos && idx < MT_N) {
+                v[t] = mt_temper(mt[cur][idx]) & mask;
+                ok[t] = v[t] <= rng;
+            }
+            mine += ok[t] ? 1 : 0;
         }
-        const int cnt = __syncthreads_count(ok);
+        // block-wide count of accepted outputs (sum over threads of 0..3)
+        const int c1 = __syncthreads_count(mine & 1), c2 = __syncthreads_count(mine & 2);
+        const int cnt = c1 + 2 * c2;
         const bool buffered = used + MT_N <= cap;       // room for a whole block of outputs (else: direct atomics, rare)
         if (acc + cnt < n) {                            // the replicate needs all of them (and more)
-            if (buffered) { if (j < MT_N) vals[used + j] = ok ? v : MT_REJECT; }
-            else if (ok) atomicAdd(&mult[v], 1);
+            if (j < L) {
+#pragma unroll
+                for (int t = 0; t < 3; ++t) {
+                    const int idx = j + t * L;
+                    if (idx < MT_N) {
+                        if (buffered) vals[used + idx] = ok[t] ? v[t] : MT_REJECT;
+                        else if (ok[t]) atomicAdd(&mult[v[t]], 1);
+                    }
+                }
+            }
             if (buffered) used += MT_N;
             acc += cnt;
             pos = MT_N;
             continue;
         }
-        // the n-th accepted output lies in this block: rank the accepted outputs in stream order
-        const unsigned bal = __ballot_sync(0xffffffffu, ok);
-        if (lane == 0) s_warp_cnt[warp] = __popc(bal);
+        // the n-th accepted output lies in this block: rank the accepted outputs in stream order (third by third)
+        unsigned bal[3];
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            bal[t] = __ballot_sync(0xffffffffu, ok[t]);
+            if (lane == 0) s_cnt[t][warp] = __popc(bal[t]);
+        }
         __syncthreads();
-        int before = __popc(bal & ((1u << lane) - 1u));
-        for (int wv = 0; wv < warp; ++wv) before += s_warp_cnt[wv];
-        const long long my_index = acc + before;        // 0-based index of this thread's sample, if accepted
-        if (ok && my_index < n) atomicAdd(&mult[v], 1);
-        if (ok && my_index == n - 1) s_newpos = j + 1;  // everything after it belongs to whoever draws next
+        long long base = acc;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            int before = __popc(bal[t] & ((1u << lane) - 1u));
+            for (int wv = 0; wv < warp; ++wv) before += s_cnt[t][wv];
+            const long long my_index = base + before;   // 0-based index of this sample, if accepted
+            if (ok[t] && my_index < n) atomicAdd(&mult[v[t]], 1);
+            if (ok[t] && my_index == n - 1) s_newpos = j + t * L + 1;   // everything after it belongs to whoever draws next
+            for (int wv = 0; wv < MT_THREADS / 32; ++wv) base += s_cnt[t][wv];
+        }
         __syncthreads();
         pos = s_newpos;
         break;
     }
-    if (j < MT_N) g_state[j] = mt[cur][j];
+    for (int i = j; i < MT_N; i += MT_THREADS) g_state[i] = mt[cur][i];
     if (j == 0) { *g_pos = pos; *g_used = used; }
 }
 
