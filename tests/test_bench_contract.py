@@ -56,3 +56,23 @@ def test_committed_engine_line_carries_every_contract_key():
     assert set(('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic')) <= set(r)
     assert abs(r['frac'] - r['achieved'] / r['peak']) < 1e-12 and 0.5 < r['frac'] < 1.0
     assert set(('value', 'unit', 'cores', 'kind', 'sample')) <= set(d['cpu_baseline'])
+
+
+def test_committed_round2_lines_carry_strong_scaling_and_parity():
+    """Round 2: the default line is the strong-scaling run of the target catalogue and every line (1, 2, 8 GPUs) carries the
+    parity block measured in that run, plus the sub-results the multi-GPU lines add."""
+    for name, n in (('r02_bench_1gpu_final.json', 1), ('r02_bench_2gpu_first.json', 2), ('r02_bench_8gpu.json', 8)):
+        d = json.loads(open(os.path.join(ROOT, 'profiles', name)).read().strip().splitlines()[-1])
+        assert d['n_gpus'] == n and d['scaling'] == 'strong' and d['config']['sources_total'] == 10000000
+        assert d['config']['sources_per_gpu'] * n == 10000000 and d['config']['walkers'] == 1024
+        p = d['parity']
+        assert p['ok'] is True and p['exchange']['ok'] and p['oracle_full_size']['ok'] and p['oracle_full_size']['max_rel'] < 1e-10
+        assert p['oracle_subshard']['walkers'] >= 8 and p['veff_counts_per_bin']['ok']
+        assert d['walker_sharded']['parity']['ok'] and d['e2e']['value'] != d['value'] and d['gpu_launches'] > 0
+        if n > 1:
+            assert d['weak']['sources_per_gpu'] == 10000000 and d['weak']['parity']['ok']
+            assert d['config4']['sources_total'] == 100000000 and d['config4']['walkers'] == 2048 and d['config4']['parity']['ok']
+    one = json.loads(open(os.path.join(ROOT, 'profiles', 'r02_bench_1gpu_final.json')).read().strip().splitlines()[-1])
+    eight = json.loads(open(os.path.join(ROOT, 'profiles', 'r02_bench_8gpu.json')).read().strip().splitlines()[-1])
+    assert eight['value'] > 1.0e12                               # the north_star target on its own configuration
+    assert 0.9 < eight['value'] / (8 * one['value']) <= 1.02     # strong-scaling efficiency
