@@ -413,8 +413,20 @@ class Bench:
                       and np.array_equal(res_e2e, res, equal_nan=True))
         ms_dev, ms_e2e = self.max_over_ranks([ms_dev, ms_e2e])
         like.close()
+        # the device-resident sampler on the same ensemble, walkers sharded over the ranks inside the captured update (the
+        # peer-memory exchange gathers the slices)
+        like_p = WalkerShardedLikelihood(inp, kind, device=self.local_rank, precision=self.args.precision, exchange='p2p', wcap=W)
+        like_p.sampler_run(thetas, 2, seed=3)
+        self.sync_all()
+        nupd = 10
+        run = like_p.sampler_run(thetas, nupd, seed=3)
+        ms_upd = self.max_over_ranks([run['device_ms'] / nupd])[0]
+        like_p.close()
         terms = float(n) * W
         return {"workload": "walker-sharded: %g sources on every GPU x %d walkers, W / N walkers per GPU, one all-gather of W doubles" % (n, W),
+                "device_sampler": {"ms_per_update": ms_upd, "updates_per_s": 1e3 / ms_upd,
+                                   "note": "lf_sampler_run with walker sharding: two half-ensemble lnprob calls per update, slices "
+                                           "gathered by the peer-memory exchange inside the CUDA graph"},
                 "sources": int(n), "walkers": W, "steps": steps, "value": terms * steps / (ms_dev * 1e-3), "unit": "terms/s",
                 "ms_per_step": ms_dev / steps,
                 "e2e": {"value": terms * steps / (ms_e2e * 1e-3), "unit": "terms/s", "ms_per_step": ms_e2e / steps},

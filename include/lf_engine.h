@@ -259,6 +259,13 @@ int lf_omega_sources(int32_t device, int64_t n, const double* lum, const double*
 int lf_sampler_run(lf_ctx* ctx, const double* pos0, int64_t W, int64_t nsteps, uint64_t seed, double a, int64_t step0,
                    double* chain, double* lnprob, int64_t* naccepted, double* pos_out, double* lnprob_out);
 
+/* Several ranks, small catalogue (SURVEY.md 8e "shard walkers when the source count is small"): every rank holds ALL sources
+ * (lf_set_sources with the whole catalogue, quadrature share (0, 1)) and, with walker sharding enabled and the peer buffers
+ * connected, lf_sampler_run lets rank r evaluate walkers [nw r / world, nw (r + 1) / world) of every half-ensemble; the other
+ * entries are exact zeros, so the rank-ordered sum of lf_allreduce_device is the all-gather of the slices.  Every rank ends
+ * with the same chain. */
+int lf_set_walker_sharding(lf_ctx* ctx, int32_t enabled);
+
 /* Device time (ms) of the nsteps graph replays of the last lf_sampler_run call. */
 int lf_sampler_last_ms(lf_ctx* ctx, double* ms);
 

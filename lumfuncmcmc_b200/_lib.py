@@ -19,7 +19,7 @@ EXPORTS = ['lf_ndim', 'lf_create', 'lf_destroy', 'lf_set_sources', 'lf_set_grid'
            'lf_lnprob_batch', 'lf_lnprob_batch_device', 'lf_last_call_info', 'lf_veff_bin', 'lf_bin_weights', 'lf_boot_bin', 'lf_boot_bin_device',
            'lf_fp64_peak', 'lf_mufu_peak', 'lf_last_kernel_ms', 'lf_sampler_run', 'lf_sampler_last_ms', 'lf_cosmo_distances', 'lf_interp_linear', 'lf_device_count', 'lf_peer_buffer_create', 'lf_peer_buffer_connect',
            'lf_allreduce_device', 'lf_peer_status', 'lf_peer_reset', 'lf_peer_set_timeout', 'lf_veff_set_sample', 'lf_veff_bin_resident',
-           'lf_veff_get_phi', 'lf_veff_set_volume_table', 'lf_veff_volumes', 'lf_omega_sources', 'lf_boot_mt_set_state', 'lf_boot_mt_get_state', 'lf_boot_bin_mt', 'lf_last_error', 'lf_version']
+           'lf_veff_get_phi', 'lf_veff_set_volume_table', 'lf_veff_volumes', 'lf_omega_sources', 'lf_set_walker_sharding', 'lf_boot_mt_set_state', 'lf_boot_mt_get_state', 'lf_boot_bin_mt', 'lf_last_error', 'lf_version']
 
 
 class LFCosmology(C.Structure):
@@ -77,6 +77,7 @@ def load():
     lib.lf_set_compressed_sources.argtypes = [vp, i64, vp, vp, vp, C.c_double]
     lib.lf_sampler_run.argtypes = [vp, vp, i64, i64, C.c_uint64, C.c_double, i64, vp, vp, vp, vp, vp]
     lib.lf_sampler_last_ms.argtypes = [vp, dp]
+    lib.lf_set_walker_sharding.argtypes = [vp, C.c_int32]
     lib.lf_cosmo_distances.argtypes = [C.c_int32, vp, vp, i64, i64, vp, vp, vp]
     lib.lf_interp_linear.argtypes = [C.c_int32, i64, vp, vp, i64, vp, vp]
     lib.lf_omega_sources.argtypes = [C.c_int32, i64, vp, vp, vp, C.c_int32, vp, vp, C.c_double, C.c_double, i64, vp, vp, vp]

@@ -291,6 +291,7 @@ struct lf_ctx {
     cudaEvent_t ev_scratch = nullptr; cudaStream_t scratch_stream = nullptr; bool scratch_pending = false;
     // peer exchange
     unsigned char* peer_base = nullptr; unsigned* peer_seq = nullptr; int* peer_timeout = nullptr; int* peer_timeout_h = nullptr;
+    bool walker_shard = false;         // lf_sampler_run over several ranks: shard walkers (all sources on every rank) instead of sources
     size_t peer_data_bytes = 0; bool peer_connected = false; void* peer_opened[PEER_MAX] = {};
     PeerArgs peer;
 };

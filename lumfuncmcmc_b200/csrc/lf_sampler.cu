@@ -118,8 +118,16 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
     // summed by the peer-memory kernel inside the captured update (identical bits on every rank keep the chains equal)
     const bool exchange = c->peer_connected && c->peer.world > 1;
     if (exchange && W > c->peer.wcap) { fail("lf_sampler_run: more walkers than the peer buffers hold"); return cleanup(); }
+    // walker sharding (small catalogues, every rank holds ALL sources): a rank evaluates only its slice of the walkers and
+    // contributes exact zeros for the others, so the same rank-ordered sum over ranks IS the all-gather of the slices
+    // (x + 0 = x bit for bit, -inf + 0 = -inf) and the exchange kernel, its flags and the captured graph stay as they are
+    const bool wshard = exchange && c->walker_shard;
     auto lnprob_all_ranks = [&](const double* th, long long nw, double* out) -> int {
-        if (launch_pipeline(c, th, nw, out, st)) return 1;
+        if (wshard) {
+            const long long lo = nw * c->peer.rank / c->peer.world, hi = nw * (c->peer.rank + 1) / c->peer.world;
+            if (cudaMemsetAsync(out, 0, sizeof(double) * nw, st) != cudaSuccess) return fail("lf_sampler_run: cudaMemsetAsync failed");
+            if (hi > lo && launch_pipeline(c, th + lo * ndim, hi - lo, out + lo, st)) return 1;
+        } else if (launch_pipeline(c, th, nw, out, st)) return 1;
         if (exchange) {
             if (peer_allreduce_launch(c, out, nw, st)) return 1;
         }
@@ -182,6 +190,13 @@ extern "C" int lf_sampler_run(lf_ctx* c, const double* pos0, int64_t W, int64_t 
 #undef SCK
     rc = 0;
     return cleanup();
+}
+
+extern "C" int lf_set_walker_sharding(lf_ctx* c, int32_t enabled) {
+    if (!c) return fail("lf_set_walker_sharding: null context");
+    if (enabled && (c->ka.nshare != 1)) return fail("lf_set_walker_sharding: a walker-sharded context integrates every walker's quadrature (quadrature share must be (0, 1))");
+    c->walker_shard = enabled != 0;
+    return 0;
 }
 
 extern "C" int lf_sampler_last_ms(lf_ctx* c, double* ms) {

@@ -84,7 +84,7 @@ class WalkerShardedLikelihood:
     exactly as a single-GPU call on that slice would (the slab partition of the sources depends on the number of walkers
     in the call, so the bits can differ from a full-ensemble call in the last place, ~1e-16 relative)."""
 
-    def __init__(self, inp, kind, device=None, group=None, precision='f64'):
+    def __init__(self, inp, kind, device=None, group=None, precision='f64', exchange='nccl', wcap=4096):
         import torch
         import torch.distributed as dist
         from .engine import LikelihoodEngine
@@ -94,6 +94,30 @@ class WalkerShardedLikelihood:
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.engine = LikelihoodEngine(inp, kind, device=self.device, precision=precision)
         self.ndim = self.engine.ndim
+        if exchange not in ('nccl', 'p2p'):
+            raise ValueError("exchange must be 'nccl' or 'p2p'")
+        # 'p2p': the engine's peer-memory kernel gathers the slices (each rank contributes zeros outside its own), which is
+        # what lets the device-resident sampler run walker-sharded inside its captured graphs (sampler_run)
+        self.exchange = exchange if self.world > 1 else 'nccl'
+        self.wcap = int(wcap)
+        if self.exchange == 'p2p':
+            handle = self.engine.peer_buffer_create(self.rank, self.world, self.wcap)
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (handle, self.rank, self.world, self.wcap), group=group)
+            check_peer_geometry(gathered, self.world, self.wcap)
+            self.engine.peer_buffer_connect([g[0] for g in gathered])
+            self.engine.set_walker_sharding(True)
+            dist.barrier(group=group)
+
+    def sampler_run(self, pos0, nsteps, seed, a=2.0, step0=0):
+        """Device-resident ensemble run with the walkers of every half-ensemble sharded over the ranks (all ranks get the
+        same chain).  More than one rank needs ``exchange='p2p'``."""
+        if self.world > 1 and self.exchange != 'p2p':
+            raise RuntimeError("the walker-sharded device-resident sampler needs exchange='p2p'")
+        out = self.engine.sampler_run(pos0, nsteps, seed, a=a, step0=step0)
+        if self.exchange == 'p2p' and self.engine.peer_timed_out():
+            raise RuntimeError("peer-memory all-reduce timed out waiting for another rank")
+        return out
 
     def lnprob_device(self, d_thetas, d_out=None):
         """Device-resident call on torch's current stream: this rank's slice of ``d_thetas`` (all W rows, identical on
@@ -103,6 +127,15 @@ class WalkerShardedLikelihood:
         lo, hi = walker_slice(W, self.rank, self.world)
         if self.world == 1:
             return self.engine.lnprob_device(d_thetas, d_out)
+        if self.exchange == 'p2p':
+            if self.engine.peer_timed_out():
+                raise RuntimeError("peer-memory all-reduce timed out waiting for another rank; results since then are NaN")
+            if W > self.wcap:
+                raise ValueError("more walkers (%d) than the peer buffers hold (wcap=%d)" % (W, self.wcap))
+            full = t.zeros(W, dtype=t.float64, device=d_thetas.device) if d_out is None else d_out.zero_()
+            if hi > lo:
+                self.engine.lnprob_device(d_thetas[lo:hi], full[lo:hi])
+            return self.engine.allreduce_device(full)          # x + 0 = x: the rank-ordered sum is the all-gather
         local = self.engine.lnprob_device(d_thetas[lo:hi]) if hi > lo else t.zeros(0, dtype=t.float64, device=d_thetas.device)
         full = gather_walker_results(local, W, self.group)
         if d_out is not None:
@@ -115,6 +148,13 @@ class WalkerShardedLikelihood:
         th = np.ascontiguousarray(np.atleast_2d(np.asarray(thetas, dtype=np.float64)))
         W = th.shape[0]
         lo, hi = walker_slice(W, self.rank, self.world)
+        if self.world > 1 and self.exchange == 'p2p':
+            with t.cuda.device(self.device):
+                d_th = t.from_numpy(th).to(t.device('cuda', self.device))
+                out = self.lnprob_device(d_th).cpu().numpy()
+            if self.engine.peer_timed_out():
+                raise RuntimeError("peer-memory all-reduce timed out waiting for another rank")
+            return out
         mine = self.engine.lnprob(th[lo:hi]) if hi > lo else np.zeros(0)
         if self.world == 1:
             return mine

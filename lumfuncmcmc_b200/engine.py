@@ -380,6 +380,11 @@ class LikelihoodEngine(_VeffOps):
         _lib.check(self.lib.lf_sampler_last_ms(self._ctx, C.byref(ms)), self.lib)
         return dict(chain=chain, lnprob=lnp, naccepted=nacc, pos=pos, lp=lp, device_ms=ms.value)
 
+    def set_walker_sharding(self, enabled=True):
+        """Several ranks, every rank holding all sources: ``sampler_run`` evaluates this rank's slice of each half-ensemble
+        and the peer-memory exchange gathers the slices (``lf_set_walker_sharding``)."""
+        _lib.check(self.lib.lf_set_walker_sharding(self._ctx, int(bool(enabled))), self.lib)
+
     # ---- peer-memory exchange (multi-GPU without NCCL on the data path) ----
     def peer_buffer_create(self, rank, world, wcap):
         """Allocate this rank's receive buffer; returns its 64-byte CUDA IPC handle (bytes)."""

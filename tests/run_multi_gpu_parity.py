@@ -11,7 +11,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from lumfuncmcmc_b200 import synth                          # noqa: E402
-from lumfuncmcmc_b200.dist import ShardedLikelihood, shard_inputs   # noqa: E402
+from lumfuncmcmc_b200.dist import ShardedLikelihood, WalkerShardedLikelihood, shard_inputs   # noqa: E402
 from lumfuncmcmc_b200.engine import LikelihoodEngine        # noqa: E402
 
 rank, world, local = int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), int(os.environ['LOCAL_RANK'])
@@ -48,6 +48,23 @@ for kind in ('free', 'fixed', 'z'):
         chain_ok = all(g == g2[0] for g in g2) and np.array_equal(run['chain'], ref_chain) and np.array_equal(run['lnprob'], ref_lnp)
     p2p_ok = p2p_ok and chain_ok
     p2p.close()
+    # walker sharding (every rank holds all sources): lnprob through NCCL all-gather and through the peer-memory exchange
+    # equals one engine; the walker-sharded device-resident sampler gives the same chain on every rank = its host replay
+    ws_n = WalkerShardedLikelihood(inp, kind, device=local)
+    ws_p = WalkerShardedLikelihood(inp, kind, device=local, exchange='p2p', wcap=256)
+    got_wn, got_wp = ws_n.lnprob(th), ws_p.lnprob(th)
+    ws_ok = np.array_equal(got_wn, got_wp, equal_nan=True)
+    ws_chain_ok = True
+    if kind != 'fixed':
+        from lumfuncmcmc_b200.sampler import philox_stretch_reference
+        p0 = synth.draw_thetas(inp, kind, 64, seed=8, mode='near', scale=0.01)
+        run = ws_p.sampler_run(p0, 12, seed=77)
+        ref_chain, ref_lnp, _ = philox_stretch_reference(ws_p.lnprob, p0, 12, 77)
+        g3 = [None] * world
+        dist.all_gather_object(g3, run['chain'].tobytes())
+        ws_chain_ok = all(g == g3[0] for g in g3) and np.array_equal(run['chain'], ref_chain) and np.array_equal(run['lnprob'], ref_lnp)
+    ws_n.close()
+    ws_p.close()
     if rank == 0:
         from oracle import lf_oracle
         single = LikelihoodEngine(inp, kind, device=local)
@@ -61,7 +78,12 @@ for kind in ('free', 'fixed', 'z'):
         print("%s: world=%d  -inf sets equal=%s  max rel vs single GPU %.2e  vs oracle %.2e   peer-memory exchange: identical on "
               "all ranks=%s, max rel vs NCCL %.2e, multi-GPU device sampler chain == host replay on all ranks: %s"
               % (kind, world, same_inf, rel, rel_o, same_everywhere, rel_p, chain_ok))
-        ok = ok and same_inf and rel < 1e-12 and rel_o < 1e-10 and p2p_ok
+        with np.errstate(invalid='ignore'):
+            rel_w = np.max(np.abs(got_wp[fin] - one[fin]) / np.abs(one[fin]))
+        ws_all = ws_ok and ws_chain_ok and np.array_equal(np.isneginf(got_wp), np.isneginf(one)) and rel_w < 1e-13
+        print("   walker-sharded: NCCL all-gather == peer-memory gather: %s, max rel vs one engine %.2e, walker-sharded device sampler "
+              "chain == host replay on all ranks: %s" % (ws_ok, rel_w, ws_chain_ok))
+        ok = ok and same_inf and rel < 1e-12 and rel_o < 1e-10 and p2p_ok and ws_all
         single.close()
     like.close()
     dist.barrier()
