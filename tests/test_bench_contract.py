@@ -61,7 +61,7 @@ def test_committed_engine_line_carries_every_contract_key():
 def test_committed_round2_lines_carry_strong_scaling_and_parity():
     """Round 2: the default line is the strong-scaling run of the target catalogue and every line (1, 2, 8 GPUs) carries the
     parity block measured in that run, plus the sub-results the multi-GPU lines add."""
-    for name, n in (('r02_bench_1gpu_final.json', 1), ('r02_bench_2gpu_first.json', 2), ('r02_bench_8gpu.json', 8)):
+    for name, n in (('r02_bench_1gpu_final.json', 1), ('r02_bench_2gpu.json', 2), ('r02_bench_8gpu.json', 8)):
         d = json.loads(open(os.path.join(ROOT, 'profiles', name)).read().strip().splitlines()[-1])
         assert d['n_gpus'] == n and d['scaling'] == 'strong' and d['config']['sources_total'] == 10000000
         assert d['config']['sources_per_gpu'] * n == 10000000 and d['config']['walkers'] == 1024
