@@ -273,7 +273,11 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
     // FREE / Z fast kernels: a source item covers TWO walkers per lane (64 per warp), so every broadcast source load
     // (16 B x 32 lanes = 4 wavefronts of the load-store data path, the busiest unit of these loops) feeds two terms
     constexpr bool PAIR = (MODEL == LF_MODEL_Z || MODEL == LF_MODEL_FREE) && !LITERAL;
-    const int n_wg = PAIR ? (count_src + 63) >> 6 : (count_src + 31) >> 5;      // n_wg == 0: n_items == 0, the loop exits at once
+    // Literal source items take ONE walker each and spread the slab's sources over the 32 lanes (fixed shuffle tree at the
+    // end): the literal class is small (a handful of walkers during burn-in, none afterwards), so one walker per lane would
+    // leave most of every warp idle while each term costs ~25x a fast one.
+    constexpr bool LANE_SRC = LITERAL;
+    const int n_wg = LANE_SRC ? count_src : (PAIR ? (count_src + 63) >> 6 : (count_src + 31) >> 5);   // n_wg == 0: no source items
     const int n_wgq = (count_quad + 31) >> 5;
     const long long n_src_items = (long long)n_wg * a.n_src_slabs;
     const long long n_items = n_src_items + (long long)n_wgq * a.n_quad_slabs;
@@ -307,8 +311,9 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
     const int row = (int)(it / groups) + (is_src ? 0 : a.n_src_slabs);
     const int count = is_src ? count_src : count_quad;
     const int* list = is_src ? (LITERAL ? a.list_lit : a.list_fast) : (LITERAL ? a.list_litq : a.list_fastq);
-    const int slot = (PAIR && is_src ? wg * 64 : wg * 32) + lane;
+    const int slot = (LANE_SRC && is_src) ? wg : (PAIR && is_src ? wg * 64 : wg * 32) + lane;
     const bool active = slot < count;
+    const int lstep = (LANE_SRC && is_src) ? 32 : 1, loff = (LANE_SRC && is_src) ? lane : 0;   // literal source loops: lane-strided
     const long long w = list[active ? slot : count - 1];       // inactive lanes shadow a valid walker
     const double* wp = a.wp + w;
     const bool activeB = PAIR && is_src && slot + 32 < count;   // second walker of the lane (Z source items)
@@ -500,7 +505,7 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
                         const double F50 = wp[(P_FIELD0 + 4 * k + 2) * WS], ftau = wp[(P_FIELD0 + 4 * k + 3) * WS];
                         const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
                         const double om = a.fs[k].om0_over_sq;
-                        for (long long i = i0; i < seg_end; ++i) {
+                        for (long long i = i0 + loff; i < seg_end; i += lstep) {
                             double phi = schechter_literal(__ldg(&a.lum[i]), sal, Lstar, phistar);
                             double Om = om * fleming_literal(__ldg(&a.flux[i]), F50, alpha, ftau, a.modified != 0);
                             acc0 += log(phi * Om);
@@ -516,7 +521,7 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
             // fast class: the whole source sum is in P_LNPART0 (sufficient statistics); literal class sums terms
             if (LITERAL) {
                 const double Lstar = wp[P_LSTAR * WS], phistar = wp[P_PHISTAR * WS], sal = wp[P_SCHAL * WS];
-                for (long long i = i0; i < i1; ++i)                                   // lumfuncmcmc.py:388
+                for (long long i = i0 + loff; i < i1; i += lstep)                     // lumfuncmcmc.py:388
                     acc0 += log(schechter_literal(__ldg(&a.lum[i]), sal, Lstar, phistar) * __ldg(&a.om_arr[i]));
             }
         } else {
@@ -615,7 +620,7 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
                 accB = -scaleB * (f0 + f1);
             } else {
                 const double aP = wp[P_AP * WS], bP = wp[P_BP * WS], cP = wp[P_CP * WS], sal = wp[P_SCHAL * WS];
-                for (long long i = i0; i < i1; ++i) {                                 // lumfuncmcmc_z.py:371
+                for (long long i = i0 + loff; i < i1; i += lstep) {                   // lumfuncmcmc_z.py:371
                     double z = __ldg(&a.z[i]);
                     double ps = aP * z * z + bP * z + cP, Ls = aL * z * z + bL * z + cL;
                     acc0 += log(schechter_literal(__ldg(&a.lum[i]), sal, Ls, ps) * __ldg(&a.om_arr[i]));
@@ -758,8 +763,14 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(
             }
         }
     }
-    if (active) a.partial[(long long)row * WS + w] = acc0 + acc1;
-    if (PAIR && activeB) a.partial[(long long)row * WS + wB] = accB;
+    if (LANE_SRC && is_src) {
+        double v = acc0 + acc1;                                              // lanes hold disjoint sources of ONE walker
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) a.partial[(long long)row * WS + w] = v;
+    } else {
+        if (active) a.partial[(long long)row * WS + w] = acc0 + acc1;
+        if (PAIR && activeB) a.partial[(long long)row * WS + wB] = accB;
+    }
   }
 }
 
@@ -1398,7 +1409,9 @@ int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_ou
     const int wpb = main_warps(c->cfg.model);
     const long long need = (items + wpb - 1) / wpb;      // never more blocks than items
     const unsigned bf = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_fast);
-    const unsigned bl = (unsigned)std::min<long long>(need, (long long)c->sm_count * c->occ_lit);
+    // literal source items are one WALKER (not one group of 32) x one slab each: up to W n_src of them
+    const long long need_lit = (W * n_src + n_wg * n_quad + wpb - 1) / wpb;
+    const unsigned bl = (unsigned)std::min<long long>(need_lit, (long long)c->sm_count * c->occ_lit);
     {
         // fast kernel: launched programmatically dependent on the kernel before it (prologue, or k_zcolumns for the Z model)
         cudaLaunchConfig_t lc;
