@@ -154,7 +154,7 @@ __global__ void k_prologue(KArgs a) {
             double fmn = fmin(s.n > 0.0 ? s.f_min : 1.0e300, s.grid_f_min);
             if (!(alpha_c * (gmin - lgF) > (a.precision == LF_PREC_F32 ? -12.0 : N_MIN_SAFE))) rok = 0;
             if (a.modified && !(fmn / ftau > X_MIN_SAFE)) rok = 0;
-            if (a.modified && !(a.fcap / ftau < 5.0e6)) rok = 0;      // exp range reduction stays in int32
+            if (a.modified && !(a.fcap / ftau < 7.0e5)) rok = 0;      // round(2048 log2(e) f / ftau) of the exp range reduction stays in int32
             if (s.n > 0.0) tmin = log(fleming_literal(s.f_min, F50, alpha_c, ftau, a.modified != 0));
             lnom = s.ln_om0;
         }
@@ -250,8 +250,10 @@ __device__ __forceinline__ int field_of(const KArgs& a, long long i) {
 }
 
 // One instantiation per (class, model): each model's loop gets its own register allocation and instruction schedule.
+// The literal kernels are chains of dependent libdevice calls (~1150 instructions per term, ncu: IPC 0.2 with 12 warps per SM):
+// they want warps, not registers, so the free-completeness one is held to two resident blocks per SM.
 template <bool LITERAL, int MODEL>
-__global__ void __launch_bounds__(32 * main_warps(MODEL), LF_MIN_BLOCKS) k_main(KArgs a) {
+__global__ void __launch_bounds__(32 * main_warps(MODEL), (LITERAL && MODEL == LF_MODEL_FREE) ? 2 : LF_MIN_BLOCKS) k_main(KArgs a) {
     extern __shared__ __align__(16) unsigned char smem_tables[];       // fast kernels only (main_smem_bytes(MODEL))
     double2* s_log = reinterpret_cast<double2*>(smem_tables);          // FREE: log table; Z / FIXED: the replicated exp table
     double* s_exp = reinterpret_cast<double*>(s_log + LOG_TAB_N * LOG_TAB_REP);     // FREE only

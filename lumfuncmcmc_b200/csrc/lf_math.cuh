@@ -63,6 +63,13 @@ constexpr double LOG1P_C0 = 4.5474875525573243324e-13;             // folded int
 constexpr double LOG1P_C1 = 0.9999999999985449674, LOG1P_C2 = -0.50000095367660766342, LOG1P_C3 = 0.33333447770293183222;
 constexpr double EXP2_C0 = 0.99999999999998250473, EXP2_C1 = 0.69314718055993561091, EXP2_C2 = 0.24022654364935376114,
                  EXP2_C3 = 0.055504116293577099979;
+// One-look-up decay factor 2^(x2), x2 <= 0 (big table): the reduction constant 1.5 * 2^41 leaves round(2048 x2) in the low
+// mantissa word; with its low three bits masked off (a LOP3, which issues in the shadow of a DFMA) that word IS the byte
+// offset of the table entry 2^(m / 256), m = floor(round(2048 x2) / 8) -- no shift -- and the same masked double gives m / 256
+// for the remainder r = x2 - m / 256 in [-2^-12, 15 * 2^-12): minimax degree 3 on that interval, 1.75e-14 (fit_coeffs.py).
+constexpr double MAGIC41 = 3298534883328.0;                        // 1.5 * 2^41: ulp 2^-11
+constexpr double EXP2B_C0 = 1.000000000000007627, EXP2B_C1 = 0.69314718062664656388, EXP2B_C2 = 0.24022637497468078452,
+                 EXP2B_C3 = 0.055569904189805140222;
 static __constant__ double KC[16] = {
     MAGIC44,                // 0
     EXP2_C3,                // 1
@@ -73,7 +80,12 @@ static __constant__ double KC[16] = {
     LOG1P_C2,               // 6
     LOG1P_C1,               // 7
     LOG2E,                  // 8
-    0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    MAGIC41,                // 9
+    EXP2B_C3,               // 10
+    EXP2B_C2,               // 11
+    EXP2B_C1,               // 12
+    EXP2B_C0,               // 13
+    0.0, 0.0};
 
 struct __align__(16) Tables {    // device-global master copies (filled by the host at lf_create)
     double exp2_frac[EXP_TAB_N];        // 2^(j/256)
@@ -144,14 +156,15 @@ __device__ __forceinline__ void exp2_parts(double a, double b, const double* s_e
 __device__ __forceinline__ double one_minus_exp2(double f, double c2, const double* s_exp, int rep) {
     double Ts, p;
 #if LF_EXP_BIG
-    double t = fma(f, c2, KC[0]);
-    int k = max(__double2loint(t), EXPB_KMIN);    // round(256 x2), clamped: 2^-40 is 0 against 1 at the budget of this routine
-    double kf = t - KC[0];
+    double t = fma(f, c2, KC[9]);
+    const int k8 = __double2loint(t) & ~7;        // 8 * floor(round(2048 x2) / 8): byte offset of the entry, from the table's end
+    double kf = __hiloint2double(__double2hiint(t), k8) - KC[9];
     double r = fma(f, c2, -kf);
-    Ts = s_exp[k - EXPB_KMIN];
-    p = fma(r, KC[1], KC[2]);
-    p = fma(r, p, KC[3]);
-    p = fma(r, p, KC[4]);
+    // clamped: 2^-40 is 0 against 1 at the budget of this routine (needs |x2| < 2^20: the classifier's fcap / ftau bound)
+    Ts = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (max(k8, 8 * EXPB_KMIN) - 8 * EXPB_KMIN));
+    p = fma(r, KC[10], KC[11]);
+    p = fma(r, p, KC[12]);
+    p = fma(r, p, KC[13]);
 #else
     exp2_parts<false>(f, c2, s_exp, rep, -1000, Ts, p);  // 2^x2 < 2^-1000 is 0 against 1
 #endif
@@ -231,7 +244,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) n[i] = fma(al[i], ux[i], af[i]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) t[i] = fma(uy[i], cc[i], KC[0]);
+    for (int i = 0; i < NT; ++i) t[i] = fma(uy[i], cc[i], LF_EXP_BIG ? KC[9] : KC[0]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = fma(n[i], n[i], 1.0);
 #pragma unroll
@@ -239,13 +252,18 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
     // exp branch while the MUFUs are in flight
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
+#if LF_EXP_BIG
+        k[i] = __double2loint(t[i]) & ~7;
+        t[i] = __hiloint2double(__double2hiint(t[i]), k[i]) - KC[9];
+#else
         k[i] = __double2loint(t[i]);
         t[i] = t[i] - KC[0];
+#endif
     }
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
 #if LF_EXP_BIG
-        Ts[i] = s_exp[max(k[i], EXPB_KMIN) - EXPB_KMIN];
+        Ts[i] = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (max(k[i], 8 * EXPB_KMIN) - 8 * EXPB_KMIN));
 #else
         double T = s_exp[(k[i] & (EXP_TAB_N - 1)) * EXP_TAB_REP + repe];
         int K = max(k[i] >> EXP_TAB_BITS, -1000);
@@ -255,7 +273,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) r[i] = fma(uy[i], cc[i], -t[i]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], KC[1], KC[2]);
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], LF_EXP_BIG ? KC[10] : KC[1], LF_EXP_BIG ? KC[11] : KC[2]);
     // rsqrt correction
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = y[i] * r0[i];
@@ -266,11 +284,11 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = fma(0.375, e[i], 0.5);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], KC[3]);
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], LF_EXP_BIG ? KC[12] : KC[3]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) e[i] = y[i] * e[i];
 #pragma unroll
-    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], KC[4]);
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], LF_EXP_BIG ? KC[13] : KC[4]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) q[i] = fma(n[i], e[i], n[i]);
 #pragma unroll

@@ -32,7 +32,38 @@ def remez(f, powers, h, iters=12, ngrid=4001):
     return [c[k] / h ** p for k, p in enumerate(powers)], emax
 
 
+def remez_ab(f, deg, a, b, iters=14, ngrid=4001):
+    """minimax fit of f(x) ~ sum_k c_k x^k on [a, b] (absolute error), coefficients in x itself; returns (c, max_err)."""
+    m = deg + 1
+    mid, h = (a + b) / 2, (b - a) / 2
+    u = [-mp.cos(mp.pi * i / m) for i in range(m + 1)]
+    grid = [mp.mpf(-1) + mp.mpf(2) * i / (ngrid - 1) for i in range(ngrid)]
+    fg = [f(mid + h * g) for g in grid]
+    c, err = None, None
+    for _ in range(iters):
+        A = mp.matrix(m + 1, m + 1)
+        b_ = mp.matrix(m + 1, 1)
+        for i, ui in enumerate(u):
+            x = mid + h * ui
+            for k in range(m):
+                A[i, k] = x ** k
+            A[i, m] = (-1) ** i
+            b_[i] = f(x)
+        sol = mp.lu_solve(A, b_)
+        c = [sol[k] for k in range(m)]
+        err = [sum(c[k] * (mid + h * g) ** k for k in range(m)) - fg[i] for i, g in enumerate(grid)]
+        ext = [0] + [i for i in range(1, ngrid - 1) if (err[i] - err[i - 1]) * (err[i + 1] - err[i]) <= 0] + [ngrid - 1]
+        ext = sorted(sorted(ext, key=lambda i: -abs(err[i]))[:m + 1])
+        if len(ext) == m + 1:
+            u = [grid[i] for i in ext]
+    return c, max(abs(e) for e in err)
+
+
 if __name__ == '__main__':
+    # decay factor of the free-completeness loop (EXP2B_*): the remainder after the masked-index look-up lies in [-2^-12, 15 2^-12)
+    c, e = remez_ab(lambda x: mp.power(2, x), 3, -mp.mpf(2) ** -12, 15 * mp.mpf(2) ** -12)
+    print("2^x degree 3 on [-2^-12, 15 * 2^-12]: max abs err %s" % mp.nstr(e, 3))
+    print("    " + ", ".join(mp.nstr(v, 20) for v in c))
     h = mp.mpf(2) ** -9
     for name, f in (("log1p(x)", mp.log1p), ("2^x", lambda x: mp.power(2, x))):
         for deg in (3, 4):
