@@ -296,7 +296,7 @@ class Bench:
         return ev0.elapsed_time(ev1), t_begin, time.time()
 
     def time_e2e(self, like, thetas, steps):
-        for _ in range(2):
+        for _ in range(3):
             like.lnprob(thetas)
         self.sync_all()
         t0 = time.perf_counter()
