@@ -41,6 +41,11 @@ constexpr double MPC_CM_REF = 3.086e24;                             // the refer
 #ifndef LF_EXP_BIG
 #define LF_EXP_BIG 1
 #endif
+#ifndef LF_EXP_MASKED
+#define LF_EXP_MASKED 0      /* big table: index = shifted integer (0, default) or masked low mantissa word (1): the masked
+                                form saves a shift per term and is 1.4 % faster for the loop in isolation, but the product kernel
+                                measures 0.3 % SLOWER with it (6.068 vs 6.085e11 terms/s, three alternating runs each) */
+#endif
 constexpr int EXP_TAB_BITS = 8, EXP_TAB_N = 1 << EXP_TAB_BITS, EXP_TAB_REP = LF_EXP_REP;   // small table: 256*16*8 B = 32 KB, replicated x16 (a half-warp never bank-conflicts)
 // LF_EXP_BIG: one unreplicated table of 2^(k/256) for k = EXPB_KMIN .. 0 (80 KB): the decay factor 2^(x2), x2 <= 0, is a
 // single look-up with the integer k clamped at -40*256 (2^-40 = 9e-13 against 1, times |ln fc| < 0.01 for a source that
@@ -63,7 +68,7 @@ constexpr double LOG1P_C0 = 4.5474875525573243324e-13;             // folded int
 constexpr double LOG1P_C1 = 0.9999999999985449674, LOG1P_C2 = -0.50000095367660766342, LOG1P_C3 = 0.33333447770293183222;
 constexpr double EXP2_C0 = 0.99999999999998250473, EXP2_C1 = 0.69314718055993561091, EXP2_C2 = 0.24022654364935376114,
                  EXP2_C3 = 0.055504116293577099979;
-// One-look-up decay factor 2^(x2), x2 <= 0 (big table): the reduction constant 1.5 * 2^41 leaves round(2048 x2) in the low
+// LF_EXP_MASKED variant of the one-look-up decay factor 2^(x2), x2 <= 0 (big table): the reduction constant 1.5 * 2^41 leaves round(2048 x2) in the low
 // mantissa word; with its low three bits masked off (a LOP3, which issues in the shadow of a DFMA) that word IS the byte
 // offset of the table entry 2^(m / 256), m = floor(round(2048 x2) / 8) -- no shift -- and the same masked double gives m / 256
 // for the remainder r = x2 - m / 256 in [-2^-12, 15 * 2^-12): minimax degree 3 on that interval, 1.75e-14 (fit_coeffs.py).
@@ -155,7 +160,16 @@ __device__ __forceinline__ void exp2_parts(double a, double b, const double* s_e
 // 1 - 2^(f * c2) for f * c2 in (-8.3e6, 0]; ABSOLUTE accuracy ~2e-14.  FP64 instructions: 7
 __device__ __forceinline__ double one_minus_exp2(double f, double c2, const double* s_exp, int rep) {
     double Ts, p;
-#if LF_EXP_BIG
+#if LF_EXP_BIG && !LF_EXP_MASKED
+    double t = fma(f, c2, KC[0]);
+    int k = max(__double2loint(t), EXPB_KMIN);    // round(256 x2), clamped: 2^-40 is 0 against 1 at the budget of this routine
+    double kf = t - KC[0];
+    double r = fma(f, c2, -kf);
+    Ts = s_exp[k - EXPB_KMIN];
+    p = fma(r, KC[1], KC[2]);
+    p = fma(r, p, KC[3]);
+    p = fma(r, p, KC[4]);
+#elif LF_EXP_BIG
     double t = fma(f, c2, KC[9]);
     const int k8 = __double2loint(t) & ~7;        // 8 * floor(round(2048 x2) / 8): byte offset of the entry, from the table's end
     double kf = __hiloint2double(__double2hiint(t), k8) - KC[9];
@@ -244,7 +258,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) n[i] = fma(al[i], ux[i], af[i]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) t[i] = fma(uy[i], cc[i], LF_EXP_BIG ? KC[9] : KC[0]);
+    for (int i = 0; i < NT; ++i) t[i] = fma(uy[i], cc[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[9] : KC[0]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = fma(n[i], n[i], 1.0);
 #pragma unroll
@@ -252,7 +266,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
     // exp branch while the MUFUs are in flight
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-#if LF_EXP_BIG
+#if LF_EXP_BIG && LF_EXP_MASKED
         k[i] = __double2loint(t[i]) & ~7;
         t[i] = __hiloint2double(__double2hiint(t[i]), k[i]) - KC[9];
 #else
@@ -262,8 +276,10 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
     }
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-#if LF_EXP_BIG
+#if LF_EXP_BIG && LF_EXP_MASKED
         Ts[i] = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (max(k[i], 8 * EXPB_KMIN) - 8 * EXPB_KMIN));
+#elif LF_EXP_BIG
+        Ts[i] = s_exp[max(k[i], EXPB_KMIN) - EXPB_KMIN];
 #else
         double T = s_exp[(k[i] & (EXP_TAB_N - 1)) * EXP_TAB_REP + repe];
         int K = max(k[i] >> EXP_TAB_BITS, -1000);
@@ -273,7 +289,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) r[i] = fma(uy[i], cc[i], -t[i]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], LF_EXP_BIG ? KC[10] : KC[1], LF_EXP_BIG ? KC[11] : KC[2]);
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[10] : KC[1], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[11] : KC[2]);
     // rsqrt correction
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = y[i] * r0[i];
@@ -284,11 +300,11 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = fma(0.375, e[i], 0.5);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], LF_EXP_BIG ? KC[12] : KC[3]);
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[12] : KC[3]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) e[i] = y[i] * e[i];
 #pragma unroll
-    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], LF_EXP_BIG ? KC[13] : KC[4]);
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[13] : KC[4]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) q[i] = fma(n[i], e[i], n[i]);
 #pragma unroll

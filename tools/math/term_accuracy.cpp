@@ -12,11 +12,19 @@
 #include <cstring>
 #include <random>
 #include <vector>
-static const double MAGIC41 = 3298534883328.0, LOG2E = 1.442695040888963407359924681001892137;
+#ifndef LF_EXP_MASKED
+#define LF_EXP_MASKED 0          /* as lf_math.cuh: 0 = shifted table index (product default), 1 = masked low mantissa word */
+#endif
+static const double MAGIC41 = 3298534883328.0, MAGIC44 = 26388279066624.0, LOG2E = 1.442695040888963407359924681001892137;
 static const double LOG1P_C0 = 4.5474875525573243324e-13, LOG1P_C1 = 0.9999999999985449674, LOG1P_C2 = -0.50000095367660766342,
                     LOG1P_C3 = 0.33333447770293183222;
+#if LF_EXP_MASKED
 static const double EXP2_C0 = 1.000000000000007627, EXP2_C1 = 0.69314718062664656388, EXP2_C2 = 0.24022637497468078452,
                     EXP2_C3 = 0.055569904189805140222;      // EXP2B_*: minimax on [-2^-12, 15 * 2^-12)
+#else
+static const double EXP2_C0 = 0.99999999999998250473, EXP2_C1 = 0.69314718055993561091, EXP2_C2 = 0.24022654364935376114,
+                    EXP2_C3 = 0.055504116293577099979;
+#endif
 static const int LOG_OCTAVES = 12, M = 256, LOG_TAB_BASE = (1023 - LOG_OCTAVES) << 8, EXPB_KMIN = -40 * 256;
 static std::vector<double> tab_invc, tab_lnc, exp_big;
 static inline int hi(double v) { uint64_t u; memcpy(&u, &v, 8); return (int)(u >> 32); }
@@ -44,6 +52,7 @@ static double term_fast(double g, double f, double alpha, double aF, double c2) 
     const double lg = fma(eps, a, tab_lnc[b]);
     // one_minus_exp2 (one-look-up table; low word of the reduction = round(2048 x2), masked to a multiple of 8 = byte offset
     // of the entry; clamped at -40 * 256 entries)
+#if LF_EXP_MASKED
     const double t = fma(f, c2, MAGIC41);
     const int k8 = lo(t) & ~7;
     uint64_t tb; memcpy(&tb, &t, 8);
@@ -53,6 +62,13 @@ static double term_fast(double g, double f, double alpha, double aF, double c2) 
     const double r = fma(f, c2, -kf);
     int k = k8 / 8;                                  // exact: k8 is a multiple of 8
     if (k < EXPB_KMIN) k = EXPB_KMIN;
+#else
+    const double t = fma(f, c2, MAGIC44);            // k clamped at -40 * 256
+    int k = lo(t);
+    if (k < EXPB_KMIN) k = EXPB_KMIN;
+    const double kf = t - MAGIC44;
+    const double r = fma(f, c2, -kf);
+#endif
     const double Ts = exp_big[k - EXPB_KMIN];
     double pp = fma(r, EXP2_C3, EXP2_C2);
     pp = fma(r, pp, EXP2_C1);
