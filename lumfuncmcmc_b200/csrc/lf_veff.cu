@@ -873,6 +873,10 @@ static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned cha
                               int64_t* counts, double* sumphi) {
     const long long n = c->vN;
     const int K = c->v_K;
+    if (!(alpha > 0.0) || !std::isfinite(alpha)) return fail("lf_veff_bin_resident: alpha must be positive and finite");
+    for (int k = 0; k < K; ++k)
+        if (!(flim[k] > 0.0) || !std::isfinite(flim[k])) return fail("lf_veff_bin_resident: flim must be positive and finite");
+    if (!(fcmin >= 0.0) || !(fcmin < 1.0)) return fail("lf_veff_bin_resident: fcmin must lie in [0, 1)");
     // (re)bin only when the edges changed
     bool same_edges = c->v_rows_valid && (int)c->v_edges_host.size() == nbins + 1 &&
                       memcmp(c->v_edges_host.data(), edges, sizeof(double) * (nbins + 1)) == 0;
@@ -918,7 +922,7 @@ static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned cha
     const size_t smem = vres_smem(nbins);
     const bool persrc = d_vol != nullptr;
     static const bool use_tma = []() { const char* e = getenv("LF_VEFF_TMA"); return !(e && e[0] == '0'); }();
-    if (!persrc && use_tma && n >= VRT_MIN_SOURCES && vres_tma_smem(nbins) <= VRT_SMEM_MAX) {
+    if (!persrc && (use_tma || smem > 72 * 1024) && n >= VRT_MIN_SOURCES && vres_tma_smem(nbins) <= VRT_SMEM_MAX) {
         // inputs staged by the copy engine (bulk async copies + mbarrier ring)
         const size_t smt = vres_tma_smem(nbins);
         if (modified) k_veff_res_tma<true><<<blocks, 32 * VR_WARPS, smt, c->stream>>>(a);
@@ -956,7 +960,8 @@ static int veff_weights_pass(lf_ctx* c, long long n, const double* d_flux, const
                              const long long* field_ind, int nfields, const double* flim, double alpha, double fcmin,
                              double sum_omega, double vol_int, const double* edges, int nbins, double* phi_out,
                              int64_t* counts, double* sumphi) {
-    if (d_flux == c->v_flux && c->v_have_sample && c->v_u && vres_smem(nbins) <= 72 * 1024 && (d_vol == nullptr) == (d_valid == nullptr))
+    const bool fits = d_vol ? vres_smem(nbins) <= 72 * 1024 : (vres_tma_smem(nbins) <= VRT_SMEM_MAX || vres_smem(nbins) <= 72 * 1024);
+    if (d_flux == c->v_flux && c->v_have_sample && c->v_u && fits && (d_vol == nullptr) == (d_valid == nullptr))
         return veff_resident_pass(c, d_vol, d_valid, flim, alpha, fcmin, sum_omega, vol_int, edges, nbins, phi_out, counts, sumphi);
     c->v_rows_valid = false;                       // the general kernel rewrites the rows for ITS edges
     const VeffPlan plan = veff_plan(c, n, nbins);

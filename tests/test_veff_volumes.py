@@ -158,6 +158,15 @@ def test_resident_sample_equals_host_buffer_path_and_weights_are_fetched_lazily(
     keep = (idx >= 0) & (idx < 25)
     assert np.array_equal(cnt2, np.bincount(idx[keep], minlength=25)[:25])
     np.testing.assert_allclose(sum2, np.bincount(idx[keep], weights=ref[keep], minlength=25)[:25], rtol=1e-12)
+    for nb3 in (100, 200):                        # more bins than the 16-column kernel holds / than either resident kernel holds
+        edges3 = np.linspace(lum.min() * 1.001, lum.max(), nb3 + 1)
+        _, cnt4, sum4 = b.veff_bin_resident(cat['Flim'], cat['alpha'], cat['fcmin'], so, 3.0e10, edges3)
+        idx3 = np.searchsorted(edges3, lum, side='right') - 1
+        keep3 = (idx3 >= 0) & (idx3 < nb3)
+        assert np.array_equal(cnt4, np.bincount(idx3[keep3], minlength=nb3)[:nb3])
+        np.testing.assert_allclose(sum4, np.bincount(idx3[keep3], weights=ref[keep3], minlength=nb3)[:nb3], rtol=1e-12)
+    with pytest.raises(Exception, match='positive'):
+        b.veff_bin_resident([2.0, -1.0, 2.5, 4.0], cat['alpha'], cat['fcmin'], so, 3.0e10, edges2)
     _, cnt3, sum3 = b.veff_bin_resident(cat['Flim'], cat['alpha'], 0.0, so, 3.0e10, edges2)        # plain Fleming curve
     ref3 = lf_oracle.veff_weights(flux, flims_arr, cat['alpha'], 0.0, so, 3.0e10, 0.0)
     np.testing.assert_allclose(b.veff_phi(), ref3, rtol=1e-13)
