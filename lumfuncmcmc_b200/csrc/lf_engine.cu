@@ -779,15 +779,21 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), (LITERAL && MODEL == L
 // ------------------------------------------------------------------------------------------------
 // finish: fixed-order reduction over slabs; lnprob = lnpart - fullint
 // ------------------------------------------------------------------------------------------------
-#define FIN_GROUPS 32
-__global__ void __launch_bounds__(32 * FIN_GROUPS) k_finish(KArgs a) {
-    // one block per 32 walkers; FIN_GROUPS row-groups read the slab partials in parallel (coalesced along walkers),
-    // each in ascending row order, and are combined in a fixed order: deterministic, no atomics
-    __shared__ double s_src[FIN_GROUPS][32], s_quad[FIN_GROUPS][32];
+#define FIN_WALKERS 8            /* walkers per block: 64-byte rows of partials per warp-load, W / 8 blocks (128 at W = 1024) */
+#define FIN_WARPS 32
+__global__ void __launch_bounds__(32 * FIN_WARPS) k_finish(KArgs a) {
+    // one block per FIN_WALKERS walkers.  Lane = (walker, row sub-slot): a warp reads 4 consecutive rows x 8 walkers (four
+    // 64-byte segments) per step, the 32 warps stride over the rows; every thread adds its rows in ascending order, the
+    // partial sums are combined by a fixed shuffle tree and a fixed-order sum over the warps: deterministic, no atomics.
+    // (Round 1 used 32 walkers x 32 row groups per block = W / 32 blocks: 24 us at 1763 rows x 1024 walkers, most of it the
+    // serial chain of 55 dependent L2 round trips per thread on 32 of the 148 SMs.)
+    __shared__ double s_src[FIN_WARPS][FIN_WALKERS], s_quad[FIN_WARPS][FIN_WALKERS];
     const int lane = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int wsub = lane & (FIN_WALKERS - 1), rsub = lane / FIN_WALKERS;          // 8 walkers x 4 row sub-slots
+    constexpr int RSTEP = FIN_WARPS * (32 / FIN_WALKERS);
     const int nf = a.cls_count[CLS_FAST], nl = a.cls_count[CLS_LIT];
-    const long long idx = (long long)blockIdx.x * 32 + lane;
-    if ((long long)blockIdx.x * 32 >= nf + nl) return;
+    const long long idx = (long long)blockIdx.x * FIN_WALKERS + wsub;
+    if ((long long)blockIdx.x * FIN_WALKERS >= nf + nl) return;
     const bool valid = idx < nf + nl;
     const bool fast = idx < nf;
     long long w = 0;
@@ -796,18 +802,21 @@ __global__ void __launch_bounds__(32 * FIN_GROUPS) k_finish(KArgs a) {
     double lnpart = 0.0, fullint = 0.0;
     if (valid) {
         const double* col = a.partial + w;
+        const int r0 = g * (32 / FIN_WALKERS) + rsub;
 #pragma unroll 4
-        for (int r = g; r < a.n_src_slabs; r += FIN_GROUPS) lnpart += col[(long long)r * WS];
+        for (int r = r0; r < a.n_src_slabs; r += RSTEP) lnpart += col[(long long)r * WS];
 #pragma unroll 4
-        for (int r = a.n_src_slabs + g; r < a.n_src_slabs + a.n_quad_slabs; r += FIN_GROUPS)
-            fullint += col[(long long)r * WS];
+        for (int r = a.n_src_slabs + r0; r < a.n_src_slabs + a.n_quad_slabs; r += RSTEP) fullint += col[(long long)r * WS];
     }
-    s_src[g][lane] = lnpart;
-    s_quad[g][lane] = fullint;
+    for (int o = FIN_WALKERS; o < 32; o <<= 1) {                                    // over the row sub-slots of the warp
+        lnpart += __shfl_xor_sync(0xffffffffu, lnpart, o);
+        fullint += __shfl_xor_sync(0xffffffffu, fullint, o);
+    }
+    if (rsub == 0) { s_src[g][wsub] = lnpart; s_quad[g][wsub] = fullint; }
     __syncthreads();
-    if (g != 0 || !valid) return;
+    if (g != 0 || rsub != 0 || !valid) return;
     lnpart = 0.0; fullint = 0.0;
-    for (int k = 0; k < FIN_GROUPS; ++k) { lnpart += s_src[k][lane]; fullint += s_quad[k][lane]; }
+    for (int k = 0; k < FIN_WARPS; ++k) { lnpart += s_src[k][wsub]; fullint += s_quad[k][wsub]; }
     if (fast) lnpart += a.wp[P_LNPART0 * WS + w];
     if (a.nshare > 1 && (w % a.nshare) != a.share) fullint = 0.0;
     double v = lnpart - fullint;
@@ -1435,7 +1444,7 @@ int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_ou
             k_main<true, LF_MODEL_Z><<<bl, 32 * main_warps(LF_MODEL_Z), 0, st>>>(a);
         }
     }
-    k_finish<<<(unsigned)((W + 31) / 32), 32 * FIN_GROUPS, 0, st>>>(a);
+    k_finish<<<(unsigned)((W + FIN_WALKERS - 1) / FIN_WALKERS), 32 * FIN_WARPS, 0, st>>>(a);
     c->launches += 3;
     CK(cudaGetLastError());
     return scratch_release(c, st);
