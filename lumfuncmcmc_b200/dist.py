@@ -225,6 +225,9 @@ class ShardedLikelihood:
         t = self.torch
         th = np.ascontiguousarray(np.atleast_2d(np.asarray(thetas, dtype=np.float64)))
         W = th.shape[0]
+        if self.world == 1:
+            # one rank: the engine's own host entry point (pinned staging, H2D, kernels, D2H, sync inside lf_lnprob_batch)
+            return self.engine.lnprob(th)
         self._ensure(W)
         self._h_th[:W].copy_(t.from_numpy(th))
         with t.cuda.device(self.device):
