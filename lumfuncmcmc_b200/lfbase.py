@@ -268,10 +268,11 @@ class LFBase:
     def phifunc(self, value):
         self._phifunc, self._phi_engine = value, None
 
-    def _veff_volumes_host(self, root_per_source):
+    def _veff_volumes_host(self, root_per_field):
         """The reference's per-source loop (lumfuncmcmc.py:521-524): one fsolve (``V.getMaxz``) and one QUADPACK integral
         per source.  Kept as the checked oracle of the device path (tests); O(N) Python, hours at 1e7 sources."""
         n = len(self.flux)
+        root_per_source = np.repeat(np.asarray(root_per_field, dtype=np.float64), np.diff(np.asarray(self.field_ind)))
         vol, valid, zmaxs = np.ones(n), np.zeros(n, dtype=np.uint8), np.zeros(n)
         for i in range(n):
             zmaxval = min(self.zmax, V.getMaxz(10 ** self.lum[i], root_per_source[i]))
@@ -281,7 +282,7 @@ class LFBase:
                 valid[i] = 1
         return zmaxs, vol, valid
 
-    def _veff(self, root_per_source):
+    def _veff(self, root_per_field):
         """Per-source 1/V_eff weights, binned LF and bootstrap errors on the GPU (reference lumfuncmcmc.py:515-525).
 
         The catalogue (flux, lum) is uploaded once per engine and stays resident: VeffLF runs after every fit and again
@@ -311,9 +312,9 @@ class LFBase:
             if self._veff_table_on is not eng:
                 eng.veff_set_volume_table(_cosmo, self.dVdzf.x, self.dVdzf.y)
                 self._veff_table_on = eng
-            fi = np.asarray(self.field_ind, dtype=np.int64)
-            root = np.asarray(root_per_source, dtype=np.float64)
-            fmin = np.array([root[fi[k]] if fi[k + 1] > fi[k] else 1.0 for k in range(self.nfields)])   # constant within a field
+            fmin = np.asarray(root_per_field, dtype=np.float64)          # minimum flux per field (cgs)
+            if fmin.shape != (self.nfields,):
+                raise ValueError("one minimum flux per field expected")
             eng.veff_volumes(self.zmin, self.zmax, float(_cosmo.luminosity_distance(self.zmin)),
                              float(_cosmo.luminosity_distance(self.zmax)), fmin)
             _, counts, sums = eng.veff_bin_resident(self.Flim, self.alpha, self.fcmin, sum_Omega, 1.0, edges,

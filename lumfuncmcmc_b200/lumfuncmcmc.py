@@ -217,7 +217,10 @@ class LumFuncMCMC(LFBase):
         """1/V_eff binned luminosity function with bootstrap errors -> ``Lavg``, ``lfbinorig``, ``var``
         (reference lumfuncmcmc.py:515-525)."""
         self.getFlim()
-        self._veff(self.rootsf.ev(self.Flims_arr, self.alpha))
+        # the reference evaluates rootsf.ev(self.Flims_arr, self.alpha) for every source (lumfuncmcmc.py:520); Flims_arr is
+        # constant within a field and the spline is evaluated point by point, so the K per-field values are the same numbers
+        flims = np.asarray(self.Flim, dtype=np.float64)
+        self._veff(self.rootsf.ev(flims, np.full(flims.shape, float(self.alpha))))
 
     def _median_model(self, nsamples, rndsamples):
         Flims, alphas = np.zeros((rndsamples, self.nfields)), np.zeros(rndsamples)

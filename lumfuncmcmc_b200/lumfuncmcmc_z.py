@@ -172,7 +172,7 @@ class LumFuncMCMCz(LFBase):
     # ------------------------------------------------------------------ 1/V_eff and posterior summaries
     def VeffLF(self):
         """1/V_eff binned LF with bootstrap errors (reference lumfuncmcmc_z.py:470-478)."""
-        self._veff(self.roots_arr)
+        self._veff(self.roots_ln)
 
     def _median_matrix(self, nsamples, lo_pad, hi_pad, zlen, Llen):
         """Model LF at the posterior-median parameters on a (redshift, luminosity) mesh -> ``Lout``, ``zout``,

@@ -27,7 +27,7 @@ def _class_and_roots(n=250, nfields=2, seed=19):
                     sch_al=configLF.sch_al, Lstar=configLF.Lstar, phistar=configLF.phistar, fcmin=cat['fcmin'],
                     min_comp_frac=0.5, field_names=cat['field_names'], field_ind=cat['field_ind'], nbins=20, nboot=30)
     m.getFlim()
-    return m, m.rootsf.ev(m.Flims_arr, m.alpha)
+    return m, m.rootsf.ev(m.Flims_arr, m.alpha)          # per source, as the reference evaluates it (lumfuncmcmc.py:520)
 
 
 def test_oracle_volumes_restatement_matches_the_reference_loop_and_golden(golden):
@@ -53,12 +53,14 @@ def test_oracle_volumes_restatement_matches_the_reference_loop_and_golden(golden
 def test_device_volumes_match_the_reference_loop():
     from lumfuncmcmc_b200.cosmology import cosmo
     m, roots = _class_and_roots(n=1200, nfields=3, seed=23)
-    zm_l, vol_l, ok_l = m._veff_volumes_host(roots)                    # the reference's loop, verbatim
+    fi = np.asarray(m.field_ind)
+    zm_l, vol_l, ok_l = m._veff_volumes_host(np.array([roots[fi[k]] for k in range(m.nfields)]))   # the reference's loop, verbatim
     eng = m._veff_engine()
     eng.veff_set_sample(m.flux, m.lum, m.field_ind)
     eng.veff_set_volume_table(cosmo, m.dVdzf.x, m.dVdzf.y)
-    fi = np.asarray(m.field_ind)
     fmin = np.array([roots[fi[k]] for k in range(m.nfields)])
+    # the per-source spline evaluation of the reference equals the per-field one the class now does, bit for bit
+    assert np.array_equal(np.repeat(m.rootsf.ev(np.asarray(m.Flim, dtype=float), np.full(m.nfields, float(m.alpha))), np.diff(fi)), roots)
     zm, vol, ok = eng.veff_volumes(m.zmin, m.zmax, float(cosmo.luminosity_distance(m.zmin)),
                                    float(cosmo.luminosity_distance(m.zmax)), fmin, want=True)
     assert np.array_equal(ok.astype(bool), ok_l.astype(bool)) and 0 < ok.sum() < len(ok)
