@@ -1346,8 +1346,21 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g
     int cur = 0;
     for (int i = j; i < MT_N; i += MT_THREADS) mt[0][i] = g_state[i];
     int pos = *g_pos;                                   // next unused output of the current state block (624: none left)
-    long long acc = 0;                                  // samples accepted so far
+    long long acc = 0;                                  // samples accepted up to the last flush (block-uniform, exact)
+    int pend = 0, since = 0;                            // this thread's accepted outputs / state blocks since the last flush
     long long used = 0;                                 // words written to vals
+    __shared__ int s_red[MT_THREADS / 32];
+    auto flush = [&]() {                                // acc += sum over the block of pend (fixed order), two barriers
+        int t = pend;
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (lane == 0) s_red[warp] = t;
+        __syncthreads();
+        int tot = 0;
+        for (int wv = 0; wv < MT_THREADS / 32; ++wv) tot += s_red[wv];
+        __syncthreads();
+        acc += tot;
+        pend = 0; since = 0;
+    };
     __syncthreads();
     for (;;) {
         if (pos >= MT_N) {                              // regenerate the state block (block-uniform)
@@ -1377,11 +1390,8 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g
             }
             mine += ok[t] ? 1 : 0;
         }
-        // block-wide count of accepted outputs (sum over threads of 0..3)
-        const int c1 = __syncthreads_count(mine & 1), c2 = __syncthreads_count(mine & 2);
-        const int cnt = c1 + 2 * c2;
         const bool buffered = used + MT_N <= cap;       // room for a whole block of outputs (else: direct atomics, rare)
-        if (acc + cnt < n) {                            // the replicate needs all of them (and more)
+        auto emit = [&]() {                              // this block's outputs belong to the replicate, all of them
             if (j < L) {
 #pragma unroll
                 for (int t = 0; t < 3; ++t) {
@@ -1393,6 +1403,22 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g
                 }
             }
             if (buffered) used += MT_N;
+        };
+        // Far from the end the exact count is not needed: even if every output since the last flush had been accepted the
+        // replicate could not end inside this block, so the threads just keep their own counts (no counting barrier) and
+        // the block adds them up every 64 state blocks.
+        if (n - acc > (long long)(since + 1) * MT_N) {
+            emit();
+            pend += mine;
+            pos = MT_N;
+            if (++since == 64) flush();
+            continue;
+        }
+        if (since > 0) flush();                         // from here on the count is exact, block by block
+        const int c1 = __syncthreads_count(mine & 1), c2 = __syncthreads_count(mine & 2);
+        const int cnt = c1 + 2 * c2;
+        if (acc + cnt < n) {                            // the replicate needs all of them (and more)
+            emit();
             acc += cnt;
             pos = MT_N;
             continue;
