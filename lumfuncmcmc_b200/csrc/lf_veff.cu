@@ -1308,14 +1308,14 @@ extern "C" int lf_boot_bin_device(lf_ctx* c, uint64_t seed, int64_t replicate, i
 // The reference resamples with np.random.randint(n, size=n) on NumPy's global RandomState (VmaxLumFunc.py:353): for
 // n - 1 < 2^32 that is, per sample, "draw 32-bit MT19937 outputs, AND them with the smallest all-ones mask >= n - 1, until
 // one is <= n - 1" (numpy/random/src/distributions/distributions.c: random_bounded_uint64_fill ->
-// buffered_bounded_masked_uint32).  One CTA reproduces exactly that stream: the 624-word state is regenerated in three
-// parallel phases (words [0, 227) depend on the old state only, [227, 454) on those, [454, 624) on the second group),
-// the words are tempered and tested, accepted values increment the multiplicity of their source (integer atomics: order does
-// not matter), and the replicate ends right after its n-th accepted output -- the state and position left behind are what
-// NumPy's would be, so the host generator can be re-synchronised afterwards (lf_boot_mt_get_state).
+// buffered_bounded_masked_uint32).  One CTA reproduces exactly that stream: the 624-word state is regenerated in parallel
+// (one thread per word, see k_mt_draw), the words are tempered and tested, accepted values increment the multiplicity of
+// their source (integer atomics: order does not matter), and the replicate ends right after its n-th accepted output --
+// the state and position left behind are what NumPy's would be, so the host generator can be re-synchronised afterwards
+// (lf_boot_mt_get_state).
 #define MT_N 624
 #define MT_M 397
-#define MT_THREADS 256
+#define MT_THREADS 672                       // 623 word threads + one warp whose first lane owns word 623
 __device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b) {
     const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
     return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
@@ -1332,24 +1332,30 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 // and counts; k_mt_scatter, a full grid, turns them into multiplicities afterwards.  (Issuing the ~370 random global atomics
 // per state block from the one generating SM made the draw five times slower than the state recurrence itself.)
 #define MT_REJECT 0xffffffffu
-// 227 working threads (8 warps: cheap barriers): thread j owns words j, j + 227 and j + 454 of the state block -- one per
-// phase of the regeneration -- and tempers / tests / stores the same three words.  Per block of 624 outputs: three barriers
-// for the recurrence and one counting barrier.
+// One barrier per state block.  The recurrence x[k + 624] = x[k + 397] ^ A(x[k], x[k + 1]) has dependency distance 227, so a
+// literal regeneration needs three barrier-separated phases per 624 words -- and the draw was bound by exactly that chain
+// (~1100 cycles per state block whether 8 or 20 warps, with or without the counting barriers).  A is linear over GF(2), so
+// the recurrence can be substituted into itself: for 227 <= i < 454, new[i] = new[i - 227] ^ A(old[i], old[i + 1]) =
+// old[i + 170] ^ A(old[i - 227], old[i - 226]) ^ A(old[i], old[i + 1]), and once more for 454 <= i < 624 -- every word of the
+// next block is then a function of the PREVIOUS block only, all 624 can be computed in parallel (one thread each, at most
+// three A's), and one __syncthreads per block remains.  Thread i tempers and tests the word it has just computed.
 __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g_state, int* __restrict__ g_pos, long long n,
                                                        uint32_t rng, uint32_t mask, uint32_t* __restrict__ vals, long long cap,
                                                        long long* __restrict__ g_used, int* __restrict__ mult) {
-    constexpr int L = MT_N - MT_M;                      // 227: words that can be regenerated in parallel
+    constexpr int L = MT_N - MT_M;                      // 227
     __shared__ uint32_t mt[2][MT_N];
-    __shared__ int s_cnt[3][MT_THREADS / 32];
+    __shared__ int s_red[MT_THREADS / 32];
     __shared__ int s_newpos;
-    const int j = threadIdx.x, lane = j & 31, warp = j >> 5;
+    // word 623 needs new[0] inside its last A and twice the arithmetic: it gets a warp of its own (thread 640) instead of
+    // serialising behind its neighbours' branch; j = the word this thread owns (624: none); thread order = stream order
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int j = t < MT_N - 1 ? t : (t == 640 ? MT_N - 1 : MT_N);
     int cur = 0;
-    for (int i = j; i < MT_N; i += MT_THREADS) mt[0][i] = g_state[i];
+    if (j < MT_N) mt[0][j] = g_state[j];
     int pos = *g_pos;                                   // next unused output of the current state block (624: none left)
     long long acc = 0;                                  // samples accepted up to the last flush (block-uniform, exact)
     int pend = 0, since = 0;                            // this thread's accepted outputs / state blocks since the last flush
     long long used = 0;                                 // words written to vals
-    __shared__ int s_red[MT_THREADS / 32];
     auto flush = [&]() {                                // acc += sum over the block of pend (fixed order), two barriers
         int t = pend;
         for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
@@ -1362,90 +1368,100 @@ __global__ void __launch_bounds__(MT_THREADS) k_mt_draw(uint32_t* __restrict__ g
         pend = 0; since = 0;
     };
     __syncthreads();
+    uint32_t word = j < MT_N ? mt[0][j] : 0u;           // this thread's word of the current block
+    auto next_block = [&](const uint32_t* o, uint32_t* nw) -> uint32_t {   // every word from the previous block alone
+        uint32_t x = 0u;
+        if (j < L) {
+            x = o[j + MT_M] ^ mt_twist(o[j], o[j + 1]);
+        } else if (j < 2 * L) {
+            x = o[j + MT_M - L] ^ mt_twist(o[j - L], o[j - L + 1]) ^ mt_twist(o[j], o[j + 1]);
+        } else if (j < MT_N - 1) {
+            x = o[j + MT_M - 2 * L] ^ mt_twist(o[j - 2 * L], o[j - 2 * L + 1]) ^ mt_twist(o[j - L], o[j - L + 1]) ^ mt_twist(o[j], o[j + 1]);
+        } else if (j == MT_N - 1) {
+            // new[623] = new[396] ^ A(old[623], new[0]);  new[396] = old[566] ^ A(old[169], old[170]) ^ A(old[396], old[397])
+            const uint32_t new0 = o[MT_M] ^ mt_twist(o[0], o[1]);
+            x = o[MT_M - 1 + MT_M - L] ^ mt_twist(o[MT_M - 1 - L], o[MT_M - L]) ^ mt_twist(o[MT_M - 1], o[MT_M]) ^ mt_twist(o[MT_N - 1], new0);
+        }
+        if (j < MT_N) nw[j] = x;
+        __syncthreads();
+        return x;
+    };
+    constexpr int G = 4;                                // state blocks per trip of the fast path (even: the buffers alternate)
     for (;;) {
-        if (pos >= MT_N) {                              // regenerate the state block (block-uniform)
-            const uint32_t* o = mt[cur];
-            uint32_t* w = mt[cur ^ 1];
-            if (j < L) w[j] = o[j + MT_M] ^ mt_twist(o[j], o[j + 1]);
-            __syncthreads();
-            if (j < L) w[j + L] = w[j] ^ mt_twist(o[j + L], o[j + L + 1]);
-            __syncthreads();
-            if (j + 2 * L < MT_N - 1) w[j + 2 * L] = w[j + L] ^ mt_twist(o[j + 2 * L], o[j + 2 * L + 1]);
-            else if (j + 2 * L == MT_N - 1) w[MT_N - 1] = w[MT_M - 1] ^ mt_twist(o[MT_N - 1], w[0]);
-            __syncthreads();
+        // Fast path, far from the end: the replicate certainly needs the next G whole blocks (even if every output since
+        // the last flush had been accepted) and the candidate buffer has room for them -- no counting, no 64-bit
+        // bookkeeping per block, the threads keep their own counts.
+        while (pos >= MT_N && n - acc > (long long)(since + G) * MT_N && used + G * MT_N <= cap) {
+            uint32_t* out = vals + used + j;
+            uint32_t* a = mt[cur];
+            uint32_t* b = mt[cur ^ 1];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                const uint32_t x = next_block((g & 1) ? b : a, (g & 1) ? a : b);
+                const uint32_t v = mt_temper(x) & mask;
+                const bool ok = v <= rng;
+                if (j < MT_N) {
+                    out[g * MT_N] = ok ? v : MT_REJECT;
+                    pend += ok ? 1 : 0;
+                }
+                word = x;
+            }
+            used += G * MT_N;
+            since += G;
+            if (since >= 64) flush();
+        }
+        if (pos >= MT_N) {                              // next state block
+            word = next_block(mt[cur], mt[cur ^ 1]);
             cur ^= 1;
             pos = 0;
         }
-        // outputs pos .. 623 of this block: thread j looks at words j, j + 227, j + 454
-        uint32_t v[3];
-        bool ok[3];
-        int mine = 0;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int idx = j + t * L;
-            ok[t] = false; v[t] = 0u;
-            if (j < L && idx >= pos && idx < MT_N) {
-                v[t] = mt_temper(mt[cur][idx]) & mask;
-                ok[t] = v[t] <= rng;
-            }
-            mine += ok[t] ? 1 : 0;
+        // outputs pos .. 623 of this block, one per thread, in stream order
+        bool ok = false;
+        uint32_t v = 0u;
+        if (j >= pos && j < MT_N) {
+            v = mt_temper(word) & mask;
+            ok = v <= rng;
         }
         const bool buffered = used + MT_N <= cap;       // room for a whole block of outputs (else: direct atomics, rare)
         auto emit = [&]() {                              // this block's outputs belong to the replicate, all of them
-            if (j < L) {
-#pragma unroll
-                for (int t = 0; t < 3; ++t) {
-                    const int idx = j + t * L;
-                    if (idx < MT_N) {
-                        if (buffered) vals[used + idx] = ok[t] ? v[t] : MT_REJECT;
-                        else if (ok[t]) atomicAdd(&mult[v[t]], 1);
-                    }
-                }
+            if (j < MT_N) {
+                if (buffered) vals[used + j] = ok ? v : MT_REJECT;
+                else if (ok) atomicAdd(&mult[v], 1);
             }
             if (buffered) used += MT_N;
         };
         // Far from the end the exact count is not needed: even if every output since the last flush had been accepted the
-        // replicate could not end inside this block, so the threads just keep their own counts (no counting barrier) and
-        // the block adds them up every 64 state blocks.
+        // replicate could not end inside this block, so the threads keep their own counts and the block adds them up every
+        // 64 state blocks.
         if (n - acc > (long long)(since + 1) * MT_N) {
             emit();
-            pend += mine;
+            pend += ok ? 1 : 0;
             pos = MT_N;
-            if (++since == 64) flush();
+            if (++since >= 64) flush();
             continue;
         }
         if (since > 0) flush();                         // from here on the count is exact, block by block
-        const int c1 = __syncthreads_count(mine & 1), c2 = __syncthreads_count(mine & 2);
-        const int cnt = c1 + 2 * c2;
+        const int cnt = __syncthreads_count(ok);
         if (acc + cnt < n) {                            // the replicate needs all of them (and more)
             emit();
             acc += cnt;
             pos = MT_N;
             continue;
         }
-        // the n-th accepted output lies in this block: rank the accepted outputs in stream order (third by third)
-        unsigned bal[3];
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            bal[t] = __ballot_sync(0xffffffffu, ok[t]);
-            if (lane == 0) s_cnt[t][warp] = __popc(bal[t]);
-        }
+        // the n-th accepted output lies in this block: rank the accepted outputs in stream order
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_red[warp] = __popc(bal);
         __syncthreads();
-        long long base = acc;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            int before = __popc(bal[t] & ((1u << lane) - 1u));
-            for (int wv = 0; wv < warp; ++wv) before += s_cnt[t][wv];
-            const long long my_index = base + before;   // 0-based index of this sample, if accepted
-            if (ok[t] && my_index < n) atomicAdd(&mult[v[t]], 1);
-            if (ok[t] && my_index == n - 1) s_newpos = j + t * L + 1;   // everything after it belongs to whoever draws next
-            for (int wv = 0; wv < MT_THREADS / 32; ++wv) base += s_cnt[t][wv];
-        }
+        int before = __popc(bal & ((1u << lane) - 1u));
+        for (int wv = 0; wv < warp; ++wv) before += s_red[wv];
+        const long long my_index = acc + before;        // 0-based index of this thread's sample, if accepted
+        if (ok && my_index < n) atomicAdd(&mult[v], 1);
+        if (ok && my_index == n - 1) s_newpos = j + 1;  // everything after it belongs to whoever draws next
         __syncthreads();
         pos = s_newpos;
         break;
     }
-    for (int i = j; i < MT_N; i += MT_THREADS) g_state[i] = mt[cur][i];
+    if (j < MT_N) g_state[j] = mt[cur][j];
     if (j == 0) { *g_pos = pos; *g_used = used; }
 }
 
