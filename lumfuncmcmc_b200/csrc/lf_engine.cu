@@ -103,6 +103,9 @@ __global__ void k_prologue(KArgs a) {
             lb = LNLN10 + LN10 * Plo + fmin(c1 * dlo, c1 * dhi) - emax + s.lnom_min;
             if (!(emax < 690.0)) lb = -1.0e300;
             if (!(dlo > -40.0)) lb = -1.0e300;
+            // the source loop evaluates 2^(log2(10) (lum - L*(z)) - log2(10) (42 - L*(z2))) without clamping the exponent field:
+            // with the two bounds above the first part lies in (-133, 9.5); this keeps the second below 665
+            if (!(fabs(42.0 - L2) < 200.0)) lb = -1.0e300;
             // compressed catalogue: |dL*/dz| over the field's redshift range must stay inside the bound it was built for
             if (a.csrc != nullptr && !(fmax(fabs(fma(2.0 * aL, s.z_min, bL)), fabs(fma(2.0 * aL, s.z_max, bL))) <= a.c_alpha_max)) lb = -1.0e300;
         }
@@ -234,10 +237,16 @@ __global__ void k_zcolumns(KArgs a) {
 #define QSTAGE 64
 // Per-model launch shape of the fast kernels.  FREE: 12 warps (up to 168 registers), shared memory = log table + exp table +
 // staging.  Z / FIXED: lighter loops (<= 128 registers) -> 16 warps; no log table, the small replicated exp table + staging.
-__host__ __device__ constexpr int main_warps(int model) { return model == LF_MODEL_FREE ? WARPS_PER_BLOCK : 16; }
+#ifndef LF_Z_CLAMP
+#define LF_Z_CLAMP 0
+#endif
+#ifndef LF_ZF_WARPS
+#define LF_ZF_WARPS 16
+#endif
+__host__ __device__ constexpr int main_warps(int model) { return model == LF_MODEL_FREE ? WARPS_PER_BLOCK : LF_ZF_WARPS; }
 __host__ __device__ constexpr size_t main_table_bytes(int model) {
     return model == LF_MODEL_FREE ? sizeof(double2) * LOG_TAB_N * LOG_TAB_REP + sizeof(double) * EXP_SMEM_DOUBLES
-                                  : sizeof(double) * EXP_TAB_N * EXP_TAB_REP;
+                                  : sizeof(double) * EXPR_SMEM_DOUBLES;
 }
 __host__ __device__ constexpr size_t main_smem_bytes(int model) {
     return main_table_bytes(model) + (size_t)main_warps(model) * QSTAGE * 3 * sizeof(double2);
@@ -289,6 +298,7 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), (LITERAL && MODEL == L
     const int lane = threadIdx.x & 31;
     const int rep16 = lane & (EXP_TAB_REP - 1), rep8 = lane & (LOG_TAB_REP - 1);   // table replica of this lane
     const double* s_exp_rep = reinterpret_cast<const double*>(s_log);               // Z / FIXED models only
+    const unsigned lane8 = 8u * lane;                                                // this lane's column of that table
     const long long WS = a.Wcap;
     int* counter = a.cls_count + (LITERAL ? 4 : 3);
     // the first item of every warp is assigned statically (its global warp index), the following ones come from the
@@ -569,7 +579,7 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), (LITERAL && MODEL == L
                     const long long m0 = (a.M * row) / a.n_src_slabs, m1 = (a.M * (row + 1)) / a.n_src_slabs;
                     for (long long m = m0; m < m1; ++m) {
                         const double xi = __ldg(&a.csrc[2 * m]).x, v = __ldg(&a.csrc[2 * m + 1]).x;
-                        accH = fma(-v, exp2_full<false>(-fma(fma(a2, xi, b2), xi, c2), s_exp_rep, rep16), accH);
+                        accH = fma(-v, exp2r_full<true>(-fma(fma(a2, xi, b2), xi, c2), s_exp_rep, lane8), accH);
                     }
                 }
                 if (h == 0) acc0 = accH; else accB = accH;
@@ -585,8 +595,10 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), (LITERAL && MODEL == L
                 const double aLB = wq[P_AL * WS], bLB = wq[P_BL * WS], cLB = wq[P_CL * WS];
                 const double a2 = aL * L2T, b2 = fma(2.0 * aL, zp, bL) * L2T;
                 const double a2B = aLB * L2T, b2B = fma(2.0 * aLB, zp, bLB) * L2T;
-                const double scale = exp2_full<false>(L2T * (42.0 - fma(fma(aL, zp, bL), zp, cL)), s_exp_rep, rep16);
-                const double scaleB = exp2_full<false>(L2T * (42.0 - fma(fma(aLB, zp, bLB), zp, cLB)), s_exp_rep, rep16);
+                const double scale = exp2r_full<true>(L2T * (42.0 - fma(fma(aL, zp, bL), zp, cL)), s_exp_rep, lane8);
+                const double scaleB = exp2r_full<true>(L2T * (42.0 - fma(fma(aLB, zp, bLB), zp, cLB)), s_exp_rep, lane8);
+                // fast-class walkers only (list_fast): k_prologue bounds the exponent to (-800, 680), no clamp needed
+                constexpr bool ZCLAMP = LF_Z_CLAMP != 0;
                 // two sources x two walkers in lock-step (four independent FP64 chains per thread); groups of four sources
                 // are double-buffered in two register sets (no copies): the next group's loads are issued before the
                 // current group's arithmetic
@@ -598,10 +610,10 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), (LITERAL && MODEL == L
                     const double d1 = fma(-fma(a2, s1.y, b2), s1.y, s1.x);
                     const double g0 = fma(-fma(a2B, s0.y, b2B), s0.y, s0.x);
                     const double g1 = fma(-fma(a2B, s1.y, b2B), s1.y, s1.x);
-                    e0 += exp2_full<false>(d0, s_exp_rep, rep16);
-                    e1 += exp2_full<false>(d1, s_exp_rep, rep16);
-                    f0 += exp2_full<false>(g0, s_exp_rep, rep16);
-                    f1 += exp2_full<false>(g1, s_exp_rep, rep16);
+                    e0 += exp2r_full<ZCLAMP>(d0, s_exp_rep, lane8);
+                    e1 += exp2r_full<ZCLAMP>(d1, s_exp_rep, lane8);
+                    f0 += exp2r_full<ZCLAMP>(g0, s_exp_rep, lane8);
+                    f1 += exp2r_full<ZCLAMP>(g1, s_exp_rep, lane8);
                 };
                 double2 A0, A1, A2, A3, B0, B1, B2, B3;
                 int j = 0;
@@ -615,8 +627,8 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), (LITERAL && MODEL == L
                 if (j + 4 <= cnt) { two(A0, A1); two(A2, A3); j += 4; }
                 for (; j < cnt; ++j) {
                     const double2 s0 = __ldg(ps + j);
-                    e0 += exp2_full<false>(fma(-fma(a2, s0.y, b2), s0.y, s0.x), s_exp_rep, rep16);
-                    f0 += exp2_full<false>(fma(-fma(a2B, s0.y, b2B), s0.y, s0.x), s_exp_rep, rep16);
+                    e0 += exp2r_full<ZCLAMP>(fma(-fma(a2, s0.y, b2), s0.y, s0.x), s_exp_rep, lane8);
+                    f0 += exp2r_full<ZCLAMP>(fma(-fma(a2B, s0.y, b2B), s0.y, s0.x), s_exp_rep, lane8);
                 }
                 acc0 = -scale * (e0 + e1);
                 accB = -scaleB * (f0 + f1);
@@ -720,13 +732,13 @@ __global__ void __launch_bounds__(32 * main_warps(MODEL), (LITERAL && MODEL == L
                             }
 #pragma unroll
                             for (int t = 0; t < 4; t += 2) {
-                                acc0 = fma(wt[t], exp_full<false>(arg[t], s_exp_rep, rep16), acc0);
-                                acc1 = fma(wt[t + 1], exp_full<false>(arg[t + 1], s_exp_rep, rep16), acc1);
+                                acc0 = fma(wt[t], expr_full(arg[t], s_exp_rep, lane8), acc0);
+                                acc1 = fma(wt[t + 1], expr_full(arg[t + 1], s_exp_rep, lane8), acc1);
                             }
                         }
                         for (; j < cnt; ++j) {
                             const double2 xl = s_stage[j * 2];
-                            acc0 = fma(s_stage[j * 2 + 1].x, exp_full<false>(fma(-xl.y, cB, fma(c1, xl.x, cA)), s_exp_rep, rep16), acc0);
+                            acc0 = fma(s_stage[j * 2 + 1].x, expr_full(fma(-xl.y, cB, fma(c1, xl.x, cA)), s_exp_rep, lane8), acc0);
                         }
                     }
                 };

@@ -55,6 +55,14 @@ constexpr int EXP_TAB_BITS = 8, EXP_TAB_N = 1 << EXP_TAB_BITS, EXP_TAB_REP = LF_
 constexpr int EXPB_KMIN = -40 * (1 << EXP_TAB_BITS), EXPB_N = -EXPB_KMIN + 1;
 constexpr int EXP_SMEM_DOUBLES = LF_EXP_BIG ? ((EXPB_N + 1) & ~1) : EXP_TAB_N * EXP_TAB_REP;
 constexpr bool EXP_BIG = LF_EXP_BIG != 0;
+// Z / FIXED models (no log table; their hot loop IS the full-range 2^x): the replicated table in a layout that makes the
+// look-up three integer instructions instead of six.  Row j is 256 B = 32 doubles, one column per lane (a half-warp never
+// bank-conflicts), and holds 2^(j/256) with its HIGH WORD LOWERED by j << 12.  With k = 256 K + j, the low mantissa word of
+// the magic-number sum:
+//     byte offset of the entry = (j << 8) | (lane << 3) = PRMT(k, lane8)      (byte 0 of k moved into byte 1)
+//     high word of 2^K T_j     = hi'(j) + (k << 12)     = one LEA             (j << 12 cancels the pre-compensation)
+// instead of shift + mask-or for the address and shift + clamp + multiply-add for the exponent.
+constexpr int EXPR_ROW_DOUBLES = 32, EXPR_SMEM_DOUBLES = EXP_TAB_N * EXPR_ROW_DOUBLES;   // 64 KB
 constexpr int LOG_OCTAVES = 12, LOG_MANT_BITS = 8;
 constexpr int LOG_TAB_N = LOG_OCTAVES * (1 << LOG_MANT_BITS) + 1, LOG_TAB_REP = LF_LOG_REP;  // 3073*2*16 B = 96 KB, two replicas (even / odd lanes)
 constexpr int LOG_TAB_BASE = (1023 - LOG_OCTAVES) << LOG_MANT_BITS;                        // index of 2^-12 in (hi >> 12)
@@ -120,7 +128,11 @@ __device__ __forceinline__ double rcp_fast(double d) {
 // cooperative fill of the (replicated) shared-memory tables
 // models without a log table: only the small replicated exp table
 __device__ __forceinline__ void load_exp_replicated(const Tables* __restrict__ t, double* s_exp_rep) {
-    for (int i = threadIdx.x; i < EXP_TAB_N * EXP_TAB_REP; i += blockDim.x) s_exp_rep[i] = t->exp2_frac[i / EXP_TAB_REP];
+    for (int i = threadIdx.x; i < EXPR_SMEM_DOUBLES; i += blockDim.x) {
+        const int j = i / EXPR_ROW_DOUBLES;
+        const double T = t->exp2_frac[j];
+        s_exp_rep[i] = __hiloint2double(__double2hiint(T) - (j << 12), __double2loint(T));
+    }
 }
 __device__ __forceinline__ void load_tables(const Tables* __restrict__ t, double* s_exp, double2* s_log) {
 #if LF_EXP_BIG
@@ -199,6 +211,37 @@ __device__ __forceinline__ double exp_full(double x, const double* s_exp, int re
     bool under = x < -707.0;
     double Ts, p;
     exp2_parts<BIG>(under ? -707.0 : x, KC[8], s_exp, rep, -1022, Ts, p);
+    return under ? 0.0 : Ts * p;
+}
+
+// The same split on the pre-compensated replicated table (Z / FIXED models): lane8 = 8 * lane, s_rep = the table.
+// CLAMP: keep the exponent field valid below 2^-1022 (one more integer instruction); callers whose argument is known to
+// stay inside (-1021, 1023) leave it off.  Same values as exp2_parts<false> bit for bit (same T_j, K, r and polynomial).
+template <bool CLAMP>
+__device__ __forceinline__ void exp2r_parts(double a, double b, const double* s_rep, unsigned lane8, double& Ts, double& p) {
+    double t = fma(a, b, KC[0]);
+    int k = __double2loint(t);                    // round(256 x2)
+    double kf = t - KC[0];
+    double r = fma(a, b, -kf);
+    if (CLAMP) k = max(k, -1022 * EXP_TAB_N);
+    const unsigned off = __byte_perm((unsigned)k, lane8, 0x7704);           // (j << 8) | lane8
+    const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_rep) + off);
+    Ts = __hiloint2double(__double2hiint(T) + (k << 12), __double2loint(T));
+    p = fma(r, KC[1], KC[2]);
+    p = fma(r, p, KC[3]);
+    p = fma(r, p, KC[4]);
+}
+template <bool CLAMP>
+__device__ __forceinline__ double exp2r_full(double x2, const double* s_rep, unsigned lane8) {
+    double Ts, p;
+    exp2r_parts<CLAMP>(x2, 1.0, s_rep, lane8, Ts, p);
+    return Ts * p;
+}
+// exp(x) for x <= 707; below -707 returns 0
+__device__ __forceinline__ double expr_full(double x, const double* s_rep, unsigned lane8) {
+    bool under = x < -707.0;
+    double Ts, p;
+    exp2r_parts<false>(under ? -707.0 : x, KC[8], s_rep, lane8, Ts, p);
     return under ? 0.0 : Ts * p;
 }
 
