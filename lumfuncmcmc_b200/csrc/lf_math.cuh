@@ -118,6 +118,34 @@ __device__ __forceinline__ double rcp_seed(double y) {
     return r;
 }
 
+// The same seeds with the LOW WORD TAKEN FROM A DONOR instead of zeroed.  MUFU.RSQ64H / RCP64H write only the high word of
+// the result; PTX semantics make the low word zero, which costs one IMAD.MOV per seed in the hot loop.  The corrections that
+// follow only need a seed within ~2^-20 of the true value, so any low word will do: when the donor is a double that dies
+// here, the seed is built in its register pair with no extra instruction.  Deterministic (the donor is a program value).
+#ifndef LF_SEED_DONOR
+#define LF_SEED_DONOR 1
+#endif
+__device__ __forceinline__ double rsqrt_seed_donor(double y, double donor) {
+#if LF_SEED_DONOR
+    double r;
+    asm("{\n\t.reg .b32 dl, dh, sl, sh;\n\t.reg .f64 s;\n\tmov.b64 {dl, dh}, %2;\n\trsqrt.approx.ftz.f64 s, %1;\n\t"
+        "mov.b64 {sl, sh}, s;\n\tmov.b64 %0, {dl, sh};\n\t}" : "=d"(r) : "d"(y), "d"(donor));
+    return r;
+#else
+    return rsqrt_seed(y);
+#endif
+}
+__device__ __forceinline__ double rcp_seed_donor(double y, double donor) {
+#if LF_SEED_DONOR
+    double r;
+    asm("{\n\t.reg .b32 dl, dh, sl, sh;\n\t.reg .f64 s;\n\tmov.b64 {dl, dh}, %2;\n\trcp.approx.ftz.f64 s, %1;\n\t"
+        "mov.b64 {sl, sh}, s;\n\tmov.b64 %0, {dl, sh};\n\t}" : "=d"(r) : "d"(y), "d"(donor));
+    return r;
+#else
+    return rcp_seed(y);
+#endif
+}
+
 // 1/d for normal positive d: MUFU seed (2^-22) + one Newton step (relative error ~6e-14): 2 FP64 instructions + 1 MUFU
 __device__ __forceinline__ double rcp_fast(double d) {
     double r0 = rcp_seed(d);
@@ -305,7 +333,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = fma(n[i], n[i], 1.0);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) r0[i] = rsqrt_seed(y[i]);
+    for (int i = 0; i < NT; ++i) r0[i] = rsqrt_seed_donor(y[i], y[i]);    // y dies here: e = 1 - r0^2 - (n r0)^2 below
     // exp branch while the MUFUs are in flight
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
@@ -333,13 +361,13 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
     for (int i = 0; i < NT; ++i) r[i] = fma(uy[i], cc[i], -t[i]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) p[i] = fma(r[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[10] : KC[1], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[11] : KC[2]);
-    // rsqrt correction
-#pragma unroll
-    for (int i = 0; i < NT; ++i) y[i] = y[i] * r0[i];
-#pragma unroll
-    for (int i = 0; i < NT; ++i) e[i] = fma(-y[i], r0[i], 1.0);
+    // rsqrt correction: e = 1 - y r0^2 with y = n^2 + 1 written as 1 - r0^2 - (n r0)^2 (same three instructions, y not needed)
 #pragma unroll
     for (int i = 0; i < NT; ++i) n[i] = n[i] * r0[i];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) e[i] = fma(-r0[i], r0[i], 1.0);
+#pragma unroll
+    for (int i = 0; i < NT; ++i) e[i] = fma(-n[i], n[i], e[i]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = fma(0.375, e[i], 0.5);
 #pragma unroll
@@ -355,7 +383,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) fc[i] = fma(0.5, q[i], 0.5);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) r0[i] = rcp_seed(dec[i]);
+    for (int i = 0; i < NT; ++i) r0[i] = rcp_seed_donor(dec[i], p[i]);      // p died in the line above
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
         // byte offset of table row b = (hi >> 12) - LOG_TAB_BASE: ((hi >> 12) * 32) = (hi >> 7) & ~31, the base folds into
