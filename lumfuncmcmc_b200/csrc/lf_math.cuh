@@ -295,12 +295,11 @@ __device__ __forceinline__ void fleming_log_parts(double g, double f, double alp
                                                   double& lg, double& rdec) {
     double n = fma(alpha, g, aF);
     double y = fma(n, n, 1.0);
-    double r0 = rsqrt_seed(y);
-    double h = y * r0;
-    double e = fma(-h, r0, 1.0);
+    double r0 = rsqrt_seed_donor(y, y);           // y dies here
+    double nr = n * r0;
+    double e = fma(-nr, nr, fma(-r0, r0, 1.0));   // 1 - y r0^2 with y = n^2 + 1
     double p = fma(0.375, e, 0.5);
     double pe = p * e;
-    double nr = n * r0;
     double q = fma(nr, pe, nr);
     double fc = fma(0.5, q, 0.5);
     lg = log_unit(fc, s_log, repl);
@@ -436,7 +435,12 @@ static __constant__ double KS[16] = {
     0.0, 0.0};
 
 __device__ __forceinline__ void load_stream_tables(const Tables* __restrict__ t, double* s_exp, double2* s_logm) {
-    for (int i = threadIdx.x; i < EXP_TAB_N; i += blockDim.x) s_exp[i] = t->exp2_frac[i];
+    // 2^(j/256) with the high word lowered by j << 12: hi(2^K T_j) = hi'(j) + (k << 12) for k = 256 K + j -- one multiply-add,
+    // no masking of j out of the shifted k (exp_stream / exp_stream_signed)
+    for (int i = threadIdx.x; i < EXP_TAB_N; i += blockDim.x) {
+        const double T = t->exp2_frac[i];
+        s_exp[i] = __hiloint2double(__double2hiint(T) - (i << 12), __double2loint(T));
+    }
     for (int i = threadIdx.x; i < STREAM_LOG_N; i += blockDim.x) {
         double2 e = t->log_tab[(LOG_OCTAVES - 1) * STREAM_LOG_N + i];     // octave [1/2, 1): (1/c, ln c + LOG1P_C0)
         s_logm[i] = make_double2(e.x, e.y - LOG1P_C0);
@@ -469,7 +473,7 @@ __device__ __forceinline__ double exp_stream(double x, const double* s_exp) {
     double r = fma(kf, KS[7], x);
     r = fma(kf, KS[8], r);                                                  // |r| <= ln2/512
     const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (((unsigned)k << 3) & ((EXP_TAB_N - 1) << 3)));
-    const double Ts = __hiloint2double(__double2hiint(T) + (int)(((unsigned)k << (20 - EXP_TAB_BITS)) & 0xfff00000u), __double2loint(T));
+    const double Ts = __hiloint2double(__double2hiint(T) + (k << (20 - EXP_TAB_BITS)), __double2loint(T));   // pre-compensated table
     double p = fma(r, KS[9], KS[10]);
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
@@ -481,15 +485,16 @@ __device__ __forceinline__ double exp_stream(double x, const double* s_exp) {
 // power of two clamped at 2^-1000 instead of the argument: for arguments below -693 the result is a finite ~1e-301 (0
 // against 1 for the decay factor 1 - exp(-x), the only caller that can get there), so no compare-and-select is needed.
 // Same arithmetic and accuracy as exp_stream on its range.
-template <bool NEG>
+// CLAMP = false: the caller guarantees |x| < 700 or discards the result (the table index is masked either way).
+template <bool NEG, bool CLAMP = true>
 __device__ __forceinline__ double exp_stream_signed(double x, const double* s_exp) {
     const double t = fma(x, NEG ? KS[13] : KS[5], KS[6]);
-    const int k = max(__double2loint(t), -1000 * EXP_TAB_N);
+    const int k = CLAMP ? max(__double2loint(t), -1000 * EXP_TAB_N) : __double2loint(t);
     const double kf = t - KS[6];
     double r = NEG ? fma(kf, KS[7], -x) : fma(kf, KS[7], x);
     r = fma(kf, KS[8], r);                                                  // |r| <= ln2/512
     const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (((unsigned)k << 3) & ((EXP_TAB_N - 1) << 3)));
-    const double Ts = __hiloint2double(__double2hiint(T) + (int)(((unsigned)k << (20 - EXP_TAB_BITS)) & 0xfff00000u), __double2loint(T));
+    const double Ts = __hiloint2double(__double2hiint(T) + (k << (20 - EXP_TAB_BITS)), __double2loint(T));   // pre-compensated table
     double p = fma(r, KS[9], KS[10]);
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);

@@ -126,10 +126,10 @@ __device__ __forceinline__ double inv_fleming_stream(double f, double invF50, do
                                                      const double* s_exp, const double2* s_logm, bool& bad) {
     const double num = alpha_log10e * log_stream(f * invF50, s_logm);       // alpha * log10(f / F50)
     const double y = fma(num, num, 1.0);
-    const double r0 = rsqrt_seed(y);
-    const double e = fma(-(y * r0), r0, 1.0);
-    const double pe = fma(0.375, e, 0.5) * e;
+    const double r0 = rsqrt_seed_donor(y, y);                               // y dies here (no low-word zeroing)
     const double nr = num * r0;
+    const double e = fma(-nr, nr, fma(-r0, r0, 1.0));                       // 1 - y r0^2 with y = num^2 + 1
+    const double pe = fma(0.375, e, 0.5) * e;
     const double fc = fma(0.5, fma(nr, pe, nr), 0.5);
     int lowest = __double2hiint(fc);                                        // fc > 1e-6
     double t = log_stream(fc, s_logm);                                      // ln fc <= 0
@@ -407,10 +407,10 @@ template <bool MODIFIED>
 __device__ __forceinline__ double inv_fleming_from_n(double num, double f, double inv_ftau, double lnscale, const double* s_exp,
                                                      const double2* s_logm, bool& bad) {
     const double y = fma(num, num, 1.0);
-    const double r0 = rsqrt_seed(y);
-    const double e = fma(-(y * r0), r0, 1.0);
-    const double pe = fma(0.375, e, 0.5) * e;
+    const double r0 = rsqrt_seed_donor(y, y);                               // y dies here (no low-word zeroing)
     const double nr = num * r0;
+    const double e = fma(-nr, nr, fma(-r0, r0, 1.0));                       // 1 - y r0^2 with y = num^2 + 1
+    const double pe = fma(0.375, e, 0.5) * e;
     const double fc = fma(0.5, fma(nr, pe, nr), 0.5);
     int lowest = __double2hiint(fc);                                        // fc > 1e-6
     double t = log_stream(fc, s_logm);                                      // ln fc <= 0
@@ -423,7 +423,7 @@ __device__ __forceinline__ double inv_fleming_from_n(double num, double f, doubl
     }
     // fc, x > 1e-6 and the exponent inside (-690, 690): compares on high words (|t| < 690 <=> hi(|t|) < hi(690))
     bad = !((lowest > 0x3eb0c6f7) & ((unsigned)(__double2hiint(t) & 0x7fffffff) < 0x40859000u));
-    return exp_stream_signed<false>(t, s_exp);
+    return exp_stream_signed<false, false>(t, s_exp);                       // |t| >= 690 or NaN is flagged bad above and redone
 }
 
 #define VR_WARPS 8
