@@ -19,7 +19,7 @@ GPU), walkers replicated, the quadrature split by walker, one all-reduce of W do
 value  : terms/s, inputs resident in HBM (theta on the device), CUDA events on the launching stream, max over ranks.
 e2e    : same metric through the public host API (ShardedLikelihood.lnprob: pinned-host theta -> H2D -> kernels
          -> all-reduce -> D2H of W doubles -> sync), host wall clock, max over ranks.
-roofline: the loop is FP64-FMA-pipe bound (no tensor cores, HBM traffic ~0.02 B/term): achieved = terms/s/GPU x 23
+roofline: the loop is FP64-FMA-pipe bound (no tensor cores, HBM traffic ~0.02 B/term): achieved = terms/s/GPU x 22
          FP64-pipe instructions per term (counted in the SASS of k_main<false>) x 2 FLOP, against the register-only
          DFMA rate measured live on the same GPU (lf_fp64_peak, best of 3) x 2 FLOP.  HBM figures are reported beside it.
 """
@@ -37,7 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FP64_INSTR_PER_TERM_BY_KIND = {'free': 23, 'z': 9, 'fixed': 0}    # DFMA/DADD/DMUL per (walker, source) term in k_main<false, MODEL>
+FP64_INSTR_PER_TERM_BY_KIND = {'free': 22, 'z': 9, 'fixed': 0}    # DFMA/DADD/DMUL per (walker, source) term in k_main<false, MODEL>
                                                                     # (tools/sass_loop_mix.py); fixed: sufficient statistics only
 MUFU_PER_TERM_BY_KIND = {'free': 4, 'z': 1, 'fixed': 0}           # FP32 mode: rsqrt, lg2, ex2, rcp / one ex2
 BYTES_PER_SOURCE = 16             # (log10 flux, flux) or (lum, z) per source per sweep

@@ -288,7 +288,7 @@ __device__ __forceinline__ double log_unit(double v, const double2* s_log, int r
 //   fc = 1/2 (1 + n/sqrt(1+n^2))                           VmaxLumFunc.py:118-120
 //   t  = ln(fc) / (1 - exp(-f/ftau))                       VmaxLumFunc.py:124-126, 141   (c2 = -log2(e)/ftau)
 // MODIFIED=false: plain Fleming curve (fcmin falsy, VmaxLumFunc.py:121-122): t = ln(fc).
-// FP64-pipe instruction count (MODIFIED): 9 + 4 + 7 + 2 = 22, +1 for the caller's accumulate.
+// FP64-pipe instruction count (MODIFIED): 8 + 4 + 7 + 2 = 21, +1 for the caller's accumulate.
 template <bool MODIFIED>
 __device__ __forceinline__ void fleming_log_parts(double g, double f, double alpha, double aF, double c2,
                                                   const double* s_exp, const double2* s_log, int repe, int repl,
@@ -298,10 +298,8 @@ __device__ __forceinline__ void fleming_log_parts(double g, double f, double alp
     double r0 = rsqrt_seed_donor(y, y);           // y dies here
     double nr = n * r0;
     double e = fma(-nr, nr, fma(-r0, r0, 1.0));   // 1 - y r0^2 with y = n^2 + 1
-    double p = fma(0.375, e, 0.5);
-    double pe = p * e;
-    double q = fma(nr, pe, nr);
-    double fc = fma(0.5, q, 0.5);
+    double q = fma(fma(0.1875, e, 0.25), e, 0.5); // 1/2 (1 + e/2 + 3 e^2/8)
+    double fc = fma(nr, q, 0.5);
     lg = log_unit(fc, s_log, repl);
     if (MODIFIED) {
         rdec = rcp_fast(one_minus_exp2(f, c2, s_exp, repe));   // f * c2 <= 0, > -8e6 guaranteed by the classifier
@@ -368,21 +366,22 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) e[i] = fma(-n[i], n[i], e[i]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) y[i] = fma(0.375, e[i], 0.5);
+    // fc = 1/2 + 1/2 n rsqrt(y) with rsqrt(y) = r0 (1 + e/2 + 3 e^2/8): = 1/2 + (n r0) (1/2 + e/4 + 3 e^2/16), three instructions
+    for (int i = 0; i < NT; ++i) y[i] = fma(0.1875, e[i], 0.25);
 #pragma unroll
     for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[12] : KC[3]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) e[i] = y[i] * e[i];
+    for (int i = 0; i < NT; ++i) q[i] = fma(y[i], e[i], 0.5);
 #pragma unroll
     for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[13] : KC[4]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) q[i] = fma(n[i], e[i], n[i]);
+    for (int i = 0; i < NT; ++i) fc[i] = fma(n[i], q[i], 0.5);
 #pragma unroll
     for (int i = 0; i < NT; ++i) dec[i] = fma(-Ts[i], p[i], 1.0);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) fc[i] = fma(0.5, q[i], 0.5);
-#pragma unroll
-    for (int i = 0; i < NT; ++i) r0[i] = rcp_seed_donor(dec[i], p[i]);      // p died in the line above
+    // (a donor low word here would save one more IMAD.MOV per term, but the single Newton step below squares the seed error:
+    //  the per-term error bound goes from 1.6e-12 to 4.3e-12, tools/math/term_accuracy.cpp -- not taken)
+    for (int i = 0; i < NT; ++i) r0[i] = rcp_seed(dec[i]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
         // byte offset of table row b = (hi >> 12) - LOG_TAB_BASE: ((hi >> 12) * 32) = (hi >> 7) & ~31, the base folds into

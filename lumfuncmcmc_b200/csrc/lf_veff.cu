@@ -129,8 +129,7 @@ __device__ __forceinline__ double inv_fleming_stream(double f, double invF50, do
     const double r0 = rsqrt_seed_donor(y, y);                               // y dies here (no low-word zeroing)
     const double nr = num * r0;
     const double e = fma(-nr, nr, fma(-r0, r0, 1.0));                       // 1 - y r0^2 with y = num^2 + 1
-    const double pe = fma(0.375, e, 0.5) * e;
-    const double fc = fma(0.5, fma(nr, pe, nr), 0.5);
+    const double fc = fma(nr, fma(fma(0.1875, e, 0.25), e, 0.5), 0.5);     // 1/2 + 1/2 nr (1 + e/2 + 3 e^2/8)
     int lowest = __double2hiint(fc);                                        // fc > 1e-6
     double t = log_stream(fc, s_logm);                                      // ln fc <= 0
     if (MODIFIED) {
@@ -410,8 +409,7 @@ __device__ __forceinline__ double inv_fleming_from_n(double num, double f, doubl
     const double r0 = rsqrt_seed_donor(y, y);                               // y dies here (no low-word zeroing)
     const double nr = num * r0;
     const double e = fma(-nr, nr, fma(-r0, r0, 1.0));                       // 1 - y r0^2 with y = num^2 + 1
-    const double pe = fma(0.375, e, 0.5) * e;
-    const double fc = fma(0.5, fma(nr, pe, nr), 0.5);
+    const double fc = fma(nr, fma(fma(0.1875, e, 0.25), e, 0.5), 0.5);     // 1/2 + 1/2 nr (1 + e/2 + 3 e^2/8)
     int lowest = __double2hiint(fc);                                        // fc > 1e-6
     double t = log_stream(fc, s_logm);                                      // ln fc <= 0
     if (MODIFIED) {

@@ -2,7 +2,8 @@
 // log_unit, one_minus_exp2 and rcp_fast -- the same operations in the same order, fma for fma) against long double.
 // The two MUFU seeds are emulated as the exact value times (1 + delta) with delta drawn uniformly inside the error
 // bounds measured on B200 (tools/microbench/mufu64_accuracy.cu: |1 - y r0^2| <= 1.86e-6, |1 - d r0| <= 9.9e-7), so
-// the maxima printed here hold for any seed inside those bounds.
+// the maxima printed here hold for any seed inside those bounds; the rsqrt seed's low word is a donor's
+// (rsqrt_seed_donor: no zeroing instruction), which adds up to 2^-20, one-sided.
 //     g++ -O2 -o term_accuracy term_accuracy.cpp && ./term_accuracy [samples]
 // tests/test_math_replica.py runs it with 2e6 samples.
 #include <cmath>
@@ -35,14 +36,12 @@ static double unit() { return std::uniform_real_distribution<double>(-1.0, 1.0)(
 static double term_fast(double g, double f, double alpha, double aF, double c2) {
     const double n = fma(alpha, g, aF);
     const double y = fma(n, n, 1.0);
-    const double r0 = (double)(1.0L / sqrtl((long double)y)) * (1.0 + 0.93e-6 * unit());     // rsqrt.approx.ftz.f64
-    const double h = y * r0;
-    const double e = fma(-h, r0, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    const double pe = p * e;
-    const double nr = n * r0;
-    const double q = fma(nr, pe, nr);
-    const double fc = fma(0.5, q, 0.5);
+    // rsqrt.approx.ftz.f64; its low word is a donor's (rsqrt_seed_donor): up to 2^-20 more, one-sided
+    const double r0 = (double)(1.0L / sqrtl((long double)y)) * (1.0 + 0.93e-6 * unit()) * (1.0 + 9.54e-7 * fabs(unit()));
+    const double nr = n * r0;                        // as lf_math.cuh: e = 1 - r0^2 - (n r0)^2, fc = 1/2 + nr (1/2 + e/4 + 3 e^2/16)
+    const double e = fma(-nr, nr, fma(-r0, r0, 1.0));
+    const double q = fma(fma(0.1875, e, 0.25), e, 0.5);
+    const double fc = fma(nr, q, 0.5);
     // log_unit
     int b = (hi(fc) >> 12) - LOG_TAB_BASE;
     if (b < 0) b = 0;
@@ -75,7 +74,7 @@ static double term_fast(double g, double f, double alpha, double aF, double c2) 
     pp = fma(r, pp, EXP2_C0);
     const double dec = fma(-Ts, pp, 1.0);
     // rcp_fast
-    const double s0 = (double)(1.0L / (long double)dec) * (1.0 + 9.9e-7 * unit());         // rcp.approx.ftz.f64
+    const double s0 = (double)(1.0L / (long double)dec) * (1.0 + 9.9e-7 * unit());         // rcp.approx.ftz.f64 (low word zero)
     const double ee = fma(-dec, s0, 1.0);
     const double rdec = fma(s0, ee, s0);
     return lg * rdec;
