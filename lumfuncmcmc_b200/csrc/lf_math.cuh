@@ -379,8 +379,10 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) dec[i] = fma(-Ts[i], p[i], 1.0);
 #pragma unroll
-    // (a donor low word here would save one more IMAD.MOV per term, but the single Newton step below squares the seed error:
-    //  the per-term error bound goes from 1.6e-12 to 4.3e-12, tools/math/term_accuracy.cpp -- not taken)
+    // (a donor low word here would save one more IMAD.MOV per term.  An arbitrary donor costs accuracy -- the single Newton
+    //  step below squares the seed error: per-term bound 1.6e-12 -> 4.3e-12, tools/math/term_accuracy.cpp.  kf = k / 256 as
+    //  the donor, whose low word is zero for |k| < 2^20, is bit-identical and was measured: 9.3 instead of 10.5 non-FP64
+    //  instructions per term, and 1.7 % SLOWER in the product kernel (6.43 vs 6.54e11 terms/s) -- not taken.)
     for (int i = 0; i < NT; ++i) r0[i] = rcp_seed(dec[i]);
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
