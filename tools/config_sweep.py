@@ -15,8 +15,8 @@ quick = len(sys.argv) > 1
 
 # FP64-pipe instructions per (walker, source) term and per (walker, quadrature point) of the fast kernels (SASS counts,
 # tools/sass_loop_mix.py): the quadrature is real work that "terms/s" does not count -- at 1e5 sources it is the larger half
-FP64_TERM = {'free': 23, 'z': 9, 'fixed': 0}
-FP64_POINT = {'free': 36, 'z': 12, 'fixed': 12}
+FP64_TERM = {'free': 22, 'z': 9, 'fixed': 0}
+FP64_POINT = {'free': 33, 'z': 11, 'fixed': 11}
 PEAK = {}
 
 
@@ -66,18 +66,33 @@ flux = 10 ** rng.uniform(-17.2, -14.5, n)
 fi = np.array([0, n // 5, 2 * n // 5, 3 * n // 5, 4 * n // 5, n], dtype=np.int64)
 edges = np.linspace(lum.min() * 1.001, lum.max(), 51)
 ve = VeffEngine()
+flim = [2.72, 3.61, 2.55, 3.31, 3.30]
 for _ in range(2):
     t0 = time.perf_counter()
-    phi, counts, sums = ve.veff_bin(flux, lum, fi, [2.72, 3.61, 2.55, 3.31, 3.30], 4.56, 0.1, 1.9e6, 3.0e10, edges)
+    phi, counts, sums = ve.veff_bin(flux, lum, fi, flim, 4.56, 0.1, 1.9e6, 3.0e10, edges)
     wall = time.perf_counter() - t0
 kms = ve.last_kernel_ms()
 want = np.histogram(lum[(lum >= edges[0]) & (lum < edges[-1])], bins=edges)[0]
-print("\nVeff: N=%d nbins=50  kernel %.3f ms (%.3e sources/s, %.1f GB/s of 26 B/source: flux, lum in; phi, bin i16 out)  host call %.1f ms  counts bit-exact: %s"
-      % (n, kms, n / (kms * 1e-3), 26.0 * n / (kms * 1e-3) / 1e9, wall * 1e3, np.array_equal(counts, want)))
+print("\nVeff, host-buffer call (lf_veff_bin: uploads flux and lum, downloads the weights -- PCIe-bound): N=%d nbins=50  kernel %.3f ms  "
+      "host call %.1f ms  counts bit-exact: %s" % (n, kms, wall * 1e3, np.array_equal(counts, want)))
+# the route VeffLF takes: sample resident on the device, weights stay there
+t0 = time.perf_counter()
+ve.veff_set_sample(flux, lum, fi)
+up = time.perf_counter() - t0
+best_k, best_w = 1e9, 1e9
+for _ in range(5):
+    t0 = time.perf_counter()
+    _, counts_r, sums_r = ve.veff_bin_resident(flim, 4.56, 0.1, 1.9e6, 3.0e10, edges)
+    best_w = min(best_w, time.perf_counter() - t0)
+    best_k = min(best_k, ve.last_kernel_ms())
+print("Veff, resident sample (lf_veff_set_sample once: %.1f ms; then lf_veff_bin_resident): kernels %.4f ms (%.3e sources/s, %.1f GB/s "
+      "of 26 B/source: flux, u, row in; phi out)  host call %.3f ms  counts bit-exact: %s  sums equal to the host-buffer call: %s"
+      % (up * 1e3, best_k, n / (best_k * 1e-3), 26.0 * n / (best_k * 1e-3) / 1e9, best_w * 1e3, np.array_equal(counts_r, want),
+         np.allclose(sums_r, sums, rtol=1e-13, atol=0)))
 mult = np.bincount(rng.integers(0, n, n), minlength=n)
 t0 = time.perf_counter()
 bc, bs = ve.boot_bin(mult)
 wall = time.perf_counter() - t0
 kms = ve.last_kernel_ms()
-print("bootstrap replicate: kernel %.3f ms (%.1f GB/s of 14 B/source: bin i16 + phi f64 + multiplicity i32)  host call %.1f ms  counts sum %d" % (
-    kms, 14.0 * n / (kms * 1e-3) / 1e9, wall * 1e3, bc.sum()))
+print("bootstrap replicate, host-drawn multiplicities (lf_boot_bin: uploads 4 B per source): kernel %.3f ms (%.1f GB/s of 14 B/source: "
+      "row i16 + phi f64 + multiplicity i32)  host call %.1f ms  counts sum %d" % (kms, 14.0 * n / (kms * 1e-3) / 1e9, wall * 1e3, bc.sum()))
