@@ -221,7 +221,7 @@ __global__ void k_zcolumns(KArgs a) {
 // main kernels: grid of warp work items = (walker group of 32) x (slab of sources | slab of quadrature points)
 // ------------------------------------------------------------------------------------------------
 // one 12-warp block per SM (3 warps per scheduler, up to 168 registers per thread): the shared-memory tables
-// (130 KB) are filled once per SM.  Measured sweep of (sources in lock-step, warps): profiles/README.md
+// (217 KB) are filled once per SM.  Measured sweep of (sources in lock-step, warps): profiles/README.md
 #ifndef LF_WARPS_PER_BLOCK
 #define LF_WARPS_PER_BLOCK 12
 #endif
@@ -952,8 +952,8 @@ extern "C" int lf_ndim(const lf_ctx* ctx) { return ctx ? ctx->ndim : -1; }
 
 static void fill_tables(Tables& t) {
     for (int j = 0; j < EXP_TAB_N; ++j) t.exp2_frac[j] = (double)exp2l((long double)j / EXP_TAB_N);
-    for (int i = 0; i < EXPB_N; ++i) t.exp2_big[i] = (double)exp2l((long double)(EXPB_KMIN + i) / EXP_TAB_N);
-    t.exp2_big[EXPB_N] = 1.0;
+    for (int i = 0; i < EXPB_N; ++i) t.exp2_big[i] = (double)((long double)EXP_TAB_SCALE * exp2l((long double)(EXPB_KMIN + i) / EXP_TAB_N));
+    t.exp2_big[EXPB_N] = EXP_TAB_SCALE;
     const int M = 1 << LOG_MANT_BITS;
     for (int b = 0; b < LOG_OCTAVES * M; ++b) {
         int E = -LOG_OCTAVES + b / M, j = b % M;

@@ -4,8 +4,9 @@
 // routine here is counted in FP64-pipe instructions, and in how many of them read THREE distinct register operands
 // (measured on B200: a DFMA with three register sources sustains 76 % of the rate of one with an immediate /
 // constant-bank operand).  Integer / MUFU / LDS work rides in the issue slots the FP64 pipe leaves free.
-//   * reciprocal square root and reciprocal: one MUFU seed (rsqrt/rcp.approx.ftz.f64, ~2^-22) + one
-//     third-order correction (error ~2^-63): 5 resp. 3 FP64 instructions, no IEEE div/sqrt sequences.
+//   * reciprocal square root and reciprocal: one MUFU seed (rsqrt/rcp.approx.ftz.f64, ~2^-20) + a correction folded into the
+//     value that needs it (third-order for the rsqrt, one Newton step for the reciprocal), no IEEE div/sqrt sequences; the
+//     rsqrt seed is built in its argument's register pair (rsqrt_seed_donor: no low-word zeroing instruction).
 //   * exp: base-2 range reduction done by ONE fma against 1.5*2^44 (the product f*c2 is never rounded on its own),
 //     256-entry table of 2^(j/256) in shared memory + minimax degree-3 polynomial on |r| <= 2^-9 (1.8e-14).
 //   * log: one table lookup indexed by the top 20 bits of the argument (exponent AND 8 mantissa bits, covering
@@ -15,7 +16,7 @@
 // Error budget (tools/math/fit_coeffs.py, tests/test_engine_gpu.py): the north-star tolerance is 1e-10 RELATIVE on
 // lnprob, whose terms are O(10) each, so a per-term absolute error of 1e-12 leaves three orders of magnitude of
 // margin; the polynomial degrees below are chosen for ~5e-13 per term instead of the 1e-16 of a libm-grade routine
-// (23 FP64-pipe instructions per term instead of 28).  Anything outside the validated argument ranges goes to the
+// (22 FP64-pipe instructions per term instead of 28).  Anything outside the validated argument ranges goes to the
 // literal kernels (see k_prologue in lf_engine.cu).
 #pragma once
 #include <cuda_runtime.h>
@@ -41,11 +42,6 @@ constexpr double MPC_CM_REF = 3.086e24;                             // the refer
 #ifndef LF_EXP_BIG
 #define LF_EXP_BIG 1
 #endif
-#ifndef LF_EXP_MASKED
-#define LF_EXP_MASKED 0      /* big table: index = shifted integer (0, default) or masked low mantissa word (1): the masked
-                                form saves a shift per term and is 1.4 % faster for the loop in isolation, but the product kernel
-                                measures 0.3 % SLOWER with it (6.068 vs 6.085e11 terms/s, three alternating runs each) */
-#endif
 constexpr int EXP_TAB_BITS = 8, EXP_TAB_N = 1 << EXP_TAB_BITS, EXP_TAB_REP = LF_EXP_REP;   // small table: 256*16*8 B = 32 KB, replicated x16 (a half-warp never bank-conflicts)
 // LF_EXP_BIG: one unreplicated table of 2^(k/256) for k = EXPB_KMIN .. 0 (80 KB): the decay factor 2^(x2), x2 <= 0, is a
 // single look-up with the integer k clamped at -40*256 (2^-40 = 9e-13 against 1, times |ln fc| < 0.01 for a source that
@@ -68,41 +64,32 @@ constexpr int LOG_TAB_N = LOG_OCTAVES * (1 << LOG_MANT_BITS) + 1, LOG_TAB_REP = 
 constexpr int LOG_TAB_BASE = (1023 - LOG_OCTAVES) << LOG_MANT_BITS;                        // index of 2^-12 in (hi >> 12)
 constexpr double LOG_ARG_MIN = 0x1p-12;
 
-// polynomial / reduction constants live in the constant bank: DFMA reads them as c[3][off] operands (two register
-// sources instead of three, and no IMAD.MOV/UMOV pairs to materialise 64-bit immediates)
+// Polynomial / reduction constants.  On sm_100a a constant reaches the FP64 pipe as an immediate (only when its low 32 bits
+// are zero), through a uniform register, or from a vector register; ptxas keeps only some __constant__ values in uniform
+// registers, and one it parks in a vector register turns "fma(r, p, C)" into a DFMA with three distinct register sources
+// (76 % rate; 6 of 23 per term in math v4).  So the polynomials are arranged to need as few non-immediate constants as possible:
+//   * 2^r = C0 (1 + c1 r + c2 r^2 + c3 r^3): C0 is folded into the table entries (EXP_TAB_SCALE, applied where the shared-memory
+//     tables are filled / on the host for the big table), the last Horner step adds the immediate 1.0;
+//   * log1p(eps) = c0 + eps + c2 eps^2 + c3 eps^3 with the linear coefficient FIXED at 1 in the minimax fit (same 4.55e-13
+//     as the free fit, tools/math/fit_coeffs.py) and c0 folded into the ln c column of the log table;
+//   * the cubic coefficients are rounded to their high words (immediates): moves the cubic term by <= 1.2e-7 relative, i.e.
+//     <= 5e-17 in 2^r and 3e-16 in log1p on |r|, |eps| <= 2^-9.
+// What is left (c1, c2 of 2^r, c2 of log1p, log2(e)) is written as literals: ptxas materialises a literal in a UNIFORM register
+// (a pair of UMOVs, hoisted or ~0.4 per term) and feeds it to the DFMA as a UR operand, whereas values read from a
+// __constant__ array ended up in vector registers (LDC.64 inside the loop) for half of the constants in math v4 and for all
+// four of them once only four were left.  The magic number has a zero low word: an immediate as well.
 constexpr double MAGIC44 = 26388279066624.0;                       // 1.5 * 2^44: ulp 2^-8, low mantissa bits = round(256 x)
 // minimax fits on [-2^-9, 2^-9] (tools/math/fit_coeffs.py)
-constexpr double LOG1P_C0 = 4.5474875525573243324e-13;             // folded into the ln c column of the log table
-constexpr double LOG1P_C1 = 0.9999999999985449674, LOG1P_C2 = -0.50000095367660766342, LOG1P_C3 = 0.33333447770293183222;
-constexpr double EXP2_C0 = 0.99999999999998250473, EXP2_C1 = 0.69314718055993561091, EXP2_C2 = 0.24022654364935376114,
-                 EXP2_C3 = 0.055504116293577099979;
-// LF_EXP_MASKED variant of the one-look-up decay factor 2^(x2), x2 <= 0 (big table): the reduction constant 1.5 * 2^41 leaves round(2048 x2) in the low
-// mantissa word; with its low three bits masked off (a LOP3, which issues in the shadow of a DFMA) that word IS the byte
-// offset of the table entry 2^(m / 256), m = floor(round(2048 x2) / 8) -- no shift -- and the same masked double gives m / 256
-// for the remainder r = x2 - m / 256 in [-2^-12, 15 * 2^-12): minimax degree 3 on that interval, 1.75e-14 (fit_coeffs.py).
-constexpr double MAGIC41 = 3298534883328.0;                        // 1.5 * 2^41: ulp 2^-11
-constexpr double EXP2B_C0 = 1.000000000000007627, EXP2B_C1 = 0.69314718062664656388, EXP2B_C2 = 0.24022637497468078452,
-                 EXP2B_C3 = 0.055569904189805140222;
-static __constant__ double KC[16] = {
-    MAGIC44,                // 0
-    EXP2_C3,                // 1
-    EXP2_C2,                // 2
-    EXP2_C1,                // 3
-    EXP2_C0,                // 4
-    LOG1P_C3,               // 5
-    LOG1P_C2,               // 6
-    LOG1P_C1,               // 7
-    LOG2E,                  // 8
-    MAGIC41,                // 9
-    EXP2B_C3,               // 10
-    EXP2B_C2,               // 11
-    EXP2B_C1,               // 12
-    EXP2B_C0,               // 13
-    0.0, 0.0};
-
+constexpr double LOG1P_C0 = 4.554593420756767562287e-13;           // folded into the ln c column of the log table
+constexpr double LOG1P_C2 = -0.5000009544211419596383;
+constexpr double LOG1P_C3_HI = 0x1.55557p-2;                       // 0.3333337151419489602819 rounded to its high word
+constexpr double EXP2_C0 = 0.99999999999998250473;                 // = EXP_TAB_SCALE; the free fit is C0 (1, c1, c2, c3):
+constexpr double EXP2N_C1 = 0.6931471805599477377071, EXP2N_C2 = 0.2402265436493579639682;
+constexpr double EXP2N_C3_HI = 0x1.c6b09p-5;                       // 0.0555041162935780710385 rounded to its high word
+constexpr double EXP_TAB_SCALE = EXP2_C0;
 struct __align__(16) Tables {    // device-global master copies (filled by the host at lf_create)
     double exp2_frac[EXP_TAB_N];        // 2^(j/256)
-    double exp2_big[EXPB_N + 1];        // 2^(k/256), k = EXPB_KMIN .. 0
+    double exp2_big[EXPB_N + 1];        // EXP_TAB_SCALE * 2^(k/256), k = EXPB_KMIN .. 0
     double2 log_tab[LOG_TAB_N + 1];     // bin b <-> argument bits (hi >> 12) == LOG_TAB_BASE + b:
                                         //   (1/c_b, ln c_b), c_b = bin centre incl. its power of two; last: (1, 0)
 };
@@ -158,7 +145,7 @@ __device__ __forceinline__ double rcp_fast(double d) {
 __device__ __forceinline__ void load_exp_replicated(const Tables* __restrict__ t, double* s_exp_rep) {
     for (int i = threadIdx.x; i < EXPR_SMEM_DOUBLES; i += blockDim.x) {
         const int j = i / EXPR_ROW_DOUBLES;
-        const double T = t->exp2_frac[j];
+        const double T = t->exp2_frac[j] * EXP_TAB_SCALE;
         s_exp_rep[i] = __hiloint2double(__double2hiint(T) - (j << 12), __double2loint(T));
     }
 }
@@ -170,7 +157,7 @@ __device__ __forceinline__ void load_tables(const Tables* __restrict__ t, double
         for (int i = threadIdx.x; i < (EXPB_N + 1) / 2; i += blockDim.x) dst[i] = src[i];
     }
 #else
-    for (int i = threadIdx.x; i < EXP_TAB_N * EXP_TAB_REP; i += blockDim.x) s_exp[i] = t->exp2_frac[i / EXP_TAB_REP];
+    for (int i = threadIdx.x; i < EXP_TAB_N * EXP_TAB_REP; i += blockDim.x) s_exp[i] = t->exp2_frac[i / EXP_TAB_REP] * EXP_TAB_SCALE;
 #endif
     for (int i = threadIdx.x; i < LOG_TAB_N * LOG_TAB_REP; i += blockDim.x) s_log[i] = t->log_tab[i / LOG_TAB_REP];
 }
@@ -179,9 +166,9 @@ __device__ __forceinline__ void load_tables(const Tables* __restrict__ t, double
 // formed inside the two fmas only (no separately rounded product).  Needs |x2| < 8.3e6.  FP64 instructions: 6.
 template <bool BIG>
 __device__ __forceinline__ void exp2_parts(double a, double b, const double* s_exp, int rep, int kmin, double& Ts, double& p) {
-    double t = fma(a, b, KC[0]);
+    double t = fma(a, b, MAGIC44);
     int k = __double2loint(t);                    // round(256 x2)
-    double kf = t - KC[0];
+    double kf = t - MAGIC44;
     double r = fma(a, b, -kf);                    // |r| <= 2^-9, exact up to one rounding
     double T;
     int K = max(k >> EXP_TAB_BITS, kmin);         // keeps the exponent field valid
@@ -192,33 +179,23 @@ __device__ __forceinline__ void exp2_parts(double a, double b, const double* s_e
         T = s_exp[(k & (EXP_TAB_N - 1)) * EXP_TAB_REP + rep];
     }
     Ts = __hiloint2double(__double2hiint(T) + (K << 20), __double2loint(T));
-    p = fma(r, KC[1], KC[2]);
-    p = fma(r, p, KC[3]);
-    p = fma(r, p, KC[4]);
+    p = fma(r, EXP2N_C3_HI, EXP2N_C2);
+    p = fma(r, p, EXP2N_C1);
+    p = fma(r, p, 1.0);                           // the table entry carries EXP_TAB_SCALE
 }
 
 // 1 - 2^(f * c2) for f * c2 in (-8.3e6, 0]; ABSOLUTE accuracy ~2e-14.  FP64 instructions: 7
 __device__ __forceinline__ double one_minus_exp2(double f, double c2, const double* s_exp, int rep) {
     double Ts, p;
-#if LF_EXP_BIG && !LF_EXP_MASKED
-    double t = fma(f, c2, KC[0]);
+#if LF_EXP_BIG
+    double t = fma(f, c2, MAGIC44);
     int k = max(__double2loint(t), EXPB_KMIN);    // round(256 x2), clamped: 2^-40 is 0 against 1 at the budget of this routine
-    double kf = t - KC[0];
+    double kf = t - MAGIC44;
     double r = fma(f, c2, -kf);
     Ts = s_exp[k - EXPB_KMIN];
-    p = fma(r, KC[1], KC[2]);
-    p = fma(r, p, KC[3]);
-    p = fma(r, p, KC[4]);
-#elif LF_EXP_BIG
-    double t = fma(f, c2, KC[9]);
-    const int k8 = __double2loint(t) & ~7;        // 8 * floor(round(2048 x2) / 8): byte offset of the entry, from the table's end
-    double kf = __hiloint2double(__double2hiint(t), k8) - KC[9];
-    double r = fma(f, c2, -kf);
-    // clamped: 2^-40 is 0 against 1 at the budget of this routine (needs |x2| < 2^20: the classifier's fcap / ftau bound)
-    Ts = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (max(k8, 8 * EXPB_KMIN) - 8 * EXPB_KMIN));
-    p = fma(r, KC[10], KC[11]);
-    p = fma(r, p, KC[12]);
-    p = fma(r, p, KC[13]);
+    p = fma(r, EXP2N_C3_HI, EXP2N_C2);
+    p = fma(r, p, EXP2N_C1);
+    p = fma(r, p, 1.0);                           // the table entry carries EXP_TAB_SCALE
 #else
     exp2_parts<false>(f, c2, s_exp, rep, -1000, Ts, p);  // 2^x2 < 2^-1000 is 0 against 1
 #endif
@@ -238,7 +215,7 @@ template <bool BIG>
 __device__ __forceinline__ double exp_full(double x, const double* s_exp, int rep) {
     bool under = x < -707.0;
     double Ts, p;
-    exp2_parts<BIG>(under ? -707.0 : x, KC[8], s_exp, rep, -1022, Ts, p);
+    exp2_parts<BIG>(under ? -707.0 : x, LOG2E, s_exp, rep, -1022, Ts, p);
     return under ? 0.0 : Ts * p;
 }
 
@@ -247,17 +224,17 @@ __device__ __forceinline__ double exp_full(double x, const double* s_exp, int re
 // stay inside (-1021, 1023) leave it off.  Same values as exp2_parts<false> bit for bit (same T_j, K, r and polynomial).
 template <bool CLAMP>
 __device__ __forceinline__ void exp2r_parts(double a, double b, const double* s_rep, unsigned lane8, double& Ts, double& p) {
-    double t = fma(a, b, KC[0]);
+    double t = fma(a, b, MAGIC44);
     int k = __double2loint(t);                    // round(256 x2)
-    double kf = t - KC[0];
+    double kf = t - MAGIC44;
     double r = fma(a, b, -kf);
     if (CLAMP) k = max(k, -1022 * EXP_TAB_N);
     const unsigned off = __byte_perm((unsigned)k, lane8, 0x7704);           // (j << 8) | lane8
     const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_rep) + off);
     Ts = __hiloint2double(__double2hiint(T) + (k << 12), __double2loint(T));
-    p = fma(r, KC[1], KC[2]);
-    p = fma(r, p, KC[3]);
-    p = fma(r, p, KC[4]);
+    p = fma(r, EXP2N_C3_HI, EXP2N_C2);
+    p = fma(r, p, EXP2N_C1);
+    p = fma(r, p, 1.0);                           // the table entry carries EXP_TAB_SCALE
 }
 template <bool CLAMP>
 __device__ __forceinline__ double exp2r_full(double x2, const double* s_rep, unsigned lane8) {
@@ -269,7 +246,7 @@ __device__ __forceinline__ double exp2r_full(double x2, const double* s_rep, uns
 __device__ __forceinline__ double expr_full(double x, const double* s_rep, unsigned lane8) {
     bool under = x < -707.0;
     double Ts, p;
-    exp2r_parts<false>(under ? -707.0 : x, KC[8], s_rep, lane8, Ts, p);
+    exp2r_parts<false>(under ? -707.0 : x, LOG2E, s_rep, lane8, Ts, p);
     return under ? 0.0 : Ts * p;
 }
 
@@ -278,8 +255,8 @@ __device__ __forceinline__ double log_unit(double v, const double2* s_log, int r
     int b = max((__double2hiint(v) >> (20 - LOG_MANT_BITS)) - LOG_TAB_BASE, 0);
     double2 tb = s_log[b * LOG_TAB_REP + rep];
     double eps = fma(v, tb.x, -1.0);              // v / c_b - 1, |eps| <= 2^-9
-    double a = fma(eps, KC[5], KC[6]);
-    a = fma(eps, a, KC[7]);
+    double a = fma(eps, LOG1P_C3_HI, LOG1P_C2);
+    a = fma(eps, a, 1.0);
     return fma(eps, a, tb.y);                     // tb.y = ln c_b + LOG1P_C0
 }
 
@@ -326,7 +303,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) n[i] = fma(al[i], ux[i], af[i]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) t[i] = fma(uy[i], cc[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[9] : KC[0]);
+    for (int i = 0; i < NT; ++i) t[i] = fma(uy[i], cc[i], MAGIC44);
 #pragma unroll
     for (int i = 0; i < NT; ++i) y[i] = fma(n[i], n[i], 1.0);
 #pragma unroll
@@ -334,19 +311,12 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
     // exp branch while the MUFUs are in flight
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-#if LF_EXP_BIG && LF_EXP_MASKED
-        k[i] = __double2loint(t[i]) & ~7;
-        t[i] = __hiloint2double(__double2hiint(t[i]), k[i]) - KC[9];
-#else
         k[i] = __double2loint(t[i]);
-        t[i] = t[i] - KC[0];
-#endif
+        t[i] = t[i] - MAGIC44;
     }
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
-#if LF_EXP_BIG && LF_EXP_MASKED
-        Ts[i] = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (max(k[i], 8 * EXPB_KMIN) - 8 * EXPB_KMIN));
-#elif LF_EXP_BIG
+#if LF_EXP_BIG
         Ts[i] = s_exp[max(k[i], EXPB_KMIN) - EXPB_KMIN];
 #else
         double T = s_exp[(k[i] & (EXP_TAB_N - 1)) * EXP_TAB_REP + repe];
@@ -357,7 +327,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) r[i] = fma(uy[i], cc[i], -t[i]);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[10] : KC[1], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[11] : KC[2]);
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], EXP2N_C3_HI, EXP2N_C2);
     // rsqrt correction: e = 1 - y r0^2 with y = n^2 + 1 written as 1 - r0^2 - (n r0)^2 (same three instructions, y not needed)
 #pragma unroll
     for (int i = 0; i < NT; ++i) n[i] = n[i] * r0[i];
@@ -369,11 +339,11 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
     // fc = 1/2 + 1/2 n rsqrt(y) with rsqrt(y) = r0 (1 + e/2 + 3 e^2/8): = 1/2 + (n r0) (1/2 + e/4 + 3 e^2/16), three instructions
     for (int i = 0; i < NT; ++i) y[i] = fma(0.1875, e[i], 0.25);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[12] : KC[3]);
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], EXP2N_C1);
 #pragma unroll
     for (int i = 0; i < NT; ++i) q[i] = fma(y[i], e[i], 0.5);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], (LF_EXP_BIG && LF_EXP_MASKED) ? KC[13] : KC[4]);
+    for (int i = 0; i < NT; ++i) p[i] = fma(r[i], p[i], 1.0);
 #pragma unroll
     for (int i = 0; i < NT; ++i) fc[i] = fma(n[i], q[i], 0.5);
 #pragma unroll
@@ -399,9 +369,9 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #pragma unroll
     for (int i = 0; i < NT; ++i) r0[i] = fma(r0[i], e[i], r0[i]);           // 1 / dec
 #pragma unroll
-    for (int i = 0; i < NT; ++i) lg[i] = fma(fc[i], KC[5], KC[6]);
+    for (int i = 0; i < NT; ++i) lg[i] = fma(fc[i], LOG1P_C3_HI, LOG1P_C2);
 #pragma unroll
-    for (int i = 0; i < NT; ++i) lg[i] = fma(fc[i], lg[i], KC[7]);
+    for (int i = 0; i < NT; ++i) lg[i] = fma(fc[i], lg[i], 1.0);
 #pragma unroll
     for (int i = 0; i < NT; ++i) lg[i] = fma(fc[i], lg[i], tb[i].y);
 #pragma unroll

@@ -13,19 +13,12 @@
 #include <cstring>
 #include <random>
 #include <vector>
-#ifndef LF_EXP_MASKED
-#define LF_EXP_MASKED 0          /* as lf_math.cuh: 0 = shifted table index (product default), 1 = masked low mantissa word */
-#endif
-static const double MAGIC41 = 3298534883328.0, MAGIC44 = 26388279066624.0, LOG2E = 1.442695040888963407359924681001892137;
-static const double LOG1P_C0 = 4.5474875525573243324e-13, LOG1P_C1 = 0.9999999999985449674, LOG1P_C2 = -0.50000095367660766342,
-                    LOG1P_C3 = 0.33333447770293183222;
-#if LF_EXP_MASKED
-static const double EXP2_C0 = 1.000000000000007627, EXP2_C1 = 0.69314718062664656388, EXP2_C2 = 0.24022637497468078452,
-                    EXP2_C3 = 0.055569904189805140222;      // EXP2B_*: minimax on [-2^-12, 15 * 2^-12)
-#else
-static const double EXP2_C0 = 0.99999999999998250473, EXP2_C1 = 0.69314718055993561091, EXP2_C2 = 0.24022654364935376114,
-                    EXP2_C3 = 0.055504116293577099979;
-#endif
+static const double MAGIC44 = 26388279066624.0, LOG2E = 1.442695040888963407359924681001892137;
+// as lf_math.cuh ("math v6"): log1p fit with the linear coefficient fixed at 1, 2^r normalised by its constant term (which the
+// table entries carry), cubic coefficients rounded to their high words (DFMA immediates)
+static const double LOG1P_C0 = 4.554593420756767562287e-13, LOG1P_C2 = -0.5000009544211419596383, LOG1P_C3_HI = 0x1.55557p-2;
+static const double EXP2_C0 = 0.99999999999998250473, EXP2N_C1 = 0.6931471805599477377071, EXP2N_C2 = 0.2402265436493579639682,
+                    EXP2N_C3_HI = 0x1.c6b09p-5;
 static const int LOG_OCTAVES = 12, M = 256, LOG_TAB_BASE = (1023 - LOG_OCTAVES) << 8, EXPB_KMIN = -40 * 256;
 static std::vector<double> tab_invc, tab_lnc, exp_big;
 static inline int hi(double v) { uint64_t u; memcpy(&u, &v, 8); return (int)(u >> 32); }
@@ -46,32 +39,19 @@ static double term_fast(double g, double f, double alpha, double aF, double c2) 
     int b = (hi(fc) >> 12) - LOG_TAB_BASE;
     if (b < 0) b = 0;
     const double eps = fma(fc, tab_invc[b], -1.0);
-    double a = fma(eps, LOG1P_C3, LOG1P_C2);
-    a = fma(eps, a, LOG1P_C1);
+    double a = fma(eps, LOG1P_C3_HI, LOG1P_C2);
+    a = fma(eps, a, 1.0);
     const double lg = fma(eps, a, tab_lnc[b]);
-    // one_minus_exp2 (one-look-up table; low word of the reduction = round(2048 x2), masked to a multiple of 8 = byte offset
-    // of the entry; clamped at -40 * 256 entries)
-#if LF_EXP_MASKED
-    const double t = fma(f, c2, MAGIC41);
-    const int k8 = lo(t) & ~7;
-    uint64_t tb; memcpy(&tb, &t, 8);
-    tb = (tb & 0xffffffff00000000ULL) | (uint32_t)k8;
-    double t8; memcpy(&t8, &tb, 8);
-    const double kf = t8 - MAGIC41;
-    const double r = fma(f, c2, -kf);
-    int k = k8 / 8;                                  // exact: k8 is a multiple of 8
-    if (k < EXPB_KMIN) k = EXPB_KMIN;
-#else
-    const double t = fma(f, c2, MAGIC44);            // k clamped at -40 * 256
+    // one_minus_exp2 (one look-up in the big table, k clamped at -40 * 256 entries)
+    const double t = fma(f, c2, MAGIC44);
     int k = lo(t);
     if (k < EXPB_KMIN) k = EXPB_KMIN;
     const double kf = t - MAGIC44;
     const double r = fma(f, c2, -kf);
-#endif
-    const double Ts = exp_big[k - EXPB_KMIN];
-    double pp = fma(r, EXP2_C3, EXP2_C2);
-    pp = fma(r, pp, EXP2_C1);
-    pp = fma(r, pp, EXP2_C0);
+    const double Ts = exp_big[k - EXPB_KMIN];        // EXP2_C0 * 2^(k / 256)
+    double pp = fma(r, EXP2N_C3_HI, EXP2N_C2);
+    pp = fma(r, pp, EXP2N_C1);
+    pp = fma(r, pp, 1.0);
     const double dec = fma(-Ts, pp, 1.0);
     // rcp_fast
     const double s0 = (double)(1.0L / (long double)dec) * (1.0 + 9.9e-7 * unit());         // rcp.approx.ftz.f64 (low word zero)
@@ -83,7 +63,7 @@ static double term_fast(double g, double f, double alpha, double aF, double c2) 
 int main(int argc, char** argv) {
     const long nsamp = argc > 1 ? atol(argv[1]) : 20000000L;
     tab_invc.resize(LOG_OCTAVES * M + 2); tab_lnc.resize(LOG_OCTAVES * M + 2); exp_big.resize(-EXPB_KMIN + 2);
-    for (int i = 0; i <= -EXPB_KMIN; ++i) exp_big[i] = (double)exp2l((long double)(EXPB_KMIN + i) / 256);
+    for (int i = 0; i <= -EXPB_KMIN; ++i) exp_big[i] = (double)((long double)EXP2_C0 * exp2l((long double)(EXPB_KMIN + i) / 256));
     for (int b = 0; b < LOG_OCTAVES * M; ++b) {
         const int E = -LOG_OCTAVES + b / M, j = b % M;
         const long double cm = 1.0L + ((long double)j + 0.5L) / M;

@@ -1,7 +1,7 @@
 // Is the walker x source loop of k_main<false, FREE> held back by shared-memory bank conflicts, or by issue slots?
 //
 // The loop body of the product kernel (fleming_terms_v<4> from lf_math.cuh: two sources x two walkers per lane, 22 FP64 +
-// ~10.5 other instructions per term) is run here on an L1-resident block of synthetic sources, 12 warps per SM with the
+// ~10.7 other instructions per term) is run here on an L1-resident block of synthetic sources, 12 warps per SM with the
 // product's 217 KB of tables, in two set-ups that execute the IDENTICAL instruction stream:
 //   distinct : every lane carries its own walker constants, as in a real ensemble -> per-lane table indices -> the bank
 //              conflicts ncu reports for the product kernel (39 % of the shared wavefronts)
@@ -20,8 +20,8 @@ using namespace lfm;
 
 static void fill_tables(Tables& t) {          // as lf_engine.cu
     for (int j = 0; j < EXP_TAB_N; ++j) t.exp2_frac[j] = (double)exp2l((long double)j / EXP_TAB_N);
-    for (int i = 0; i < EXPB_N; ++i) t.exp2_big[i] = (double)exp2l((long double)(EXPB_KMIN + i) / EXP_TAB_N);
-    t.exp2_big[EXPB_N] = 1.0;
+    for (int i = 0; i < EXPB_N; ++i) t.exp2_big[i] = (double)((long double)EXP_TAB_SCALE * exp2l((long double)(EXPB_KMIN + i) / EXP_TAB_N));
+    t.exp2_big[EXPB_N] = EXP_TAB_SCALE;
     const int M = 1 << LOG_MANT_BITS;
     for (int b = 0; b < LOG_OCTAVES * M; ++b) {
         int E = -LOG_OCTAVES + b / M, j = b % M;
@@ -142,7 +142,7 @@ int main() {
         }
         const double terms_per_s = terms_per_warp * 32.0 * WARPS * sms / (best * 1e-3);
         const double cyc_per_term = (double)sms * 4 * 32 * (khz * 1e3) / terms_per_s;  // per warp-term per scheduler
-        const double NF = 22.0, NO = 10.5;                                             // per term, from the SASS of this loop
+        const double NF = 22.0, NO = 10.7;                                             // per term, from the SASS of this loop
         printf("%-8s walker constants: %.3e terms/s  = %.1f cycles per term per scheduler; %.0f FP64 at the measured %.2f = %.1f -> "
                "%.3f of the DFMA peak; the other %.1f cycles = %.2f per non-FP64 instruction (%.1f per term)\n",
                uniform ? "uniform" : "distinct", terms_per_s, cyc_per_term, NF, cyc_per_dfma, NF * cyc_per_dfma,
