@@ -1,4 +1,4 @@
-"""Near-minimax polynomial coefficients for the trimmed FP64 routines of lf_math.cuh (math v4).
+"""Near-minimax polynomial coefficients for the trimmed FP64 routines of lf_math.cuh (math v4 - v6).
 Remez exchange in 40-digit arithmetic (mpmath) on the scaled variable u = x / h; prints the coefficients and the
 achieved maximum absolute error.    python tools/math/fit_coeffs.py"""
 import mpmath as mp
@@ -60,13 +60,22 @@ def remez_ab(f, deg, a, b, iters=14, ngrid=4001):
 
 
 if __name__ == '__main__':
-    # decay factor of the free-completeness loop (EXP2B_*): the remainder after the masked-index look-up lies in [-2^-12, 15 2^-12)
-    c, e = remez_ab(lambda x: mp.power(2, x), 3, -mp.mpf(2) ** -12, 15 * mp.mpf(2) ** -12)
-    print("2^x degree 3 on [-2^-12, 15 * 2^-12]: max abs err %s" % mp.nstr(e, 3))
-    print("    " + ", ".join(mp.nstr(v, 20) for v in c))
     h = mp.mpf(2) ** -9
     for name, f in (("log1p(x)", mp.log1p), ("2^x", lambda x: mp.power(2, x))):
         for deg in (3, 4):
             c, e = remez(f, list(range(0, deg + 1)), h)
             print("%s degree %d on |x| <= 2^-9: max abs err %s" % (name, deg, mp.nstr(e, 3)))
             print("    " + ", ".join(mp.nstr(v, 20) for v in c))
+            if name == "2^x" and deg == 3:
+                # math v6: C0 (1 + c1 x + c2 x^2 + c3 x^3) -- C0 goes into the table entries (EXP_TAB_SCALE), the last Horner
+                # step adds the immediate 1.0, c3 is rounded to its high word
+                print("    normalised by the constant term: " + ", ".join(mp.nstr(v / c[0], 22) for v in c))
+    # math v6: log1p with the linear coefficient FIXED at 1 (the last-but-one Horner step adds the immediate 1.0)
+    c, e = remez(lambda x: mp.log1p(x) - x, [0, 2, 3], h)
+    print("log1p(x) - x ~ c0 + c2 x^2 + c3 x^3 on |x| <= 2^-9: max abs err %s" % mp.nstr(e, 3))
+    print("    " + ", ".join(mp.nstr(v, 22) for v in c))
+    # (git history: the decay factor with a masked-index look-up, remainder in [-2^-12, 15 2^-12) -- LF_EXP_MASKED, measured
+    #  and dropped in round 2)
+    c, e = remez_ab(lambda x: mp.power(2, x), 3, -mp.mpf(2) ** -12, 15 * mp.mpf(2) ** -12)
+    print("2^x degree 3 on [-2^-12, 15 * 2^-12]: max abs err %s" % mp.nstr(e, 3))
+    print("    " + ", ".join(mp.nstr(v, 20) for v in c))
