@@ -372,13 +372,20 @@ class Bench:
         ms_e2e, result_e2e = self.time_e2e(like, thetas, steps)
         assert np.array_equal(result_e2e, result_dev, equal_nan=True)
         parity = self.check_parity(like, inp, kind, thetas, result_dev)
-        ms_dev, ms_e2e = self.max_over_ranks([ms_dev, ms_e2e])
+        # N > 1: a second, identically bracketed region of K steps.  `value` stays the FIRST region (the contract's number);
+        # the repeat is reported beside it so that a one-off stall on a shared box (seen once: +7 % on one 4-GPU run, with the
+        # host-API loop that followed at the expected rate) is visible as such
+        ms_rep = self.time_device(like, d_th, d_out, steps, warmup)[0] if self.world > 1 else ms_dev
+        ms_dev, ms_e2e, ms_rep = self.max_over_ranks([ms_dev, ms_e2e, ms_rep])
         terms = float(n_total) * W
         rec = {"workload": name, "sources_total": int(n_total), "sources_per_gpu": len(inp['lum']), "walkers": W, "steps": steps,
                "value": terms * steps / (ms_dev * 1e-3), "unit": "terms/s", "ms_per_step": ms_dev / steps,
                "e2e": {"value": terms * steps / (ms_e2e * 1e-3), "unit": "terms/s", "ms_per_step": ms_e2e / steps,
                        "h2d_bytes_per_step": W * like.ndim * 8, "d2h_bytes_per_step": W * 8},
                "setup_s": t_setup, "parity": parity}
+        if self.world > 1:
+            rec["repeat_region"] = {"ms_per_step": ms_rep / steps, "value": terms * steps / (ms_rep * 1e-3),
+                                    "note": "second region of the same K steps, informational; `value` is the first region"}
         if keep:
             return rec, like, inp, thetas, d_th, d_out, result_dev, (t_begin, t_end)
         like.close()
@@ -715,6 +722,8 @@ def main():
             "roofline": roof,
         }
         line.update(extras)
+        if "repeat_region" in head:
+            line["repeat_region"] = head["repeat_region"]
         if veff and "weights_gbs" in veff:
             veff["hbm_peak_gbs"] = hbm_peak
             veff["weights_frac_of_hbm"] = veff["weights_gbs"] / hbm_peak
