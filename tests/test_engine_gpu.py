@@ -386,6 +386,34 @@ def test_config3_size_z_model_against_oracle():
     e32.close()
 
 
+@pytest.mark.gpu
+def test_z_model_walker_with_a_far_away_middle_pivot_takes_the_literal_kernels():
+    """The z-evolving source loop evaluates 2^(log2(10) (lum - L*(z)) - log2(10) (42 - L*(z2))) without clamping the exponent
+    field; k_prologue keeps walkers whose middle-pivot value L*(z2) lies more than 200 dex from 42 out of the fast class.  With
+    the middle pivot far outside the catalogue's redshift range L*(z) is perfectly ordinary over the sources while L*(z2) is
+    not: such a walker must come out right (literal kernels), and its neighbours must stay fast."""
+    cat = synth.make_catalogue(20000, seed=91, evolve=(0.3, -0.2))
+    inp = dict(synth.direct_inputs(cat, nknots=1024, size_ln=101, tabulated=True))
+    inp['z2'] = 60.0                                     # pivots: z1, z3 at the ends of the survey, z2 far away
+    inp['Lstar_lims'] = [-500.0, 900.0]
+    th = synth.draw_thetas(inp, 'z', 40, seed=3, mode='near', scale=0.01)
+    z1, z3 = float(inp['z1']), float(inp['z3'])
+    # L*(z) linear from 42.4 to 42.6 across the survey, extrapolated to z2 and then bent so that L*(z2) is 450 / 800
+    for row, L2 in ((5, 450.0), (17, 800.0)):
+        th[row, 0], th[row, 2], th[row, 1] = 42.4, 42.6, L2
+    for row in range(40):
+        if row not in (5, 17):                           # the others: the straight line itself (an ordinary L*(z2))
+            th[row, 1] = th[row, 0] + (th[row, 2] - th[row, 0]) * (60.0 - z1) / (z3 - z1)
+    ref = lf_oracle.lnprob_batch(inp, 'z', th)
+    assert np.isfinite(ref[[5, 17]]).all()
+    eng = _engine(inp, 'z')
+    got = eng.lnprob(th)
+    info = eng.last_call_info()
+    _assert_parity(got, ref)
+    assert info['literal'] >= 2 and info['fast'] >= 30, info
+    eng.close()
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # compressed catalogue (opt-in): weighted pseudo-sources instead of the walker x source loop
 # ---------------------------------------------------------------------------------------------------------------
