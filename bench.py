@@ -653,6 +653,9 @@ def main():
             extras["config4"] = B.run_sharded_case("BASELINE.json configs[4]: 1e8 sources in total x 2048 walkers, source-sharded",
                                                    100000000, 2048, 'free', max(3, min(args.steps, 5)), args.warmup, seed=3000, mode=mode)
         extras["walker_sharded"] = B.run_walker_sharded(100000, 4096, 'free', sub_steps, args.warmup, mode)
+        # BASELINE.json configs[2]: the redshift-evolving model at its own size (k_main<false, Z>), source-sharded like the headline
+        extras["config2_z"] = B.run_sharded_case("BASELINE.json configs[2]: redshift-evolving model, 1e6 sources in total x 512 walkers, "
+                                                 "source-sharded", 1000000, 512, 'z', sub_steps, args.warmup, seed=5000, mode=mode)
 
     if rank == 0:
         value, e2e = head["value"], head["e2e"]
@@ -677,6 +680,9 @@ def main():
                             "rate measured live on this GPU (lf_fp64_peak, best of 3: %.3e DFMA/s) x 2 FLOP; the per-walker quadrature (K S^2 points) is "
                             "extra work not counted as terms" % (FP64_INSTR_PER_TERM_BY_KIND[args.kind], peak_dfma)}
         roof["frac"] = roof["achieved"] / roof["peak"]
+        if "config2_z" in extras and not f32:
+            extras["config2_z"]["frac_of_dfma_peak"] = extras["config2_z"]["value"] / world * FP64_INSTR_PER_TERM_BY_KIND['z'] / peak_dfma
+            extras["config2_z"]["frac_note"] = "terms/s/GPU x 9 FP64-pipe instr/term over the DFMA rate measured in this run; the S x S quadrature is not counted"
         # DRAM bytes of one k_main launch from the committed ncu --set full capture of this workload (profiles/), if any
         roof["traffic"] = None
         try:

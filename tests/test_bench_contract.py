@@ -75,4 +75,6 @@ def test_committed_round2_lines_carry_strong_scaling_and_parity():
     one = json.loads(open(os.path.join(ROOT, 'profiles', 'r02_bench_1gpu_final.json')).read().strip().splitlines()[-1])
     eight = json.loads(open(os.path.join(ROOT, 'profiles', 'r02_bench_8gpu.json')).read().strip().splitlines()[-1])
     assert eight['value'] > 1.0e12                               # the north_star target on its own configuration
+    z = one['config2_z']                                         # BASELINE configs[2] rides in the default line
+    assert z['sources_total'] == 1000000 and z['walkers'] == 512 and z['parity']['ok'] and 0.5 < z['frac_of_dfma_peak'] < 1.0
     assert 0.9 < eight['value'] / (8 * one['value']) <= 1.02     # strong-scaling efficiency
