@@ -37,6 +37,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+WARMUP_MIN_S = 0.3      # minimum duration of the untimed warm-up before a device-timed region
 FP64_INSTR_PER_TERM_BY_KIND = {'free': 22, 'z': 9, 'fixed': 0}    # DFMA/DADD/DMUL per (walker, source) term in k_main<false, MODEL>
                                                                     # (tools/sass_loop_mix.py); fixed: sufficient statistics only
 MUFU_PER_TERM_BY_KIND = {'free': 4, 'z': 1, 'fixed': 0}           # FP32 mode: rsqrt, lg2, ex2, rcp / one ex2
@@ -283,8 +284,21 @@ class Bench:
 
     def time_device(self, like, d_th, d_out, steps, warmup):
         t = self.torch
-        for _ in range(max(3, warmup)):
+        # warm-up: the W steps asked for (at least 3), then more of the same until about WARMUP_MIN_S of GPU work has run -- a
+        # region timed right after a few short steps on a GPU that idled during the set-up has measured 3-7 % slow (2 of 10
+        # multi-GPU runs; the regions that followed in the same process were at the expected rate).  The number of extra steps
+        # is agreed between the ranks (every step contains a collective).
+        n0 = max(3, warmup)
+        t0 = time.perf_counter()
+        for _ in range(n0):
             like.lnprob_device(d_th, d_out)
+        t.cuda.synchronize()
+        dt = max(time.perf_counter() - t0, 1e-6)
+        extra = int(min(400, max(0, np.ceil((WARMUP_MIN_S - dt) / (dt / n0)))))
+        extra = int(self.max_over_ranks([extra])[0])
+        for _ in range(extra):
+            like.lnprob_device(d_th, d_out)
+        self.warmup_steps_done = n0 + extra
         self.sync_all()
         ev0, ev1 = t.cuda.Event(enable_timing=True), t.cuda.Event(enable_timing=True)
         t_begin = time.time()
@@ -368,6 +382,7 @@ class Bench:
         d_th = t.from_numpy(thetas).cuda()
         d_out = t.empty(W, dtype=t.float64, device='cuda')
         ms_dev, t_begin, t_end = self.time_device(like, d_th, d_out, steps, warmup)
+        warmup_done = self.warmup_steps_done
         result_dev = d_out.cpu().numpy()
         ms_e2e, result_e2e = self.time_e2e(like, thetas, steps)
         assert np.array_equal(result_e2e, result_dev, equal_nan=True)
@@ -382,7 +397,7 @@ class Bench:
                "value": terms * steps / (ms_dev * 1e-3), "unit": "terms/s", "ms_per_step": ms_dev / steps,
                "e2e": {"value": terms * steps / (ms_e2e * 1e-3), "unit": "terms/s", "ms_per_step": ms_e2e / steps,
                        "h2d_bytes_per_step": W * like.ndim * 8, "d2h_bytes_per_step": W * 8},
-               "setup_s": t_setup, "parity": parity}
+               "setup_s": t_setup, "parity": parity, "warmup_steps": warmup_done}
         if self.world > 1:
             rec["repeat_region"] = {"ms_per_step": ms_rep / steps, "value": terms * steps / (ms_rep * 1e-3),
                                     "note": "second region of the same K steps, informational; `value` is the first region"}
@@ -708,7 +723,7 @@ def main():
             parity["ok"] = bool(parity["ok"] and sub["parity"]["ok"])
         line = {
             "metric": metric_name(args.kind, args.precision), "value": value, "unit": "terms/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": head["ms_per_step"], "higher_is_better": True,
+            "warmup": max(3, args.warmup), "warmup_steps_run": head["warmup_steps"], "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": args.scaling, "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": workload_name(args), "kind": args.kind, "sources_total": n_total, "sources_per_gpu": n, "walkers": W,
                        "ndim": like.ndim, "nfields": eng.nfields, "size_ln": eng.size_ln,
