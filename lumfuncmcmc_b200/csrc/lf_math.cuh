@@ -178,7 +178,7 @@ __device__ __forceinline__ void exp2_parts(double a, double b, const double* s_e
     } else {
         T = s_exp[(k & (EXP_TAB_N - 1)) * EXP_TAB_REP + rep];
     }
-    Ts = __hiloint2double(__double2hiint(T) + (K << 20), __double2loint(T));
+    Ts = __hiloint2double(__double2hiint(T) + (int)((unsigned)K << 20), __double2loint(T));
     p = fma(r, EXP2N_C3_HI, EXP2N_C2);
     p = fma(r, p, EXP2N_C1);
     p = fma(r, p, 1.0);                           // the table entry carries EXP_TAB_SCALE
@@ -231,7 +231,7 @@ __device__ __forceinline__ void exp2r_parts(double a, double b, const double* s_
     if (CLAMP) k = max(k, -1022 * EXP_TAB_N);
     const unsigned off = __byte_perm((unsigned)k, lane8, 0x7704);           // (j << 8) | lane8
     const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_rep) + off);
-    Ts = __hiloint2double(__double2hiint(T) + (k << 12), __double2loint(T));
+    Ts = __hiloint2double(__double2hiint(T) + (int)((unsigned)k << 12), __double2loint(T));
     p = fma(r, EXP2N_C3_HI, EXP2N_C2);
     p = fma(r, p, EXP2N_C1);
     p = fma(r, p, 1.0);                           // the table entry carries EXP_TAB_SCALE
@@ -321,7 +321,7 @@ __device__ __forceinline__ void fleming_terms_v(const double (&ux)[NT], const do
 #else
         double T = s_exp[(k[i] & (EXP_TAB_N - 1)) * EXP_TAB_REP + repe];
         int K = max(k[i] >> EXP_TAB_BITS, -1000);
-        Ts[i] = __hiloint2double(__double2hiint(T) + (K << 20), __double2loint(T));
+        Ts[i] = __hiloint2double(__double2hiint(T) + (int)((unsigned)K << 20), __double2loint(T));
 #endif
     }
 #pragma unroll
@@ -444,7 +444,7 @@ __device__ __forceinline__ double exp_stream(double x, const double* s_exp) {
     double r = fma(kf, KS[7], x);
     r = fma(kf, KS[8], r);                                                  // |r| <= ln2/512
     const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (((unsigned)k << 3) & ((EXP_TAB_N - 1) << 3)));
-    const double Ts = __hiloint2double(__double2hiint(T) + (k << (20 - EXP_TAB_BITS)), __double2loint(T));   // pre-compensated table
+    const double Ts = __hiloint2double(__double2hiint(T) + (int)((unsigned)k << (20 - EXP_TAB_BITS)), __double2loint(T));   // pre-compensated table
     double p = fma(r, KS[9], KS[10]);
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
@@ -465,7 +465,7 @@ __device__ __forceinline__ double exp_stream_signed(double x, const double* s_ex
     double r = NEG ? fma(kf, KS[7], -x) : fma(kf, KS[7], x);
     r = fma(kf, KS[8], r);                                                  // |r| <= ln2/512
     const double T = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(s_exp) + (((unsigned)k << 3) & ((EXP_TAB_N - 1) << 3)));
-    const double Ts = __hiloint2double(__double2hiint(T) + (k << (20 - EXP_TAB_BITS)), __double2loint(T));   // pre-compensated table
+    const double Ts = __hiloint2double(__double2hiint(T) + (int)((unsigned)k << (20 - EXP_TAB_BITS)), __double2loint(T));   // pre-compensated table
     double p = fma(r, KS[9], KS[10]);
     p = fma(r, p, 0.5);
     p = fma(r, p, 1.0);
