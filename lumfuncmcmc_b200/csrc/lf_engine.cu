@@ -1437,8 +1437,7 @@ int launch_pipeline(lf_ctx* c, const double* d_thetas, long long W, double* d_ou
     const unsigned bl = (unsigned)std::min<long long>(need_lit, (long long)c->sm_count * c->occ_lit);
     {
         // fast kernel: launched programmatically dependent on the kernel before it (prologue, or k_zcolumns for the Z model)
-        cudaLaunchConfig_t lc;
-        memset(&lc, 0, sizeof(lc));
+        cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(bf); lc.blockDim = dim3(32 * main_warps(c->cfg.model)); lc.dynamicSmemBytes = main_smem_bytes(c->cfg.model);
         lc.stream = st;
         cudaLaunchAttribute attr[1];

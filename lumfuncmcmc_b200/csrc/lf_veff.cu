@@ -933,8 +933,7 @@ static int veff_resident_pass(lf_ctx* c, const double* d_vol, const unsigned cha
         else k_veff_res<false, false><<<blocks, 32 * VR_WARPS, smem, c->stream>>>(a);
     }
     {
-        cudaLaunchConfig_t lc;
-        memset(&lc, 0, sizeof(lc));
+        cudaLaunchConfig_t lc = {};
         lc.gridDim = dim3(nbins); lc.blockDim = dim3(VRS_THREADS); lc.dynamicSmemBytes = 0; lc.stream = c->stream;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
